@@ -1,0 +1,218 @@
+"""TEST INFRASTRUCTURE ONLY — generates ``tests/golden/*.npz`` by running the UNMODIFIED reference.
+
+Run in the build container (needs /root/reference):  ``python -m oracle.make_golden``
+
+The reference's ``model.py`` / ``utilities/solver.py`` are imported verbatim from /root/reference behind
+``oracle/ref_shim.py`` and driven on seeded synthetic meshes (psi_gnn_b200/synthetic.py) with (a) the shipped
+checkpoints and (b) random-init weights.  Each fixture stores the inputs (batch tensors, weights, probe vectors)
+and the reference's outputs, so the tests need neither the reference nor the mesh generator:
+
+  f1, f2            two applications of Function.forward from the encoder output
+  vjp_*             autograd.grad(f(H), H, y) at H = f2 for a stored y
+  fw_*              broyden forward solve (result, lowest, nstep, rel/abs trace, first iterates)
+  u, residual       decoder(result), residual_loss(u, batch)
+  train_*           ModelDEQDSS.forward + loss.backward(): losses, parameter gradients, backward-solve statistics
+  forced_*          teacher-forced quasi-Newton states captured from the oracle's bit-identical Broyden loop,
+                    with the rank-one update recomputed in fp64 from those fp32 inputs as the truth
+"""
+from __future__ import annotations
+
+import os
+import sys
+import tempfile
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import psignn_oracle as O          # noqa: E402
+from oracle import ref_shim                     # noqa: E402
+from psi_gnn_b200 import synthetic              # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+BATCH_FIELDS = ["x", "edge_index", "edge_attr", "a_ij", "y", "sol", "prb_data", "tags", "unit_normal_vector", "ptr", "edge_ptr"]
+
+
+def build_model(family: str, weights: str, logdir: str):
+    model_mod, solver_mod, _ = ref_shim.load_reference(family)
+    ck = ref_shim.load_checkpoint(ref_shim.CHECKPOINTS[family], family)
+    cfg = dict(ck["hyperparameters"])
+    cfg["solver"] = solver_mod.broyden
+    cfg["path_logs"] = logdir
+    if weights == "ckpt":
+        model = model_mod.ModelDEQDSS(cfg)
+        model.load_state_dict(ck["state_dict"])
+    else:
+        torch.manual_seed(int(weights.replace("seed", "")))
+        model = model_mod.ModelDEQDSS(cfg)
+    return model, solver_mod, cfg
+
+
+def forced_states(P, f, h0, threshold, eps, steps):
+    """Re-run the oracle's Broyden loop (bit-identical to the reference's) and capture the state entering the
+    rank-one update of the requested steps; truth = the reference formulas evaluated in fp64 on those fp32 inputs."""
+    x = h0[None]
+    g = lambda y: f(y) - y
+    gx = g(x[0])[None]
+    n_rows, d = h0.shape
+    Us = torch.zeros(1, n_rows, d, threshold)
+    VTs = torch.zeros(1, threshold, n_rows, d)
+    step_dir = gx
+    out = {}
+    n = 0
+    while n < threshold:
+        x_new = x + step_dir
+        g_new = g(x_new[0])[None]
+        dx, dg = x_new - x, g_new - gx
+        x_old, g_old = x, gx
+        x, gx = x_new, g_new
+        n += 1
+        r = torch.norm(gx).item() / (torch.norm(gx + x).item() + 1e-9)
+        if r < eps:
+            break
+        pU, pV = Us[:, :, :, :n - 1], VTs[:, :n - 1]
+        vT = O._lowrank_apply_t(pU, pV, dx)
+        u = (dx - O._lowrank_apply(pU, pV, dg)) / torch.einsum("bij,bij->b", vT, dg)[:, None, None]
+        vT[vT != vT] = 0
+        u[u != u] = 0
+        VTs[:, n - 1] = vT
+        Us[:, :, :, n - 1] = u
+        step_dir = -O._lowrank_apply(Us[:, :, :, :n], VTs[:, :n], gx)
+        if n in steps:
+            U64 = Us[0, :, :, :n - 1].permute(2, 0, 1).double()           # [n-1, N, d]
+            V64 = VTs[0, :n - 1].double()
+            dx64, dg64, g64 = dx[0].double(), dg[0].double(), gx[0].double()
+            a = (U64 * dx64).sum((1, 2))
+            v64 = -dx64 + (a[:, None, None] * V64).sum(0)
+            c = (V64 * dg64).sum((1, 2))
+            w64 = -dg64 + (c[:, None, None] * U64).sum(0)
+            u64 = (dx64 - w64) / (v64 * dg64).sum()
+            e = (V64 * g64).sum((1, 2))
+            upd64 = -(-g64 + (e[:, None, None] * U64).sum(0) + u64 * (v64 * g64).sum())
+            out[n] = dict(x=x_old[0], gx=g_old[0], xnew=x[0], gnew=gx[0],
+                          U=Us[0, :, :, :n - 1].permute(2, 0, 1).contiguous(), V=VTs[0, :n - 1].contiguous(),
+                          u32=u[0], v32=vT[0], upd32=step_dir[0], u64=u64, v64=v64, upd64=upd64)
+        if n >= max(steps):
+            break
+    return out
+
+
+def make_fixture(family: str, weights: str, n_graphs: int, seed0: int, h: float, name: str, train: bool = True,
+                 forced=(2, 5)):
+    mixed = family.startswith("mixed")
+    batch = synthetic.make_batch(n_graphs, seed0=seed0, h=h, mixed=mixed)
+    with tempfile.TemporaryDirectory() as logdir:
+        model, solver_mod, cfg = build_model(family, weights, logdir)
+        torch.set_flush_denormal(True)
+        P = {k: v.detach().clone() for k, v in model.state_dict().items()}
+        fx = {}
+        for k in BATCH_FIELDS:
+            v = getattr(batch, k, None)
+            if v is not None:
+                fx["batch." + k] = v.numpy()
+        fx["batch.num_nodes"] = np.int64(batch.num_nodes)
+        for k, v in P.items():
+            fx["param." + k] = v.numpy()
+        for k in ("fw_tol", "fw_thres", "bw_tol", "bw_thres"):
+            fx["cfg." + k] = np.float64(cfg[k])
+        f = model.deqdss.f
+        with torch.no_grad():
+            h0 = model.autoencoder.encoder(batch.x)
+            f1 = f(h0.clone(), h0, batch)
+            f2 = f(f1.clone(), h0, batch)
+        fx.update(h0=h0.numpy(), f1=f1.numpy(), f2=f2.numpy())
+        # VJP at H = f2
+        gen = torch.Generator().manual_seed(1234 + seed0)
+        y = torch.randn(h0.shape, generator=gen)
+        H = f2.clone().requires_grad_()
+        out = f(H, h0, batch)
+        vjp = torch.autograd.grad(out, H, y)[0]
+        fx.update(vjp_y=y.numpy(), vjp_out=vjp.numpy())
+        # forward solve
+        with torch.no_grad():
+            fw = solver_mod.broyden(lambda Hh: f(Hh, h0, batch), h0, threshold=cfg["fw_thres"], eps=cfg["fw_tol"])
+            u = model.autoencoder.decoder(fw["result"])
+            res = model.residual_loss(u, batch)
+            res_x = model.residual_loss(batch.x, batch)
+        fx.update(fw_result=fw["result"].numpy(), fw_lowest=np.float64(fw["lowest"]), fw_nstep=np.int64(fw["nstep"]),
+                  fw_rel_trace=np.asarray(fw["rel_trace"], np.float64), fw_abs_trace=np.asarray(fw["abs_trace"], np.float64),
+                  fw_prot_break=np.int64(bool(fw["prot_break"])),
+                  fw_x1=fw["xest_trace"][1].numpy(), fw_x2=fw["xest_trace"][2].numpy(), fw_x3=fw["xest_trace"][3].numpy(),
+                  fw_steps_run=np.int64(len(fw["xest_trace"]) - 1),
+                  u=u.numpy(), residual=np.float64(res.item()), residual_x=np.float64(res_x.item()))
+        # the oracle must reproduce the reference bit for bit on this fixture (checked again in tests)
+        of = O.f_mixed if mixed else O.f_dirichlet
+        with torch.no_grad():
+            ofw = O.broyden(lambda Hh: of(P, Hh, h0, batch), h0, threshold=int(cfg["fw_thres"]), eps=cfg["fw_tol"])
+        assert ofw["nstep"] == fw["nstep"] and torch.equal(ofw["result"], fw["result"]), "oracle != reference"
+        # teacher-forced quasi-Newton states
+        steps = [s for s in forced if s < len(fw["xest_trace"]) - 2]
+        with torch.no_grad():
+            fs = {} if not steps else forced_states(P, lambda Hh: of(P, Hh, h0, batch), h0, int(cfg["fw_thres"]), cfg["fw_tol"], steps)
+        fx["forced_steps"] = np.asarray(sorted(fs), np.int64)
+        for n, dct in fs.items():
+            for k, v in dct.items():
+                fx["forced%d_%s" % (n, k)] = v.numpy()
+        # Picard and Anderson forward solves (reference solver.py:215-341)
+        with torch.no_grad():
+            pic = solver_mod.forward_iteration(lambda Hh: f(Hh, h0, batch), h0, eps=1e-4, threshold=60)
+            fx.update(picard_result=pic["result"].numpy(), picard_nstep=np.int64(pic["nstep"]),
+                      picard_rel_trace=np.asarray([float(t) for t in pic["rel_trace"]], np.float64))
+            andr = solver_mod.anderson(lambda Hh: f(Hh, h0, batch), h0, m=2, threshold=60, eps=1e-4)
+            fx.update(anderson_result=andr["result"].numpy(), anderson_nstep=np.int64(andr["nstep"]),
+                      anderson_lowest=np.float64(andr["lowest"]), anderson_rel_trace=np.asarray(andr["rel_trace"], np.float64))
+        if train:
+            # training step: ModelDEQDSS.forward + backward with the launch-script loss (training_class.py:156-160)
+            rec = {}
+            orig = solver_mod.broyden
+
+            def recording_solver(fn, x0, threshold, eps):
+                out_ = orig(fn, x0, threshold=threshold, eps=eps)
+                rec.setdefault("calls", []).append(out_)
+                return out_
+
+            model.config_deq["solver"] = recording_solver
+            model.deqdss.config_deq["solver"] = recording_solver
+            torch.cuda.synchronize = lambda *a, **k: None          # reference model.py:213 on a CUDA-less build
+            model.train()
+            model.zero_grad()
+            torch.manual_seed(4321)
+            v = torch.randn(h0.shape)                                # the probe jac_loss_estimate will draw (model.py:431)
+            torch.manual_seed(4321)
+            u_tr, loss_dic = model(batch)
+            loss = loss_dic["residual_loss"].mean() + 1.0 * loss_dic["jacobian_loss"].mean() + \
+                loss_dic["encoder_loss"].mean() + loss_dic["autoencoder_loss"].mean()
+            loss.backward()
+            fx["train_v"] = v.numpy()
+            fx["train_u"] = u_tr.detach().numpy()
+            fx["train_loss"] = np.float64(loss.item())
+            for k, t in loss_dic.items():
+                fx["train_loss." + k] = np.float64(t.item())
+            for k, p in model.named_parameters():
+                fx["train_grad." + k] = (p.grad if p.grad is not None else torch.zeros_like(p)).numpy()
+            bw = rec["calls"][1]
+            fx.update(train_fw_nstep=np.int64(rec["calls"][0]["nstep"]), train_bw_nstep=np.int64(bw["nstep"]),
+                      train_bw_lowest=np.float64(bw["lowest"]), train_bw_result=bw["result"].numpy(),
+                      train_bw_rel_trace=np.asarray(bw["rel_trace"], np.float64),
+                      train_bw_steps_run=np.int64(len(bw["xest_trace"]) - 1))
+    os.makedirs(OUT, exist_ok=True)
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **fx)
+    print("%-28s N=%d nnz=%d fw_nstep=%d lowest=%.3e  -> %s (%.0f kB)" % (
+        name, batch.num_nodes, batch.edge_index.shape[1], fw["nstep"], fw["lowest"], os.path.relpath(path, ROOT),
+        os.path.getsize(path) / 1024))
+
+
+def main():
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    make_fixture("dirichlet/psignn", "ckpt", 3, 0, 0.075, "dirichlet_ckpt", forced=())
+    make_fixture("dirichlet/psignn", "ckpt", 1, 20, 0.11, "dirichlet_ckpt_small", train=False, forced=(2, 5, 20, 40))
+    make_fixture("dirichlet/psignn", "seed0", 2, 10, 0.11, "dirichlet_seed0")
+    make_fixture("mixed/psignn", "ckpt", 3, 0, 0.075, "mixed_ckpt", forced=())
+    make_fixture("mixed/psignn", "seed0", 2, 10, 0.11, "mixed_seed0")
+
+
+if __name__ == "__main__":
+    main()

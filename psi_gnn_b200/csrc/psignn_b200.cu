@@ -1,0 +1,743 @@
+// psignn_b200.cu — C ABI of the B200-native PSI-GNN implicit message-passing solve (include/psignn_b200.h).
+//
+// Single translation unit: the kernels live in the .cuh files next to this one, this file holds the
+// host side — handle lifetime, launch sequencing of the fused iteration, the device-resident solver loops.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC (psi_gnn_b200/build.py).
+#include "../../include/psignn_b200.h"
+#include "common.cuh"
+#include "weights.cuh"
+#include "graph.cuh"
+#include "layer.cuh"
+#include "vjp.cuh"
+#include "broyden.cuh"
+#include "anderson.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <limits>
+#include <vector>
+
+thread_local std::string g_psi_err;
+
+static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+static inline unsigned node_grid(int64_t N) { return (unsigned)((N + PSI_NODE_BLOCK - 1) / PSI_NODE_BLOCK); }
+
+extern "C" int psi_version(void) { return 100; }
+extern "C" const char* psi_last_error(void) { return g_psi_err.c_str(); }
+extern "C" int psi_weights_floats(void) { return (int)(sizeof(LayerWeights) / sizeof(float)); }
+
+extern "C" int psi_weights_upload(const float* dev_blob, int n_floats, void* stream) {
+    if (dev_blob == nullptr) PSI_FAIL("psi_weights_upload: null blob");
+    if (n_floats != psi_weights_floats()) PSI_FAIL("psi_weights_upload: blob has the wrong number of floats");
+    PSI_CK(cudaMemcpyToSymbolAsync(cW, dev_blob, sizeof(LayerWeights), 0, cudaMemcpyDeviceToDevice, as_stream(stream)));
+    return 0;
+}
+
+// ================================================================================================
+// graph
+// ================================================================================================
+static void graph_free(psi_graph* g) {
+    void* ps[] = {g->p_recs_T, g->p_recs_F, g->p_recs_Ar, g->p_recs_Ac, g->p_off_T, g->p_off_F, g->p_off_Ar, g->p_off_Ac,
+                  g->p_xm_T, g->p_xm_F, g->p_tag, g->p_prb, g->p_nrm, g->p_vjp, g->p_scratch};
+    for (void* p : ps)
+        if (p) cudaFree(p);
+    delete g;
+}
+
+extern "C" int psi_graph_create(psi_graph_t** out, int64_t num_nodes, int64_t nnz, const int64_t* dev_edge_index,
+                                const float* dev_edge_attr, int attr_dim, const float* dev_a_ij, const float* dev_tags,
+                                int tag_dim, const float* dev_prb, int prb_dim, const float* dev_normals, void* stream) {
+    if (out == nullptr) PSI_FAIL("psi_graph_create: null out");
+    *out = nullptr;
+    if (num_nodes < 0 || nnz < 0) PSI_FAIL("psi_graph_create: negative size");
+    if (num_nodes >= (1ll << 31) - 64 || nnz >= (1ll << 31) - 64) PSI_FAIL("psi_graph_create: graph exceeds int32 indexing");
+    if (attr_dim < 1 || attr_dim > 3) PSI_FAIL("psi_graph_create: attr_dim must be 1..3");
+    if (prb_dim < 0 || prb_dim > 3) PSI_FAIL("psi_graph_create: prb_dim must be 0..3");
+    if (dev_tags != nullptr && tag_dim != 1 && tag_dim != 3) PSI_FAIL("psi_graph_create: tag_dim must be 1 or 3");
+    if (nnz > 0 && (dev_edge_index == nullptr || dev_edge_attr == nullptr)) PSI_FAIL("psi_graph_create: null edge arrays");
+    if (num_nodes > 0 && prb_dim > 0 && dev_prb == nullptr) PSI_FAIL("psi_graph_create: null prb");
+    cudaStream_t st = as_stream(stream);
+    psi_graph* g = new psi_graph();
+    g->N = num_nodes; g->nnz = nnz; g->attr_dim = attr_dim; g->prb_dim = prb_dim; g->tag_dim = tag_dim;
+    const int64_t N1 = num_nodes > 0 ? num_nodes : 1;
+    SellBuild bT, bF, bAr, bAc;
+    if (build_sell(num_nodes, nnz, dev_edge_index, dev_edge_attr, attr_dim, nullptr, true, true, st, &bT)) { graph_free(g); return -1; }
+    g->p_recs_T = bT.recs; g->p_off_T = bT.off; g->slots_T = bT.slots;
+    if (build_sell(num_nodes, nnz, dev_edge_index, dev_edge_attr, attr_dim, nullptr, true, false, st, &bF)) { graph_free(g); return -1; }
+    g->p_recs_F = bF.recs; g->p_off_F = bF.off; g->slots_F = bF.slots;
+    g->E = bT.kept;
+    if (dev_a_ij != nullptr) {
+        if (build_sell(num_nodes, nnz, dev_edge_index, nullptr, 0, dev_a_ij, false, false, st, &bAr)) { graph_free(g); return -1; }
+        g->p_recs_Ar = bAr.recs; g->p_off_Ar = bAr.off; g->slots_Ar = bAr.slots;
+        if (build_sell(num_nodes, nnz, dev_edge_index, nullptr, 0, dev_a_ij, false, true, st, &bAc)) { graph_free(g); return -1; }
+        g->p_recs_Ac = bAc.recs; g->p_off_Ac = bAc.off; g->slots_Ac = bAc.slots;
+    }
+    // node data
+    unsigned long long* counts = nullptr;
+    if (cudaMalloc(&g->p_tag, N1) != cudaSuccess || cudaMalloc(&counts, 2 * sizeof(unsigned long long)) != cudaSuccess) {
+        graph_free(g); PSI_FAIL("psi_graph_create: out of device memory");
+    }
+    cudaMemsetAsync(counts, 0, 2 * sizeof(unsigned long long), st);
+    if (num_nodes > 0) {
+        k_graph_tags<<<(unsigned)((num_nodes + 255) / 256), 256, 0, st>>>((int)num_nodes, dev_tags, tag_dim, (uint8_t*)g->p_tag, counts);
+    }
+    if (prb_dim > 0) {
+        if (cudaMalloc(&g->p_prb, N1 * prb_dim * sizeof(float)) != cudaSuccess) { graph_free(g); PSI_FAIL("psi_graph_create: out of device memory"); }
+        if (num_nodes > 0) cudaMemcpyAsync(g->p_prb, dev_prb, num_nodes * prb_dim * sizeof(float), cudaMemcpyDeviceToDevice, st);
+    }
+    if (dev_normals != nullptr) {
+        if (cudaMalloc(&g->p_nrm, N1 * 2 * sizeof(float)) != cudaSuccess) { graph_free(g); PSI_FAIL("psi_graph_create: out of device memory"); }
+        if (num_nodes > 0) cudaMemcpyAsync(g->p_nrm, dev_normals, num_nodes * 2 * sizeof(float), cudaMemcpyDeviceToDevice, st);
+    }
+    g->scratch_floats = 2 * (int64_t)node_grid(N1) + 8;
+    if (cudaMalloc(&g->p_scratch, g->scratch_floats * sizeof(float)) != cudaSuccess) { graph_free(g); PSI_FAIL("psi_graph_create: out of device memory"); }
+    unsigned long long hc[2] = {0, 0};
+    cudaMemcpyAsync(hc, counts, sizeof(hc), cudaMemcpyDeviceToHost, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    cudaFree(counts);
+    if (e != cudaSuccess || (e = cudaGetLastError()) != cudaSuccess) {
+        graph_free(g);
+        PSI_FAIL(std::string("psi_graph_create: ") + cudaGetErrorString(e));
+    }
+    g->n_dir = (int64_t)hc[0]; g->n_neu = (int64_t)hc[1];
+    GraphDev& D = g->dev;
+    D.N = (int)num_nodes;
+    D.num_slices = (int)((num_nodes + 31) / 32);
+    D.prb_dim = prb_dim;
+    D.T = SellDev{(const int4*)g->p_recs_T, nullptr, (const int64_t*)g->p_off_T, nullptr};
+    D.F = SellDev{(const int4*)g->p_recs_F, nullptr, (const int64_t*)g->p_off_F, nullptr};
+    D.Ar = SellDev{nullptr, (const int2*)g->p_recs_Ar, (const int64_t*)g->p_off_Ar, nullptr};
+    D.Ac = SellDev{nullptr, (const int2*)g->p_recs_Ac, (const int64_t*)g->p_off_Ac, nullptr};
+    D.tag = (const uint8_t*)g->p_tag;
+    D.prb = (const float*)g->p_prb;
+    D.nrm = (const float*)g->p_nrm;
+    g->bytes = g->slots_T * 16 + g->slots_F * 16 + g->slots_Ar * 8 + g->slots_Ac * 8 + 4 * (D.num_slices + 1) * 8 + N1 +
+               N1 * prb_dim * 4 + (dev_normals ? N1 * 8 : 0) + g->scratch_floats * 4;
+    *out = g;
+    return 0;
+}
+
+extern "C" int psi_graph_destroy(psi_graph_t* g) {
+    if (g == nullptr) return 0;
+    graph_free(g);
+    return 0;
+}
+
+extern "C" int psi_graph_info(const psi_graph_t* g, int64_t info[8]) {
+    if (g == nullptr || info == nullptr) PSI_FAIL("psi_graph_info: null argument");
+    info[0] = g->N; info[1] = g->E; info[2] = g->nnz; info[3] = g->n_dir; info[4] = g->n_neu;
+    info[5] = g->slots_T; info[6] = g->slots_F; info[7] = g->bytes;
+    return 0;
+}
+
+static int check_kind(const psi_graph* g, int kind) {
+    if (g == nullptr) PSI_FAIL("null graph handle");
+    if (kind < 0 || kind > 3) PSI_FAIL("unknown layer kind");
+    const int want_prb = (kind == PSI_KIND_MIXED || kind == PSI_KIND_DSS) ? 3 : 2;
+    if (g->prb_dim != want_prb) PSI_FAIL("graph second-member width does not match the layer kind");
+    if (kind == PSI_KIND_MIXED && g->p_nrm == nullptr) PSI_FAIL("mixed layer needs unit normals");
+    if (kind == PSI_KIND_DSS && g->attr_dim != 1) PSI_FAIL("DSS layer needs 1 edge attribute");
+    if (kind != PSI_KIND_DSS && g->attr_dim != 3) PSI_FAIL("layer needs 3 edge attributes");
+    return 0;
+}
+
+// ================================================================================================
+// layer / VJP / residual / encoder / decoder
+// ================================================================================================
+template <bool EPI>
+static int launch_layer(const psi_graph* g, int kind, const float* h, const float* h0, float* out, SolverEpi E, cudaStream_t st) {
+    if (g->N == 0) return 0;
+    const unsigned grid = node_grid(g->N);
+    switch (kind) {
+        case PSI_KIND_DIRICHLET: k_layer_forward<KIND_DIRICHLET, EPI><<<grid, PSI_NODE_BLOCK, 0, st>>>(g->dev, h, h0, out, E); break;
+        case PSI_KIND_MIXED:     k_layer_forward<KIND_MIXED, EPI><<<grid, PSI_NODE_BLOCK, 0, st>>>(g->dev, h, h0, out, E); break;
+        case PSI_KIND_DSS:       k_layer_forward<KIND_DSS, EPI><<<grid, PSI_NODE_BLOCK, 0, st>>>(g->dev, h, h0, out, E); break;
+        default:                 k_layer_forward<KIND_DSGPS, EPI><<<grid, PSI_NODE_BLOCK, 0, st>>>(g->dev, h, h0, out, E); break;
+    }
+    PSI_CK_LAUNCH();
+    return 0;
+}
+
+extern "C" int psi_layer_forward(const psi_graph_t* g, int kind, const float* dev_h, const float* dev_h0, float* dev_out, void* stream) {
+    if (check_kind(g, kind)) return -1;
+    if (g->N > 0 && (dev_h == nullptr || dev_out == nullptr)) PSI_FAIL("psi_layer_forward: null pointer");
+    if (g->N > 0 && kind != PSI_KIND_DSS && dev_h0 == nullptr) PSI_FAIL("psi_layer_forward: null h0");
+    if (dev_h == dev_out) PSI_FAIL("psi_layer_forward: in-place application is not supported");
+    return launch_layer<false>(g, kind, dev_h, dev_h0, dev_out, SolverEpi{nullptr, nullptr, nullptr, nullptr}, as_stream(stream));
+}
+
+static int vjp_alloc(psi_graph* g) {
+    if (g->p_vjp != nullptr) return 0;
+    const int64_t N = g->N > 0 ? g->N : 1;
+    const int64_t floats = N * (10 + 1 + 1 + 10 + 30 + 1 + 20 + 10);
+    PSI_CK(cudaMalloc(&g->p_vjp, floats * sizeof(float)));
+    PSI_CK(cudaMalloc(&g->p_xm_T, (g->slots_T > 0 ? g->slots_T : 1) * sizeof(uint32_t)));
+    PSI_CK(cudaMalloc(&g->p_xm_F, (g->slots_F > 0 ? g->slots_F : 1) * sizeof(uint32_t)));
+    float* p = (float*)g->p_vjp;
+    VjpCacheDev& C = g->vjp;
+    C.rhat = p; p += N * 10;
+    C.m = p; p += N * 10;
+    C.cnt = p; p += N * 30;
+    C.Sb = p; p += N * 20;
+    C.Dloc = p; p += N * 10;
+    C.rstd = p; p += N;
+    C.alpha = p; p += N;
+    C.nmask = (uint32_t*)p; p += N;
+    g->dev.T.xmask = (uint32_t*)g->p_xm_T;
+    g->dev.F.xmask = (uint32_t*)g->p_xm_F;
+    g->bytes += floats * 4 + (g->slots_T + g->slots_F) * 4;
+    return 0;
+}
+
+extern "C" int psi_vjp_prepare(psi_graph_t* g, int kind, const float* dev_hstar, const float* dev_h0, void* stream) {
+    (void)dev_h0;   // the Dirichlet rows of f do not depend on h: h0 never enters the Jacobian
+    if (check_kind(g, kind)) return -1;
+    if (kind != PSI_KIND_DIRICHLET && kind != PSI_KIND_MIXED) PSI_FAIL("psi_vjp_prepare: VJP exists for the PSI-GNN layers only");
+    if (g->N > 0 && dev_hstar == nullptr) PSI_FAIL("psi_vjp_prepare: null pointer");
+    if (vjp_alloc(g)) return -1;
+    cudaStream_t st = as_stream(stream);
+    if (g->N > 0) {
+        PSI_CK(cudaMemsetAsync(g->p_xm_T, 0, (g->slots_T > 0 ? g->slots_T : 1) * sizeof(uint32_t), st));
+        PSI_CK(cudaMemsetAsync(g->p_xm_F, 0, (g->slots_F > 0 ? g->slots_F : 1) * sizeof(uint32_t), st));
+        if (kind == PSI_KIND_DIRICHLET) k_vjp_prepare<KIND_DIRICHLET><<<node_grid(g->N), PSI_NODE_BLOCK, 0, st>>>(g->dev, g->vjp, dev_hstar);
+        else k_vjp_prepare<KIND_MIXED><<<node_grid(g->N), PSI_NODE_BLOCK, 0, st>>>(g->dev, g->vjp, dev_hstar);
+        PSI_CK_LAUNCH();
+    }
+    g->vjp_ready = true;
+    g->vjp_kind = kind;
+    return 0;
+}
+
+template <bool EPI>
+static int launch_vjp(psi_graph* g, int kind, const float* y, const float* grad, float* out, SolverEpi E, cudaStream_t st) {
+    if (g->N == 0) return 0;
+    const unsigned grid = node_grid(g->N);
+    if (kind == PSI_KIND_DIRICHLET) {
+        k_vjp_phase_a<KIND_DIRICHLET><<<grid, PSI_NODE_BLOCK, 0, st>>>(g->dev, g->vjp, y, E.done);
+        k_vjp_phase_b<KIND_DIRICHLET, EPI><<<grid, PSI_NODE_BLOCK, 0, st>>>(g->dev, g->vjp, y, grad, out, E);
+    } else {
+        k_vjp_phase_a<KIND_MIXED><<<grid, PSI_NODE_BLOCK, 0, st>>>(g->dev, g->vjp, y, E.done);
+        k_vjp_phase_b<KIND_MIXED, EPI><<<grid, PSI_NODE_BLOCK, 0, st>>>(g->dev, g->vjp, y, grad, out, E);
+    }
+    PSI_CK_LAUNCH();
+    return 0;
+}
+
+extern "C" int psi_vjp_apply(psi_graph_t* g, int kind, const float* dev_y, const float* dev_grad, float* dev_out, void* stream) {
+    if (check_kind(g, kind)) return -1;
+    if (!g->vjp_ready || g->vjp_kind != kind) PSI_FAIL("psi_vjp_apply: call psi_vjp_prepare first");
+    if (g->N > 0 && (dev_y == nullptr || dev_out == nullptr)) PSI_FAIL("psi_vjp_apply: null pointer");
+    return launch_vjp<false>(g, kind, dev_y, dev_grad, dev_out, SolverEpi{nullptr, nullptr, nullptr, nullptr}, as_stream(stream));
+}
+
+extern "C" int psi_residual(const psi_graph_t* g, const float* dev_u, const float* dev_y, float* dev_r, float* dev_mean_sq, void* stream) {
+    if (g == nullptr) PSI_FAIL("psi_residual: null graph");
+    if (g->p_recs_Ar == nullptr) PSI_FAIL("psi_residual: graph was created without a_ij");
+    cudaStream_t st = as_stream(stream);
+    if (g->N == 0) {
+        if (dev_mean_sq) {   // mean over an empty tensor is NaN in torch
+            const float nanv = std::numeric_limits<float>::quiet_NaN();
+            PSI_CK(cudaMemcpyAsync(dev_mean_sq, &nanv, sizeof(float), cudaMemcpyHostToDevice, st));
+            PSI_CK(cudaStreamSynchronize(st));
+        }
+        return 0;
+    }
+    if (dev_u == nullptr || dev_y == nullptr) PSI_FAIL("psi_residual: null pointer");
+    const unsigned grid = node_grid(g->N);
+    k_residual<<<grid, PSI_NODE_BLOCK, 0, st>>>(g->dev, dev_u, dev_y, dev_r, g->p_scratch);
+    PSI_CK_LAUNCH();
+    if (dev_mean_sq != nullptr) {
+        k_reduce_partials<<<1, 256, 0, st>>>((int)grid, g->p_scratch, 1.0f / (float)g->N, dev_mean_sq);
+        PSI_CK_LAUNCH();
+    }
+    return 0;
+}
+
+extern "C" int psi_spmv_t(const psi_graph_t* g, const float* dev_v, float* dev_out, void* stream) {
+    if (g == nullptr) PSI_FAIL("psi_spmv_t: null graph");
+    if (g->p_recs_Ac == nullptr) PSI_FAIL("psi_spmv_t: graph was created without a_ij");
+    if (g->N == 0) return 0;
+    if (dev_v == nullptr || dev_out == nullptr) PSI_FAIL("psi_spmv_t: null pointer");
+    k_spmv_t<<<node_grid(g->N), PSI_NODE_BLOCK, 0, as_stream(stream)>>>(g->dev, dev_v, dev_out);
+    PSI_CK_LAUNCH();
+    return 0;
+}
+
+extern "C" int psi_encode(int64_t num_nodes, const float* dev_x, float* dev_h, void* stream) {
+    if (num_nodes < 0) PSI_FAIL("psi_encode: negative size");
+    if (num_nodes == 0) return 0;
+    if (dev_x == nullptr || dev_h == nullptr) PSI_FAIL("psi_encode: null pointer");
+    k_encode<<<node_grid(num_nodes), PSI_NODE_BLOCK, 0, as_stream(stream)>>>((int)num_nodes, dev_x, dev_h);
+    PSI_CK_LAUNCH();
+    return 0;
+}
+
+extern "C" int psi_decode(int64_t num_nodes, const float* dev_h, float* dev_u, void* stream) {
+    if (num_nodes < 0) PSI_FAIL("psi_decode: negative size");
+    if (num_nodes == 0) return 0;
+    if (dev_h == nullptr || dev_u == nullptr) PSI_FAIL("psi_decode: null pointer");
+    k_decode<<<node_grid(num_nodes), PSI_NODE_BLOCK, 0, as_stream(stream)>>>((int)num_nodes, dev_h, dev_u);
+    PSI_CK_LAUNCH();
+    return 0;
+}
+
+// ================================================================================================
+// solver workspace
+// ================================================================================================
+struct psi_solver {
+    int64_t numel = 0, stride = 0;        // stride = numel rounded up to whole QN_CHUNKs (tail kept at zero)
+    int cap = 0;                          // largest threshold the workspace can hold
+    int num_chunks = 0, axpy_ctas = 0, norm_cap = 0;
+    float *x = nullptr, *g = nullptr, *dg = nullptr, *dx = nullptr, *best = nullptr, *fx = nullptr;
+    float *partial = nullptr, *partial2 = nullptr, *coef = nullptr, *norm_part = nullptr;
+    QnCtrl* ctrl = nullptr;               // device
+    QnCtrl* h_ctrl = nullptr;             // pinned host mirror
+    double *rel_trace = nullptr, *abs_trace = nullptr;
+    QnHistory hist{};
+    int slabs_alloc = 0;
+    int64_t bytes = 0;
+    // Anderson window (allocated on first use)
+    float* and_X = nullptr; float* and_F = nullptr; float* and_small = nullptr; int and_m = 0;
+    // state of the step API
+    int threshold = 0; double eps = 0.0; int n = 0; int launches = 0; int f_evals = 0; bool active = false;
+    float* xtrace = nullptr; int norm_blocks = 0;
+};
+
+static int solver_alloc(psi_solver* s, void** p, size_t bytes) {
+    PSI_CK(cudaMalloc(p, bytes));
+    s->bytes += (int64_t)bytes;
+    return 0;
+}
+
+extern "C" int psi_solver_create(psi_solver_t** out, int64_t numel, int max_threshold) {
+    if (out == nullptr) PSI_FAIL("psi_solver_create: null out");
+    *out = nullptr;
+    if (numel < 0 || max_threshold < 1) PSI_FAIL("psi_solver_create: bad size");
+    psi_solver* s = new psi_solver();
+    s->numel = numel;
+    s->stride = round_up64(numel > 0 ? numel : 1, QN_CHUNK);
+    s->cap = max_threshold;
+    s->num_chunks = (int)(s->stride / QN_CHUNK);
+    s->axpy_ctas = std::min(s->num_chunks, QN_AXPY_MAX_CTAS);
+    s->norm_cap = std::max((int)node_grid(numel / PSI_D + 1), s->num_chunks) + 1;
+    const size_t vb = s->stride * sizeof(float);
+    int rc = 0;
+    rc |= solver_alloc(s, (void**)&s->x, vb);
+    rc |= solver_alloc(s, (void**)&s->g, vb);
+    rc |= solver_alloc(s, (void**)&s->dg, vb);
+    rc |= solver_alloc(s, (void**)&s->dx, vb);
+    rc |= solver_alloc(s, (void**)&s->best, vb);
+    rc |= solver_alloc(s, (void**)&s->fx, vb);
+    rc |= solver_alloc(s, (void**)&s->partial, (size_t)3 * s->cap * s->num_chunks * sizeof(float));
+    rc |= solver_alloc(s, (void**)&s->partial2, (size_t)2 * QN_AXPY_MAX_CTAS * sizeof(float));
+    rc |= solver_alloc(s, (void**)&s->coef, (size_t)3 * s->cap * sizeof(float));
+    rc |= solver_alloc(s, (void**)&s->norm_part, (size_t)2 * s->norm_cap * sizeof(float));
+    rc |= solver_alloc(s, (void**)&s->ctrl, sizeof(QnCtrl));
+    rc |= solver_alloc(s, (void**)&s->rel_trace, (size_t)(s->cap + 2) * sizeof(double));
+    rc |= solver_alloc(s, (void**)&s->abs_trace, (size_t)(s->cap + 2) * sizeof(double));
+    if (!rc && cudaMallocHost((void**)&s->h_ctrl, sizeof(QnCtrl)) != cudaSuccess) { g_psi_err = "psi_solver_create: pinned allocation failed"; rc = -1; }
+    if (rc) { psi_solver_destroy(s); return -1; }
+    float* vecs[] = {s->x, s->g, s->dg, s->dx, s->best, s->fx};
+    for (float* v : vecs) cudaMemset(v, 0, vb);
+    // history slabs: at most QN_MAX_SLABS, each at least ~64 MB so that small problems use a single slab
+    int sv = (s->cap + QN_MAX_SLABS - 1) / QN_MAX_SLABS;
+    const int64_t min_vecs = std::max<int64_t>(1, (64ll << 20) / (int64_t)vb);
+    if (sv < min_vecs) sv = (int)std::min<int64_t>(min_vecs, s->cap);
+    s->hist.slab_vecs = sv;
+    s->hist.stride = s->stride;
+    for (int i = 0; i < QN_MAX_SLABS; ++i) { s->hist.U[i] = nullptr; s->hist.V[i] = nullptr; }
+    *out = s;
+    return 0;
+}
+
+extern "C" int psi_solver_destroy(psi_solver_t* s) {
+    if (s == nullptr) return 0;
+    void* ps[] = {s->x, s->g, s->dg, s->dx, s->best, s->fx, s->partial, s->partial2, s->coef, s->norm_part, s->ctrl,
+                  s->rel_trace, s->abs_trace, s->and_X, s->and_F, s->and_small};
+    for (void* p : ps)
+        if (p) cudaFree(p);
+    for (int i = 0; i < QN_MAX_SLABS; ++i) {
+        if (s->hist.U[i]) cudaFree(s->hist.U[i]);
+        if (s->hist.V[i]) cudaFree(s->hist.V[i]);
+    }
+    if (s->h_ctrl) cudaFreeHost(s->h_ctrl);
+    delete s;
+    return 0;
+}
+
+extern "C" int64_t psi_solver_bytes(const psi_solver_t* s) { return s ? s->bytes : 0; }
+extern "C" int64_t psi_solver_stride(const psi_solver_t* s) { return s ? s->stride : 0; }
+
+// make sure history vector index k (0-based) has storage
+static int hist_ensure(psi_solver* s, int k) {
+    const int slab = k / s->hist.slab_vecs;
+    if (slab >= QN_MAX_SLABS) PSI_FAIL("solver history exhausted");
+    while (s->slabs_alloc <= slab) {
+        const int first = s->slabs_alloc * s->hist.slab_vecs;
+        const int vecs = std::min(s->hist.slab_vecs, s->cap - first);
+        if (vecs <= 0) PSI_FAIL("solver history exhausted");
+        const size_t b = (size_t)vecs * s->stride * sizeof(float);
+        if (solver_alloc(s, (void**)&s->hist.U[s->slabs_alloc], b)) return -1;
+        if (solver_alloc(s, (void**)&s->hist.V[s->slabs_alloc], b)) return -1;
+        ++s->slabs_alloc;
+    }
+    return 0;
+}
+
+// ---- shared pieces of the Broyden loop ------------------------------------------------------------------
+static int qn_begin(psi_solver* s, const float* x0, int threshold, double eps, float* xtrace, cudaStream_t st) {
+    if (s == nullptr) PSI_FAIL("null solver handle");
+    if (threshold < 0 || threshold > s->cap) PSI_FAIL("threshold exceeds the solver workspace (psi_solver_create max_threshold)");
+    if (s->numel > 0 && x0 == nullptr) PSI_FAIL("null x0");
+    s->threshold = threshold; s->eps = eps; s->n = 0; s->launches = 0; s->f_evals = 0; s->xtrace = xtrace; s->active = true;
+    k_qn_ctrl_init<<<1, 1, 0, st>>>(s->ctrl);
+    PSI_CK_LAUNCH();
+    if (s->numel > 0) {
+        PSI_CK(cudaMemcpyAsync(s->x, x0, s->numel * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        // lowest_xest starts as x0 (solver.py:150)
+        PSI_CK(cudaMemcpyAsync(s->best, x0, s->numel * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        if (xtrace != nullptr) PSI_CK(cudaMemcpyAsync(xtrace, s->x, s->stride * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    }
+    s->launches += 1;
+    return 0;
+}
+
+// after g_0 is in s->g: update_0 = g_0, x_1 = x_0 + update_0
+static int qn_first(psi_solver* s, cudaStream_t st) {
+    if (s->threshold == 0) return 0;
+    k_qn_first<<<s->axpy_ctas, QN_THREADS, 0, st>>>(s->dx, s->g, s->x, s->xtrace ? s->xtrace + s->stride : nullptr, s->num_chunks);
+    PSI_CK_LAUNCH();
+    s->launches += 1;
+    return 0;
+}
+
+// bookkeeping of step n (1-based) after the operator epilogue produced g_n, δg and the norm partials
+static int qn_update(psi_solver* s, int n, int norm_blocks, cudaStream_t st) {
+    const int nhist = n - 1;
+    if (hist_ensure(s, n - 1)) return -1;
+    if (nhist > 0) {
+        dim3 grid(s->num_chunks, (nhist + QN_KTILE - 1) / QN_KTILE);
+        k_qn_dots<<<grid, QN_THREADS, 0, st>>>(s->hist, nhist, s->dx, s->dg, s->g, s->partial, s->num_chunks, &s->ctrl->done);
+        PSI_CK_LAUNCH();
+        s->launches += 1;
+    }
+    const int fin_blocks = std::max(1, std::min(64, (nhist * 3 + 7) / 8));
+    k_qn_fin1<<<fin_blocks, 256, 0, st>>>(nhist, s->partial, s->num_chunks, s->coef, s->cap, s->norm_part, norm_blocks, s->ctrl,
+                                          s->rel_trace, s->abs_trace, n, s->eps, 1e3 * PSI_D, s->threshold);
+    PSI_CK_LAUNCH();
+    const size_t sh = (size_t)3 * std::max(nhist, 1) * sizeof(float);
+    k_qn_axpy<<<s->axpy_ctas, QN_THREADS, sh, st>>>(s->hist, nhist, n, s->coef, s->cap, s->dx, s->dg, s->g, s->x, s->best, s->partial2,
+                                                    s->num_chunks, s->ctrl);
+    PSI_CK_LAUNCH();
+    float* xt = s->xtrace ? s->xtrace + (int64_t)(n + 1) * s->stride : nullptr;
+    if (n >= s->threshold) xt = nullptr;
+    k_qn_fin2<<<s->axpy_ctas, QN_THREADS, 0, st>>>(s->hist, n, s->dx, s->g, s->x, s->partial2, s->axpy_ctas, xt, s->ctrl, s->num_chunks);
+    PSI_CK_LAUNCH();
+    s->launches += 3;
+    return 0;
+}
+
+static int qn_poll(psi_solver* s, cudaStream_t st) {
+    PSI_CK(cudaMemcpyAsync(s->h_ctrl, s->ctrl, sizeof(QnCtrl), cudaMemcpyDeviceToHost, st));
+    PSI_CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+static int qn_finish(psi_solver* s, float* result, psi_solve_stats_t* stats, double* rel_trace, double* abs_trace, cudaStream_t st) {
+    if (qn_poll(s, st)) return -1;
+    const QnCtrl& c = *s->h_ctrl;
+    const int ran = c.nstep;
+    if (result != nullptr && s->numel > 0)
+        PSI_CK(cudaMemcpyAsync(result, s->best, s->numel * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (stats != nullptr) {
+        stats->lowest = c.best_rel;
+        stats->nstep = c.best_step_rel;
+        stats->steps_run = ran;
+        stats->prot_break = c.prot_break;
+        stats->stop_reason = (c.stop_reason == 5 || c.stop_reason == 4) ? 0 : c.stop_reason;
+        stats->f_evals = s->f_evals;
+        stats->launches = s->launches;
+    }
+    if (rel_trace != nullptr || abs_trace != nullptr) {
+        std::vector<double> tmp(s->threshold + 1);
+        for (int which = 0; which < 2; ++which) {
+            double* dst = which == 0 ? rel_trace : abs_trace;
+            if (dst == nullptr) continue;
+            if (ran > 0)
+                PSI_CK(cudaMemcpyAsync(tmp.data(), which == 0 ? s->rel_trace : s->abs_trace, ran * sizeof(double), cudaMemcpyDeviceToHost, st));
+            PSI_CK(cudaStreamSynchronize(st));
+            const double low = which == 0 ? c.best_rel : c.best_abs;
+            for (int i = 0; i < s->threshold + 1; ++i) dst[i] = i < ran ? tmp[i] : low;   // padded with the lowest value (solver.py:195-197)
+        }
+    }
+    s->active = false;
+    return 0;
+}
+
+static int op_eval(psi_solver* s, psi_graph* g, int kind, int op, const float* aux, float* out, cudaStream_t st) {
+    SolverEpi E{s->g, s->dg, s->norm_part, &s->ctrl->done};
+    s->f_evals += 1;
+    if (op == PSI_OP_LAYER) {
+        s->launches += 1;
+        return launch_layer<true>(g, kind, s->x, aux, out, E, st);
+    }
+    s->launches += 2;
+    return launch_vjp<true>(g, kind, s->x, aux, out, E, st);
+}
+
+extern "C" int psi_solver_broyden(psi_solver_t* s, psi_graph_t* g, int kind, int op, const float* dev_x0, const float* dev_aux,
+                                  int threshold, double eps, float* dev_result, psi_solve_stats_t* stats, double* rel_trace,
+                                  double* abs_trace, float* dev_xtrace, void* stream) {
+    if (s == nullptr) PSI_FAIL("psi_solver_broyden: null solver");
+    if (check_kind(g, kind)) return -1;
+    if (op != PSI_OP_LAYER && op != PSI_OP_VJP) PSI_FAIL("psi_solver_broyden: unknown operator");
+    if (op == PSI_OP_VJP && (!g->vjp_ready || g->vjp_kind != kind)) PSI_FAIL("psi_solver_broyden: call psi_vjp_prepare first");
+    if (op == PSI_OP_VJP && kind != PSI_KIND_DIRICHLET && kind != PSI_KIND_MIXED) PSI_FAIL("psi_solver_broyden: no VJP for this kind");
+    if (g->N * PSI_D != s->numel) PSI_FAIL("psi_solver_broyden: solver workspace size does not match the graph");
+    if (g->N > 0 && dev_aux == nullptr && !(op == PSI_OP_LAYER && kind == PSI_KIND_DSS)) PSI_FAIL("psi_solver_broyden: null aux (h0 / grad)");
+    cudaStream_t st = as_stream(stream);
+    if (qn_begin(s, dev_x0, threshold, eps, dev_xtrace, st)) return -1;
+    const int norm_blocks = (int)node_grid(g->N);
+    if (g->N > 0) {
+        if (op_eval(s, g, kind, op, dev_aux, nullptr, st)) return -1;        // g_0 = op(x_0) − x_0
+        if (qn_first(s, st)) return -1;
+        // poll the device-side stop flag every `poll` steps; kernels of steps past the stop are no-ops
+        const int poll = s->numel < (1 << 22) ? 16 : 4;
+        for (int n = 1; n <= threshold; ++n) {
+            if (op_eval(s, g, kind, op, dev_aux, nullptr, st)) return -1;
+            if (qn_update(s, n, norm_blocks, st)) return -1;
+            if (n % poll == 0 && n < threshold) {
+                if (qn_poll(s, st)) return -1;
+                if (s->h_ctrl->done) break;
+            }
+        }
+    }
+    return qn_finish(s, dev_result, stats, rel_trace, abs_trace, st);
+}
+
+// ---- step API for an arbitrary operator -----------------------------------------------------------------
+extern "C" int psi_broyden_begin(psi_solver_t* s, const float* dev_x0, int threshold, double eps, float* dev_xtrace, void* stream) {
+    return qn_begin(s, dev_x0, threshold, eps, dev_xtrace, as_stream(stream));
+}
+
+extern "C" const float* psi_broyden_x(const psi_solver_t* s) { return s ? s->x : nullptr; }
+
+static int qn_post(psi_solver* s, const float* fx, cudaStream_t st) {
+    if (s->numel == 0) return 0;
+    if (fx == nullptr) PSI_FAIL("null operator output");
+    s->norm_blocks = (int)((s->numel + QN_THREADS * 4 - 1) / (QN_THREADS * 4));
+    k_qn_post<<<s->norm_blocks, QN_THREADS, 0, st>>>(s->numel, fx, s->x, s->g, s->dg, s->norm_part, &s->ctrl->done);
+    PSI_CK_LAUNCH();
+    s->launches += 1;
+    s->f_evals += 1;
+    return 0;
+}
+
+extern "C" int psi_broyden_first(psi_solver_t* s, const float* dev_fx, void* stream) {
+    if (s == nullptr || !s->active) PSI_FAIL("psi_broyden_first: call psi_broyden_begin first");
+    cudaStream_t st = as_stream(stream);
+    if (qn_post(s, dev_fx, st)) return -1;
+    if (s->numel > 0 && qn_first(s, st)) return -1;
+    return 0;
+}
+
+extern "C" int psi_broyden_step(psi_solver_t* s, const float* dev_fx, int* done, void* stream) {
+    if (s == nullptr || !s->active) PSI_FAIL("psi_broyden_step: call psi_broyden_begin first");
+    cudaStream_t st = as_stream(stream);
+    if (s->n >= s->threshold || s->numel == 0) { if (done) *done = 1; return 0; }
+    s->n += 1;
+    if (qn_post(s, dev_fx, st)) return -1;
+    if (qn_update(s, s->n, s->norm_blocks, st)) return -1;
+    if (done != nullptr) {
+        if (qn_poll(s, st)) return -1;
+        *done = s->h_ctrl->done;
+    }
+    return 0;
+}
+
+extern "C" int psi_broyden_finish(psi_solver_t* s, float* dev_result, psi_solve_stats_t* stats, double* rel_trace, double* abs_trace,
+                                  void* stream) {
+    if (s == nullptr || !s->active) PSI_FAIL("psi_broyden_finish: call psi_broyden_begin first");
+    return qn_finish(s, dev_result, stats, rel_trace, abs_trace, as_stream(stream));
+}
+
+// ---- teacher-forced single rank-one update (parity tests) -----------------------------------------------
+__global__ void k_forced_load(int64_t numel, const float* __restrict__ x, const float* __restrict__ gx, const float* __restrict__ xn,
+                              const float* __restrict__ gn, float* __restrict__ sx, float* __restrict__ sg, float* __restrict__ sdx,
+                              float* __restrict__ sdg) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= numel) return;
+    sx[i] = xn[i];
+    sg[i] = gn[i];
+    sdx[i] = xn[i] - x[i];
+    sdg[i] = gn[i] - gx[i];
+}
+
+extern "C" int psi_broyden_forced_step(psi_solver_t* s, int n, const float* dev_x, const float* dev_gx, const float* dev_xnew,
+                                       const float* dev_gnew, const float* dev_U, const float* dev_V, float* dev_u, float* dev_v,
+                                       float* dev_update, void* stream) {
+    if (s == nullptr) PSI_FAIL("psi_broyden_forced_step: null solver");
+    if (n < 1 || n > s->cap) PSI_FAIL("psi_broyden_forced_step: n out of range");
+    if (s->numel == 0) return 0;
+    cudaStream_t st = as_stream(stream);
+    if (hist_ensure(s, n - 1)) return -1;
+    s->threshold = s->cap + 1; s->eps = 0.0; s->xtrace = nullptr; s->launches = 0; s->f_evals = 0;
+    k_qn_ctrl_init<<<1, 1, 0, st>>>(s->ctrl);
+    for (int k = 0; k < n - 1; ++k) {
+        float* du = s->hist.U[k / s->hist.slab_vecs] + (int64_t)(k % s->hist.slab_vecs) * s->stride;
+        float* dv = s->hist.V[k / s->hist.slab_vecs] + (int64_t)(k % s->hist.slab_vecs) * s->stride;
+        PSI_CK(cudaMemsetAsync(du, 0, s->stride * sizeof(float), st));
+        PSI_CK(cudaMemsetAsync(dv, 0, s->stride * sizeof(float), st));
+        PSI_CK(cudaMemcpyAsync(du, dev_U + (int64_t)k * s->numel, s->numel * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        PSI_CK(cudaMemcpyAsync(dv, dev_V + (int64_t)k * s->numel, s->numel * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    }
+    k_forced_load<<<(unsigned)((s->numel + 255) / 256), 256, 0, st>>>(s->numel, dev_x, dev_gx, dev_xnew, dev_gnew, s->x, s->g, s->dx, s->dg);
+    PSI_CK_LAUNCH();
+    PSI_CK(cudaMemsetAsync(s->norm_part, 0, 2 * sizeof(float), st));
+    const int saved_thr = s->threshold;
+    if (qn_update(s, n, 1, st)) return -1;
+    s->threshold = saved_thr;
+    float* du = s->hist.U[(n - 1) / s->hist.slab_vecs] + (int64_t)((n - 1) % s->hist.slab_vecs) * s->stride;
+    float* dv = s->hist.V[(n - 1) / s->hist.slab_vecs] + (int64_t)((n - 1) % s->hist.slab_vecs) * s->stride;
+    if (dev_u) PSI_CK(cudaMemcpyAsync(dev_u, du, s->numel * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (dev_v) PSI_CK(cudaMemcpyAsync(dev_v, dv, s->numel * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (dev_update) PSI_CK(cudaMemcpyAsync(dev_update, s->dx, s->numel * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+// ================================================================================================
+// Picard iteration (forward_iteration, solver.py:301-341) on the layer operator
+// ================================================================================================
+extern "C" int psi_solver_picard(psi_solver_t* s, psi_graph_t* g, int kind, const float* dev_x0, const float* dev_h0, int threshold,
+                                 double eps, float* dev_result, psi_solve_stats_t* stats, double* rel_trace, double* abs_trace,
+                                 void* stream) {
+    if (s == nullptr) PSI_FAIL("psi_solver_picard: null solver");
+    if (check_kind(g, kind)) return -1;
+    if (g->N * PSI_D != s->numel) PSI_FAIL("psi_solver_picard: solver workspace size does not match the graph");
+    if (threshold < 0 || threshold > s->cap) PSI_FAIL("psi_solver_picard: threshold exceeds the solver workspace");
+    cudaStream_t st = as_stream(stream);
+    if (qn_begin(s, dev_x0, threshold, eps, nullptr, st)) return -1;
+    const int norm_blocks = (int)node_grid(g->N);
+    int it = 0, evals = 0;
+    double last_rel = 0.0;
+    if (g->N > 0) {
+        // z = f(z_prev): the epilogue yields ‖z − z_prev‖² and ‖z‖² partials; s->fx receives z, then the buffers swap.
+        const int poll = s->numel < (1 << 22) ? 16 : 4;
+        bool done = false;
+        while (!done) {
+            SolverEpi E{s->g, s->dg, s->norm_part, &s->ctrl->done};
+            if (launch_layer<true>(g, kind, s->x, dev_h0, s->fx, E, st)) return -1;
+            k_picard_fin<<<1, 32, 0, st>>>(s->norm_part, norm_blocks, s->ctrl, s->rel_trace, s->abs_trace, evals, (float)eps, threshold);
+            PSI_CK_LAUNCH();
+            std::swap(s->x, s->fx);
+            ++evals;
+            s->launches += 2;
+            if (evals % poll == 0 || evals > threshold) {
+                if (qn_poll(s, st)) return -1;
+                done = s->h_ctrl->done != 0;
+            }
+        }
+        // after the stop, later evaluations were no-ops but the host kept swapping: the live iterate is the
+        // buffer written by evaluation number ctrl.nstep (1-based); recover it from the parity of the swaps.
+        const int used = s->h_ctrl->nstep;                     // evaluations that actually ran
+        if ((evals - used) % 2 != 0) std::swap(s->x, s->fx);
+        it = used - 1;
+        last_rel = s->h_ctrl->best_rel;
+        evals = used;
+    }
+    if (dev_result != nullptr && s->numel > 0)
+        PSI_CK(cudaMemcpyAsync(dev_result, s->x, s->numel * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (stats != nullptr) {
+        stats->lowest = last_rel; stats->nstep = it; stats->steps_run = it; stats->prot_break = 0;
+        stats->stop_reason = (it < threshold) ? 1 : 0; stats->f_evals = evals; stats->launches = s->launches;
+    }
+    for (int which = 0; which < 2; ++which) {
+        double* dst = which == 0 ? rel_trace : abs_trace;
+        if (dst == nullptr) continue;
+        for (int i = 0; i < threshold + 1; ++i) dst[i] = std::numeric_limits<double>::quiet_NaN();
+        if (evals > 0) PSI_CK(cudaMemcpyAsync(dst, which == 0 ? s->rel_trace : s->abs_trace, evals * sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
+    PSI_CK(cudaStreamSynchronize(st));
+    s->active = false;
+    return 0;
+}
+
+// ================================================================================================
+// Anderson acceleration (solver.py:215-293) on the layer operator
+// ================================================================================================
+extern "C" int psi_solver_anderson(psi_solver_t* s, psi_graph_t* g, int kind, const float* dev_x0, const float* dev_h0, int m, double lam,
+                                   int threshold, double eps, double beta, float* dev_result, psi_solve_stats_t* stats,
+                                   double* rel_trace, double* abs_trace, void* stream) {
+    if (s == nullptr) PSI_FAIL("psi_solver_anderson: null solver");
+    if (check_kind(g, kind)) return -1;
+    if (g->N * PSI_D != s->numel) PSI_FAIL("psi_solver_anderson: solver workspace size does not match the graph");
+    if (m < 2 || m > AND_MAX_M) PSI_FAIL("psi_solver_anderson: m must be in [2, 8]");
+    if (threshold < 0 || threshold > s->cap) PSI_FAIL("psi_solver_anderson: threshold exceeds the solver workspace");
+    cudaStream_t st = as_stream(stream);
+    if (s->and_m < m) {
+        if (s->and_X) { cudaFree(s->and_X); cudaFree(s->and_F); cudaFree(s->and_small); s->and_X = s->and_F = s->and_small = nullptr; }
+        if (solver_alloc(s, (void**)&s->and_X, (size_t)m * s->stride * sizeof(float))) return -1;
+        if (solver_alloc(s, (void**)&s->and_F, (size_t)m * s->stride * sizeof(float))) return -1;
+        if (solver_alloc(s, (void**)&s->and_small, (size_t)(AND_MAX_M * AND_MAX_M * (s->num_chunks + 1) + 64) * sizeof(float))) return -1;
+        s->and_m = m;
+    }
+    if (qn_begin(s, dev_x0, threshold, eps, nullptr, st)) return -1;
+    if (g->N > 0) {
+        const size_t vb = s->stride * sizeof(float);
+        const SolverEpi noE{nullptr, nullptr, nullptr, nullptr};
+        PSI_CK(cudaMemsetAsync(s->and_X, 0, (size_t)m * vb, st));
+        PSI_CK(cudaMemsetAsync(s->and_F, 0, (size_t)m * vb, st));
+        // X[0] = x0 ; F[0] = f(x0) ; X[1] = F[0] ; F[1] = f(F[0])      (solver.py:227-230)
+        PSI_CK(cudaMemcpyAsync(s->and_X, dev_x0, s->numel * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        if (launch_layer<false>(g, kind, s->and_X, dev_h0, s->and_F, noE, st)) return -1;
+        PSI_CK(cudaMemcpyAsync(s->and_X + s->stride, s->and_F, vb, cudaMemcpyDeviceToDevice, st));
+        if (launch_layer<false>(g, kind, s->and_X + s->stride, dev_h0, s->and_F + s->stride, noE, st)) return -1;
+        s->f_evals = 2; s->launches += 2;
+        float* part = s->and_small;                                    // [n*n][num_chunks]
+        float* alpha = s->and_small + (size_t)AND_MAX_M * AND_MAX_M * s->num_chunks;   // [AND_MAX_M]
+        const int poll = s->numel < (1 << 22) ? 8 : 2;
+        for (int k = 2; k < threshold; ++k) {
+            const int n = std::min(k, m);
+            const int slot = k % m;
+            k_and_gram<<<s->num_chunks, QN_THREADS, 0, st>>>(s->and_X, s->and_F, s->stride, n, part, s->num_chunks, &s->ctrl->done);
+            k_and_solve<<<1, 32, 0, st>>>(part, s->num_chunks, n, (float)lam, alpha, &s->ctrl->done);
+            k_and_mix<<<s->axpy_ctas, QN_THREADS, 0, st>>>(s->and_X, s->and_F, s->stride, n, slot, alpha, (float)beta, s->num_chunks, &s->ctrl->done);
+            PSI_CK_LAUNCH();
+            float* xs = s->and_X + (size_t)slot * s->stride;
+            float* fs = s->and_F + (size_t)slot * s->stride;
+            if (launch_layer<false>(g, kind, xs, dev_h0, fs, noE, st)) return -1;   // overwritten only while !done: guarded below
+            k_and_post<<<s->num_chunks, QN_THREADS, 0, st>>>(xs, fs, s->best, s->norm_part, s->num_chunks, &s->ctrl->done);
+            k_and_fin<<<1, 32, 0, st>>>(s->norm_part, s->num_chunks, s->ctrl, s->rel_trace, s->abs_trace, k, eps);
+            k_and_keep<<<s->axpy_ctas, QN_THREADS, 0, st>>>(xs, s->best, s->num_chunks, s->ctrl);
+            PSI_CK_LAUNCH();
+            s->f_evals += 1; s->launches += 7;
+            if ((k - 1) % poll == 0) {
+                if (qn_poll(s, st)) return -1;
+                if (s->h_ctrl->done) break;
+            }
+        }
+    }
+    if (qn_poll(s, st)) return -1;
+    const QnCtrl& c = *s->h_ctrl;
+    const int ran = c.nstep >= 2 ? c.nstep - 1 : 0;       // trace entries written (k = 2 .. nstep)
+    if (dev_result != nullptr && s->numel > 0)
+        PSI_CK(cudaMemcpyAsync(dev_result, s->best, s->numel * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (stats != nullptr) {
+        stats->lowest = c.best_rel; stats->nstep = c.best_step_rel; stats->steps_run = ran; stats->prot_break = 0;
+        stats->stop_reason = c.done ? 1 : 0; stats->f_evals = s->f_evals; stats->launches = s->launches;
+    }
+    // trace length: threshold−2 entries (k = 2..threshold−1), padded with the lowest after an early stop (solver.py:275-278)
+    const int len = std::max(threshold - 2, 0);
+    std::vector<double> tmp(std::max(ran, 1));
+    for (int which = 0; which < 2; ++which) {
+        double* dst = which == 0 ? rel_trace : abs_trace;
+        if (dst == nullptr) continue;
+        if (ran > 0) PSI_CK(cudaMemcpyAsync(tmp.data(), which == 0 ? s->rel_trace : s->abs_trace, ran * sizeof(double), cudaMemcpyDeviceToHost, st));
+        PSI_CK(cudaStreamSynchronize(st));
+        const double low = which == 0 ? c.best_rel : c.best_abs;
+        for (int i = 0; i < threshold + 1; ++i) dst[i] = i < ran ? tmp[i] : (i < len ? low : std::numeric_limits<double>::quiet_NaN());
+    }
+    PSI_CK(cudaStreamSynchronize(st));
+    s->active = false;
+    return 0;
+}

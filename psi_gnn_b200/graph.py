@@ -1,0 +1,139 @@
+"""One-off re-layout of a PyG-style batch into the native destination-sorted lists (csrc/graph.cuh).
+
+Replaces what the reference recomputes on every evaluation of f: ``remove_self_loops``
+(dirichlet/psignn/model.py:342,360), ``torch.where(batch.tags == 1)`` (:281) and the
+``SparseTensor`` construction (:159-163).  The handle is cached on the batch object.
+"""
+from __future__ import annotations
+
+import ctypes
+from ctypes import byref, c_int64, c_void_p
+from typing import Optional
+
+import torch
+
+from . import _native as N
+
+KIND_NAMES = {N.KIND_DIRICHLET: "dirichlet", N.KIND_MIXED: "mixed", N.KIND_DSS: "dss", N.KIND_DSGPS: "dsgps"}
+
+
+class NativeGraph:
+    """Owns a ``psi_graph_t`` handle (destroyed with the object)."""
+
+    def __init__(self, num_nodes: int, edge_index: torch.Tensor, edge_attr: torch.Tensor, a_ij: Optional[torch.Tensor],
+                 tags: Optional[torch.Tensor], prb: Optional[torch.Tensor], normals: Optional[torch.Tensor] = None):
+        lib = N.load()
+        if edge_index.dtype != torch.int64:
+            raise RuntimeError("psi_gnn_b200: edge_index must be int64 (PyG convention)")
+        if edge_index.dim() != 2 or edge_index.shape[0] != 2:
+            raise RuntimeError("psi_gnn_b200: edge_index must have shape [2, nnz]")
+        nnz = int(edge_index.shape[1])
+        ei = edge_index.contiguous()
+        attr = N.f32(edge_attr.reshape(nnz, -1))
+        aij = N.f32(a_ij.reshape(-1)) if a_ij is not None else None
+        if aij is not None and aij.numel() != nnz:
+            raise RuntimeError("psi_gnn_b200: a_ij must have one entry per edge")
+        tg = N.f32(tags.reshape(num_nodes, -1)) if tags is not None else None
+        pr = N.f32(prb.reshape(num_nodes, -1)) if prb is not None else None
+        nr = N.f32(normals.reshape(num_nodes, 2)) if normals is not None else None
+        self.device = ei.device
+        self.num_nodes = int(num_nodes)
+        self.handle = c_void_p()
+        with torch.cuda.device(self.device):
+            N.check(lib.psi_graph_create(byref(self.handle), self.num_nodes, nnz, N.ptr(ei), N.ptr(attr), int(attr.shape[1]) if nnz else 3,
+                                         N.ptr(aij), N.ptr(tg), int(tg.shape[1]) if tg is not None else 1, N.ptr(pr),
+                                         int(pr.shape[1]) if pr is not None else 0, N.ptr(nr), N.stream_ptr()), "psi_graph_create")
+        info = (c_int64 * 8)()
+        N.check(lib.psi_graph_info(self.handle, info), "psi_graph_info")
+        self.num_offdiag, self.nnz, self.num_dirichlet, self.num_neumann = int(info[1]), int(info[2]), int(info[3]), int(info[4])
+        self.slots_to, self.slots_from, self.bytes = int(info[5]), int(info[6]), int(info[7])
+        self._solver = None          # lazily created workspace shared by the forward and backward solves
+
+    def __del__(self):
+        try:
+            if self._solver is not None:
+                self._solver.close()
+            if self.handle:
+                N.load().psi_graph_destroy(self.handle)
+                self.handle = c_void_p()
+        except Exception:
+            pass
+
+    # ---- single applications ------------------------------------------------------------------------
+    def layer_forward(self, kind: int, h: torch.Tensor, h0: Optional[torch.Tensor]) -> torch.Tensor:
+        h = N.f32(h)
+        h0c = N.f32(h0) if h0 is not None else None
+        out = torch.empty_like(h)
+        with torch.cuda.device(self.device):
+            N.check(N.load().psi_layer_forward(self.handle, kind, N.ptr(h), N.ptr(h0c), N.ptr(out), N.stream_ptr()), "psi_layer_forward")
+        return out
+
+    def vjp_prepare(self, kind: int, hstar: torch.Tensor, h0: Optional[torch.Tensor] = None):
+        hs = N.f32(hstar)
+        with torch.cuda.device(self.device):
+            N.check(N.load().psi_vjp_prepare(self.handle, kind, N.ptr(hs), None, N.stream_ptr()), "psi_vjp_prepare")
+
+    def vjp_apply(self, kind: int, y: torch.Tensor, grad: Optional[torch.Tensor] = None) -> torch.Tensor:
+        y = N.f32(y)
+        g = N.f32(grad) if grad is not None else None
+        out = torch.empty_like(y)
+        with torch.cuda.device(self.device):
+            N.check(N.load().psi_vjp_apply(self.handle, kind, N.ptr(y), N.ptr(g), N.ptr(out), N.stream_ptr()), "psi_vjp_apply")
+        return out
+
+    def residual(self, u: torch.Tensor, y: torch.Tensor, want_vector: bool = False):
+        """(mean((A u − y)²), residual vector or None)  — dirichlet/psignn/model.py:157-167."""
+        u = N.f32(u.reshape(-1))
+        y = N.f32(y.reshape(-1))
+        r = torch.empty_like(u) if want_vector else None
+        ms = torch.empty(1, dtype=torch.float32, device=u.device)
+        with torch.cuda.device(self.device):
+            N.check(N.load().psi_residual(self.handle, N.ptr(u), N.ptr(y), N.ptr(r), N.ptr(ms), N.stream_ptr()), "psi_residual")
+        return ms[0], r
+
+    def spmv_t(self, v: torch.Tensor) -> torch.Tensor:
+        v = N.f32(v.reshape(-1))
+        out = torch.empty_like(v)
+        with torch.cuda.device(self.device):
+            N.check(N.load().psi_spmv_t(self.handle, N.ptr(v), N.ptr(out), N.stream_ptr()), "psi_spmv_t")
+        return out
+
+    def solver(self, threshold: int):
+        from .solver import SolverWorkspace
+        if self._solver is None or self._solver.cap < threshold:
+            if self._solver is not None:
+                self._solver.close()
+            self._solver = SolverWorkspace(self.num_nodes * 10, max(threshold, 1), self.device)
+        return self._solver
+
+
+def _cache_slot(batch):
+    d = getattr(batch, "__dict__", None)
+    return d if isinstance(d, dict) else None
+
+
+def graph_of(batch, kind: int) -> NativeGraph:
+    """The (cached) native graph of a batch for a layer kind.
+
+    PSI-GNN / DSGPS use ``edge_attr [nnz,3]`` and ``prb_data``; DSS uses the 1-column normalised stiffness
+    ``a_ij_norm`` and ``b_prime_norm`` on its own diagonal-free edge list (dirichlet/dss/utilities/reader.py).
+    """
+    slot = _cache_slot(batch)
+    key = "_psi_graph_%d" % kind
+    ei = batch.edge_index
+    if slot is not None and key in slot:
+        g, stamp = slot[key]
+        if stamp == (ei.data_ptr(), tuple(ei.shape), ei.device):
+            return g
+    if not ei.is_cuda:
+        raise RuntimeError("psi_gnn_b200: the batch must live on a CUDA device (no CPU fallback exists)")
+    n = int(batch.num_nodes) if getattr(batch, "num_nodes", None) is not None else int(batch.x.shape[0])
+    if kind == N.KIND_DSS:
+        g = NativeGraph(n, ei, batch.a_ij_norm, getattr(batch, "a_ij", None), None, batch.b_prime_norm)
+    elif kind == N.KIND_MIXED:
+        g = NativeGraph(n, ei, batch.edge_attr, batch.a_ij, batch.tags, batch.prb_data, batch.unit_normal_vector)
+    else:
+        g = NativeGraph(n, ei, batch.edge_attr, batch.a_ij, batch.tags, batch.prb_data)
+    if slot is not None:
+        slot[key] = (g, (ei.data_ptr(), tuple(ei.shape), ei.device))
+    return g

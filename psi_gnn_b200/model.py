@@ -1,0 +1,461 @@
+"""PSI-GNN modules with the class names, constructor signatures and ``state_dict`` keys of the reference
+(``dirichlet/psignn/model.py`` and ``mixed/psignn/model.py``), running the implicit solve on the native kernels.
+
+Import through ``psi_gnn_b200.dirichlet.psignn.model`` / ``psi_gnn_b200.mixed.psignn.model``, which bind the
+boundary-condition family.  What runs where:
+
+* forward fixed-point solve, backward implicit-adjoint solve, ``inference``, residual, encoder/decoder in
+  inference, spectral-radius power iteration: CUDA kernels behind the C ABI (include/psignn_b200.h);
+* the *single* differentiable re-application ``f(H*)`` per training step (reference model.py:204-207), whose
+  autograd graph carries the parameter gradients and the Jacobian regulariser's double backward: torch ops on
+  the same device (≈1 of ≈660 evaluations of a step).
+CPU tensors raise ``RuntimeError`` everywhere — there is no CPU path.
+"""
+from __future__ import annotations
+
+import os
+import weakref
+from typing import Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+from torch import autograd
+
+from . import _native as N
+from . import solver as _solver
+from . import weights as W
+from .graph import NativeGraph, graph_of
+
+
+def initialize_weights_xavier(m, gain=1.0):
+    if isinstance(m, nn.Linear):
+        nn.init.xavier_uniform_(m.weight, gain=gain)
+        if m.bias is not None:
+            nn.init.constant_(m.bias, 0)
+
+
+class MLP(nn.Module):
+    """Linear → act → … → Linear (reference model.py:316-332); keys ``mlp.{0,2}.{weight,bias}``."""
+
+    def __init__(self, hidden_channels=None, activation=None):
+        super().__init__()
+        layers = []
+        units = hidden_channels[0]
+        for k in range(1, len(hidden_channels)):
+            layers.append(nn.Linear(units, hidden_channels[k]))
+            if k != len(hidden_channels) - 1:
+                layers.append(activation)
+            units = hidden_channels[k]
+        self.mlp = nn.Sequential(*layers).apply(initialize_weights_xavier)
+
+    def forward(self, x):
+        return self.mlp(x)
+
+
+def _offdiag(batch, edge_index, edge_attr):
+    """``remove_self_loops`` hoisted out of the iteration: computed once per batch and cached on it."""
+    d = getattr(batch, "__dict__", None)
+    stamp = (edge_index.data_ptr(), edge_attr.data_ptr())
+    if isinstance(d, dict) and d.get("_psi_offdiag_stamp") == stamp:
+        return d["_psi_offdiag"]
+    keep = edge_index[0] != edge_index[1]
+    out = (edge_index[:, keep].contiguous(), edge_attr[keep].contiguous())
+    if isinstance(d, dict):
+        d["_psi_offdiag"], d["_psi_offdiag_stamp"] = out, stamp
+    return out
+
+
+class _Phi(nn.Module):
+    """Σ_e MLP(cat[x_i, x_j, a_e]) with PyG ``aggr='add'`` semantics (reference model.py:334-368)."""
+    _to = True
+
+    def __init__(self, hidden_channels=None, activation=None):
+        super().__init__()
+        self.mlp = MLP(hidden_channels, activation)
+
+    def forward(self, x, edge_index, edge_attr, batch=None):
+        if not x.is_cuda:
+            raise RuntimeError("psi_gnn_b200: CUDA tensors required (no CPU path)")
+        ei, attr = _offdiag(batch, edge_index, edge_attr) if batch is not None else \
+            (lambda k: (edge_index[:, k], edge_attr[k]))(edge_index[0] != edge_index[1])
+        i, j = (ei[1], ei[0]) if self._to else (ei[0], ei[1])       # source_to_target : target_to_source
+        msg = self.mlp(torch.cat([x[i], x[j], attr], dim=1))
+        return torch.zeros(x.size(0), msg.size(1), dtype=msg.dtype, device=msg.device).index_add(0, i, msg)
+
+
+class Phi_to(_Phi):
+    _to = True
+
+
+class Phi_from(_Phi):
+    _to = False
+
+
+class Encoder(nn.Module):
+    def __init__(self, hidden_channels=None, activation=None):
+        super().__init__()
+        self.mlp = MLP(hidden_channels, activation)
+
+    def forward(self, x):
+        return self.mlp(x)
+
+
+class Decoder(nn.Module):
+    def __init__(self, hidden_channels=None, activation=None):
+        super().__init__()
+        self.mlp = MLP(hidden_channels, activation)
+
+    def forward(self, x):
+        return self.mlp(x)
+
+
+class Autoencoder(nn.Module):
+    def __init__(self, hidden_channels=None, activation=None):
+        super().__init__()
+        self.encoder = Encoder(hidden_channels, activation)
+        self.decoder = Decoder(list(reversed(hidden_channels)), activation)
+
+    def forward(self, x, sens):
+        if sens == "latent":
+            return self.encoder(self.decoder(x))
+        elif sens == "physics":
+            return self.decoder(self.encoder(x))
+        else:
+            print("Specify autoencoder direction")
+
+
+# ---------------------------------------------------------------------------------------------------------
+# f_theta
+# ---------------------------------------------------------------------------------------------------------
+class _FunctionBase(nn.Module):
+    """One message-passing layer f_θ(h, h_initial, batch) (dirichlet model.py:263-300, mixed model.py:196-245)."""
+    kind = N.KIND_DIRICHLET
+
+    def __init__(self, n_layers=None, latent_dim=None, edge_features_dim=None, second_member_dim=None, activation=None):
+        super().__init__()
+        self.n_layers = n_layers
+        self.latent_dim = latent_dim
+        self.laynorm = nn.LayerNorm(latent_dim)
+        ch = [2 * latent_dim + edge_features_dim, latent_dim, latent_dim]
+        self.phi_to_list = nn.ModuleList([Phi_to(ch, activation) for _ in range(n_layers)])
+        self.phi_from_list = nn.ModuleList([Phi_from(ch, activation) for _ in range(n_layers)])
+        self.alpha = nn.Sequential(nn.Linear(3 * latent_dim + second_member_dim, 1), nn.Sigmoid()).apply(initialize_weights_xavier)
+        self.update_list = nn.ModuleList([MLP([3 * latent_dim + second_member_dim, latent_dim, latent_dim], activation)
+                                          for _ in range(n_layers)])
+        if self.kind == N.KIND_MIXED:
+            self.phi_neumann = Phi_from(ch, activation)
+            self.update_neumann = MLP([2 * latent_dim + second_member_dim + 2, latent_dim, latent_dim], activation)
+        self._autoencoder_ref = None          # set by ModelDEQDSS so that encoder/decoder kernels share the block
+        self._pack_cache = (None, None)
+
+    # ---- native plumbing ---------------------------------------------------------------------------------
+    def _check_native(self):
+        if self.n_layers != 1:
+            raise NotImplementedError("psi_gnn_b200: the fused kernel implements n_layers=1 (every shipped reference config)")
+        if self.latent_dim != W.D:
+            raise NotImplementedError("psi_gnn_b200: the fused kernel is built for latent_dim=10 (every shipped reference config)")
+        if not isinstance(self.update_list[0].mlp[1], nn.ReLU):
+            raise NotImplementedError("psi_gnn_b200: the fused kernel implements the ReLU activation of the reference")
+
+    def native_graph(self, batch) -> NativeGraph:
+        self._check_native()
+        return graph_of(batch, self.kind)
+
+    def _named(self):
+        P = W.named_tensors(self, "deqdss.f.")
+        ae = self._autoencoder_ref() if self._autoencoder_ref is not None else None
+        if ae is not None:
+            P.update(W.named_tensors(ae, "autoencoder."))
+        return P
+
+    def upload_weights(self, device):
+        P = self._named()
+        key = (id(self), W.version_key(P), str(device))
+        if self._pack_cache[0] != key:
+            with torch.no_grad():
+                self._pack_cache = (key, W.pack_psignn(P, self.kind == N.KIND_MIXED, device))
+        W.upload(self._pack_cache[1], key)
+
+    # ---- forward --------------------------------------------------------------------------------------------
+    def forward(self, h, h_initial, batch):
+        if not h.is_cuda:
+            raise RuntimeError("psi_gnn_b200: CUDA tensors required — the PSI-GNN layer has no CPU implementation")
+        needs_graph = torch.is_grad_enabled() and (h.requires_grad or h_initial.requires_grad
+                                                   or any(p.requires_grad for p in self.parameters()))
+        if not needs_graph:
+            g = self.native_graph(batch)
+            self.upload_weights(h.device)
+            return g.layer_forward(self.kind, h, h_initial)
+        return self._forward_torch(h, h_initial, batch)
+
+    def _forward_torch(self, h, h_initial, batch):
+        raise NotImplementedError
+
+
+class FunctionDirichlet(_FunctionBase):
+    kind = N.KIND_DIRICHLET
+
+    def _forward_torch(self, h, h_initial, batch):
+        dmask = (batch.tags.reshape(-1) == 1)[:, None]
+        for k in range(self.n_layers):
+            mp_to = self.phi_to_list[k](h, batch.edge_index, batch.edge_attr, batch)
+            mp_from = self.phi_from_list[k](h, batch.edge_index, batch.edge_attr, batch)
+            concat = torch.cat([h, mp_to, mp_from, batch.prb_data], dim=1)
+            update = self.alpha(concat) * self.update_list[k](concat)
+            h = self.laynorm(h + update) if k == self.n_layers - 1 else h + update
+            h = torch.where(dmask, h_initial, h)              # h[index_dirichlet,:] = h_initial[index_dirichlet,:]
+        return h
+
+
+class FunctionMixed(_FunctionBase):
+    kind = N.KIND_MIXED
+
+    def _forward_torch(self, h, h_initial, batch):
+        dmask = (batch.tags[:, 1] == 1)[:, None]
+        nmask = (batch.tags[:, 2] == 1)[:, None]
+        h_next = h
+        for k in range(self.n_layers):                          # the reference never reassigns h inside the loop (mixed model.py:221-243)
+            mp_to = self.phi_to_list[k](h, batch.edge_index, batch.edge_attr, batch)
+            mp_from = self.phi_from_list[k](h, batch.edge_index, batch.edge_attr, batch)
+            mp_neu = self.phi_neumann(h, batch.edge_index, batch.edge_attr, batch)
+            concat = torch.cat([h, mp_to, mp_from, batch.prb_data], dim=1)
+            update_interior = self.alpha(concat) * self.update_list[k](concat)
+            update_neumann = self.update_neumann(torch.cat([h, mp_neu, batch.prb_data, batch.unit_normal_vector], dim=1))
+            h_next = torch.where(nmask, update_neumann, h + update_interior)
+            if k == self.n_layers - 1:
+                h_next = self.laynorm(h_next)
+            h_next = torch.where(dmask, h_initial, h_next)
+        return h_next
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Jacobian diagnostics
+# ---------------------------------------------------------------------------------------------------------
+def jac_loss_estimate(f0, z0, vecs=2, create_graph=True):
+    """Hutchinson estimate of tr(JᵀJ)/numel (reference model.py:416-435)."""
+    result = 0
+    for _ in range(vecs):
+        v = torch.randn(*z0.shape, device=z0.device)
+        vJ = torch.autograd.grad(f0, z0, v, retain_graph=True, create_graph=create_graph)[0]
+        result += vJ.norm() ** 2
+    return result / vecs / np.prod(z0.shape)
+
+
+def power_method(f0, z0, n_iters=200, operator: Optional[_solver.VjpOperator] = None):
+    """Spectral radius of J by power iteration on Jᵀ (reference model.py:437-452).
+
+    With ``operator`` (a prepared :class:`VjpOperator` with zero ``grad``) each product is one fused VJP kernel pair
+    instead of an autograd graph walk."""
+    evector = torch.randn_like(z0)
+    bsz = 1
+    evalue = None
+    for i in range(n_iters):
+        if operator is not None:
+            vTJ = operator.graph.vjp_apply(operator.kind, evector, None)
+        else:
+            vTJ = torch.autograd.grad(f0, z0, evector, retain_graph=(i < n_iters - 1), create_graph=False)[0]
+        evalue = (vTJ * evector).reshape(bsz, -1).sum(1, keepdim=True) / (evector * evector).reshape(bsz, -1).sum(1, keepdim=True)
+        evector = (vTJ.reshape(bsz, -1) / vTJ.reshape(bsz, -1).norm(dim=1, keepdim=True)).reshape_as(z0)
+    return (evector, torch.abs(evalue))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# DEQ wrapper
+# ---------------------------------------------------------------------------------------------------------
+class DeepEquilibrium(nn.Module):
+    """reference model.py:177-253: no-grad forward solve → one differentiable f(H*) → backward hook that solves
+    y = Jᵀy + grad with the same solver."""
+
+    def __init__(self, function=None, config_deq=None):
+        super().__init__()
+        self.f = function
+        self.config_deq = config_deq
+        self.path_logs = self.config_deq.get("path_logs")
+        self.hook = None
+        self.last_forward = None        # solver dicts of the most recent solves (diagnostics / benchmarks)
+        self.last_backward = None
+
+    def _log(self, name, text):
+        if self.path_logs:
+            with open(os.path.join(self.path_logs, name), 'a') as f:
+                f.write(text)
+
+    def _solve(self, op, x0, thres, tol):
+        return self.config_deq["solver"](op, x0, threshold=self.config_deq[thres], eps=self.config_deq[tol])
+
+    def forward(self, H_init, batch):
+        with torch.no_grad():
+            out_fw = self._solve(_solver.LayerOperator(self.f, H_init, batch), H_init, "fw_thres", "fw_tol")
+            H_star = out_fw['result']
+        self.last_forward = out_fw
+        new_H_star = H_star
+
+        if torch.is_grad_enabled():
+            self._log("forward_iteration.csv", '\n{} \t {}'.format(out_fw['lowest'], out_fw['nstep']))
+            H_star.requires_grad_()
+            new_H_star = self.f(H_star, H_init, batch)
+            jac_loss = jac_loss_estimate(new_H_star, H_star, vecs=1)
+
+            def backward_hook(grad):
+                if self.hook is not None:
+                    self.hook.remove()
+                    torch.cuda.synchronize()
+                op = _solver.VjpOperator(self.f, H_star, batch, grad)
+                out_bw = self._solve(op, torch.zeros_like(grad), "bw_thres", "bw_tol")
+                self.last_backward = out_bw
+                self._log("backward_iteration.csv", '\n{} \t {}'.format(out_bw['lowest'], out_bw['nstep']))
+                return out_bw['result']
+
+            self.hook = new_H_star.register_hook(backward_hook)
+        else:
+            with torch.enable_grad():
+                H_star.requires_grad_()
+                new_H_star = self.f(H_star, H_init, batch)
+            jac_loss = jac_loss_estimate(new_H_star, H_star, vecs=1)
+            op = _solver.VjpOperator(self.f, H_star, batch, torch.zeros_like(H_star))
+            _, sradius = power_method(new_H_star, H_star, n_iters=150, operator=op)
+            self._log("spectral_radius.csv", '\n{}'.format(sradius.item()))
+        return new_H_star, jac_loss
+
+    def inference(self, H_init, batch, keep_trace=None):
+        op = _solver.LayerOperator(self.f, H_init, batch)
+        kw = {} if keep_trace is None else {"keep_trace": keep_trace}
+        out_fw = self.config_deq["solver"](op, H_init, threshold=self.config_deq["fw_thres"], eps=self.config_deq["fw_tol"], **kw)
+        self.last_forward = out_fw
+        return out_fw
+
+
+# ---------------------------------------------------------------------------------------------------------
+# physics residual with a native forward and backward
+# ---------------------------------------------------------------------------------------------------------
+class _ResidualLoss(autograd.Function):
+    """mean((A u − y)²): forward = fused SpMV + reduction kernel, backward = (2/N)·Aᵀr kernel."""
+
+    @staticmethod
+    def forward(ctx, u, y, graph):
+        ms, r = graph.residual(u.detach(), y, want_vector=True)
+        ctx.graph = graph
+        ctx.save_for_backward(r)
+        ctx.shape = u.shape
+        return ms.clone()
+
+    @staticmethod
+    def backward(ctx, gout):
+        (r,) = ctx.saved_tensors
+        gu = ctx.graph.spmv_t(r) * (2.0 / max(r.numel(), 1)) * gout
+        return gu.view(ctx.shape), None, None
+
+
+# ---------------------------------------------------------------------------------------------------------
+# full model
+# ---------------------------------------------------------------------------------------------------------
+class _ModelBase(nn.Module):
+    """``ModelDEQDSS(config)`` (reference dirichlet model.py:28-167, mixed model.py:28-109)."""
+    _function_cls = FunctionDirichlet
+    _second_member_dim = 2
+
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        self.autoencoder = Autoencoder(hidden_channels=[1, self.config["latent_dim"], self.config["latent_dim"]], activation=nn.ReLU())
+        self.config_deq = {"solver": self.config["solver"], "fw_tol": self.config["fw_tol"], "fw_thres": self.config["fw_thres"],
+                           "bw_tol": self.config["bw_tol"], "bw_thres": self.config["bw_thres"], "path_logs": self.config.get("path_logs")}
+        self.deqdss = DeepEquilibrium(function=self._function_cls(n_layers=self.config["n_layers"], latent_dim=self.config["latent_dim"],
+                                                                  edge_features_dim=3, second_member_dim=self._second_member_dim,
+                                                                  activation=nn.ReLU()),
+                                      config_deq=self.config_deq)
+        self.deqdss.f._autoencoder_ref = weakref.ref(self.autoencoder)
+        self.mse_loss = nn.MSELoss()
+
+    def _dirichlet_index(self, batch):
+        t = batch.tags
+        return torch.where((t if t.dim() == 1 or t.shape[1] == 1 else t[:, 1:2]) == 1)[0]
+
+    def forward(self, batch):
+        loss_dic = {}
+        h_initial = self.autoencoder.encoder(batch.x)
+        h_final, jacobian_loss = self.deqdss(h_initial, batch)
+        u_final = self.autoencoder.decoder(h_final)
+        residual_loss = self.residual_loss(u_final, batch)
+        u_detached = u_final.detach()
+        h_detached = h_final.detach()
+        encoder_loss = self.mse_loss(self.autoencoder.encoder(u_detached), h_detached)
+        autoencoder_loss = self.mse_loss(self.autoencoder.decoder(self.autoencoder.encoder(u_detached).detach()), u_detached)
+        mse = self.mse_loss(u_final, batch.sol)
+        index_dirichlet = self._dirichlet_index(batch)
+        mse_dirichlet = self.mse_loss(u_final[index_dirichlet, :], batch.x[index_dirichlet, :])
+        loss_dic["residual_loss"] = residual_loss
+        loss_dic["jacobian_loss"] = jacobian_loss
+        loss_dic["encoder_loss"] = encoder_loss
+        loss_dic["autoencoder_loss"] = autoencoder_loss
+        loss_dic["mse_loss"] = mse
+        loss_dic["mse_dirichlet"] = mse_dirichlet
+        return u_final, loss_dic
+
+    # ---- inference: encoder → native solve → decoder, all on the extension ------------------------------------
+    def _encode_native(self, x):
+        f = self.deqdss.f
+        f._check_native()
+        f.upload_weights(x.device)
+        xc = N.f32(x.detach().reshape(-1))
+        h = torch.empty(xc.numel(), W.D, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            N.check(N.load().psi_encode(xc.numel(), N.ptr(xc), N.ptr(h), N.stream_ptr()), "psi_encode")
+        return h
+
+    def _decode_native(self, h):
+        f = self.deqdss.f
+        f.upload_weights(h.device)
+        hc = N.f32(h.detach())
+        u = torch.empty(hc.shape[0], 1, dtype=torch.float32, device=h.device)
+        with torch.cuda.device(h.device):
+            N.check(N.load().psi_decode(hc.shape[0], N.ptr(hc), N.ptr(u), N.stream_ptr()), "psi_decode")
+        return u
+
+    def inference(self, batch):
+        if not batch.x.is_cuda:
+            raise RuntimeError("psi_gnn_b200: CUDA tensors required — there is no CPU path")
+        h_initial = self._encode_native(batch.x)
+        out = self.deqdss.inference(h_initial, batch)
+        return self._decode_native(out["result"])
+
+    def iterative_inference(self, batch):
+        """Decode every Broyden iterate (reference dirichlet model.py:109-155; it indexes the tuple returned by
+        ``DeepEquilibrium.forward`` there, which cannot work — this follows the evident intent and the working
+        ``ModelPSIGNNIterative`` of tests/model_psignn.py:114-214: use the solver dict of ``inference``)."""
+        out_dic = {"sol_dic": [], "res_dic": [], "mse_dic": [], "bound_mse_dic": [], "inter_mse_dic": [], "nstep": []}
+        t = batch.tags if batch.tags.dim() == 1 or batch.tags.shape[1] == 1 else batch.tags[:, 1:2]
+        index_boundary = torch.where(t == 1)[0]
+        index_interior = torch.where(t == 0)[0]
+
+        def record(u):
+            out_dic["sol_dic"].append(u.cpu())
+            out_dic["res_dic"].append(self.residual_loss(u, batch).cpu().item())
+            out_dic["mse_dic"].append(torch.mean((u - batch.sol) ** 2).cpu().item())
+            out_dic["bound_mse_dic"].append(torch.mean((u[index_boundary, :] - batch.sol[index_boundary, :]) ** 2).cpu().item())
+            out_dic["inter_mse_dic"].append(torch.mean((u[index_interior, :] - batch.sol[index_interior, :]) ** 2).cpu().item())
+
+        record(batch.x)
+        h_initial = self._encode_native(batch.x)
+        out_fw = self.deqdss.inference(h_initial, batch, keep_trace=True)
+        for h_star in out_fw["xest_trace"]:
+            record(self._decode_native(h_star.contiguous()))
+        out_dic["nstep"] = out_fw["nstep"]
+        return out_dic
+
+    def residual_loss(self, u, batch):
+        if not u.is_cuda:
+            raise RuntimeError("psi_gnn_b200: CUDA tensors required — there is no CPU path")
+        kind = self.deqdss.f.kind
+        return _ResidualLoss.apply(u, batch.y, graph_of(batch, kind))
+
+
+class ModelDEQDSSDirichlet(_ModelBase):
+    _function_cls = FunctionDirichlet
+    _second_member_dim = 2
+
+
+class ModelDEQDSSMixed(_ModelBase):
+    _function_cls = FunctionMixed
+    _second_member_dim = 3

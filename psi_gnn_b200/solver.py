@@ -1,0 +1,250 @@
+"""Fixed-point solvers with the call signatures of the reference's ``utilities/solver.py``.
+
+``broyden(f, x0, threshold, eps=1e-3, stop_mode="rel", ls=False, name="unknown")`` (solver.py:116-207),
+``anderson(f, x0, m=2, lam=1e-4, threshold=50, eps=1e-3, stop_mode='rel', beta=1.0)`` (:215-293) and
+``forward_iteration(f, z0, eps=1e-5, threshold=50)`` (:301-341) return the reference's result dict.
+
+``f`` may be
+  * a :class:`LayerOperator` / :class:`VjpOperator` — what ``DeepEquilibrium`` passes.  The whole solve then runs
+    as a device-resident loop of fused CUDA kernels (one operator kernel + four quasi-Newton kernels per
+    step, no torch op and no host synchronisation inside the loop except a stop-flag poll every few steps);
+  * any other callable on CUDA tensors — the same quasi-Newton kernels are driven through the step API, with
+    one Python call of ``f`` per step.
+There is no CPU implementation: CPU tensors raise ``RuntimeError``.
+"""
+from __future__ import annotations
+
+import ctypes
+from ctypes import POINTER, byref, c_double, c_int, c_void_p
+from typing import Callable, List, Optional
+
+import torch
+
+from . import _native as N
+
+# The reference keeps every iterate alive in ``xest_trace`` ((threshold+1)·N·d floats).  Off by default here;
+# set to True (or pass keep_trace=True) for ``iterative_inference``-style consumers.
+KEEP_TRACE = False
+
+
+class SolverWorkspace:
+    """Owns a ``psi_solver_t``: iterate, residual, δx/δg, best iterate and the U/V history (lazily grown)."""
+
+    def __init__(self, numel: int, max_threshold: int, device):
+        self.numel, self.cap, self.device = int(numel), int(max_threshold), torch.device(device)
+        self.handle = c_void_p()
+        with torch.cuda.device(self.device):
+            N.check(N.load().psi_solver_create(byref(self.handle), self.numel, self.cap), "psi_solver_create")
+        self.stride = int(N.load().psi_solver_stride(self.handle))
+
+    def close(self):
+        if self.handle:
+            N.load().psi_solver_destroy(self.handle)
+            self.handle = c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def nbytes(self) -> int:
+        return int(N.load().psi_solver_bytes(self.handle))
+
+
+class NativeOperator:
+    """Base class of the operators whose solves run entirely inside the extension."""
+    graph = None
+    kind = 0
+    op = N.OP_LAYER
+    aux: Optional[torch.Tensor] = None
+
+    def upload(self):
+        pass
+
+
+class LayerOperator(NativeOperator):
+    """``lambda H: f(H, H_init, batch)`` of dirichlet/psignn/model.py:189,247 as an object the solvers recognise."""
+    op = N.OP_LAYER
+
+    def __init__(self, function, h_init: torch.Tensor, batch):
+        self.function, self.batch = function, batch
+        self.graph = function.native_graph(batch)
+        self.kind = function.kind
+        self.aux = N.f32(h_init.detach())
+
+    def upload(self):
+        self.function.upload_weights(self.aux.device)
+
+    def __call__(self, h: torch.Tensor) -> torch.Tensor:
+        self.upload()
+        return self.graph.layer_forward(self.kind, h, self.aux)
+
+
+class VjpOperator(NativeOperator):
+    """``lambda y: autograd.grad(f(H*), H*, y)[0] + grad`` of model.py:214 at the frozen point H*."""
+    op = N.OP_VJP
+
+    def __init__(self, function, h_star: torch.Tensor, batch, grad: torch.Tensor):
+        self.function, self.batch = function, batch
+        self.graph = function.native_graph(batch)
+        self.kind = function.kind
+        self.aux = N.f32(grad.detach())
+        self.upload()
+        self.graph.vjp_prepare(self.kind, h_star.detach())
+
+    def upload(self):
+        self.function.upload_weights(self.aux.device)
+
+    def __call__(self, y: torch.Tensor) -> torch.Tensor:
+        self.upload()
+        return self.graph.vjp_apply(self.kind, y, self.aux)
+
+
+def _result_dict(result, stats: N.SolveStats, rel, abs_, trace, eps, threshold, extra=None):
+    out = {"result": result, "lowest": float(stats.lowest), "nstep": int(stats.nstep), "prot_break": bool(stats.prot_break),
+           "abs_trace": list(abs_), "rel_trace": list(rel), "xest_trace": trace, "eps": eps, "threshold": threshold,
+           # additions (not in the reference dict)
+           "steps_run": int(stats.steps_run), "f_evals": int(stats.f_evals), "launches": int(stats.launches),
+           "stop_reason": int(stats.stop_reason)}
+    if extra:
+        out.update(extra)
+    return out
+
+
+def _require_cuda(x0: torch.Tensor):
+    if not x0.is_cuda:
+        raise RuntimeError("psi_gnn_b200.solver: CUDA tensors required — the solvers have no CPU implementation")
+    if x0.dtype != torch.float32:
+        raise RuntimeError("psi_gnn_b200.solver: fp32 only (the reference allocates its history in fp32, solver.py:134-135)")
+
+
+def _trace_views(buf: Optional[torch.Tensor], count: int, numel: int, shape) -> List[torch.Tensor]:
+    if buf is None:
+        return []
+    return [buf[i, :numel].view(shape) for i in range(count)]
+
+
+def broyden(f: Callable, x0: torch.Tensor, threshold: int, eps: float = 1e-3, stop_mode: str = "rel", ls: bool = False,
+            name: str = "unknown", keep_trace: Optional[bool] = None) -> dict:
+    """Good-Broyden on g(x) = f(x) − x, whole batch as one vector, step length 1 (reference solver.py:116-207)."""
+    if stop_mode != "rel":
+        raise NotImplementedError("psi_gnn_b200.solver.broyden: only stop_mode='rel' (the mode every reference call site uses)")
+    if ls:
+        raise NotImplementedError("psi_gnn_b200.solver.broyden: line search is never enabled by the reference (ls=False)")
+    _require_cuda(x0)
+    lib = N.load()
+    keep = KEEP_TRACE if keep_trace is None else keep_trace
+    x0c = N.f32(x0.detach())
+    shape, numel = x0c.shape, x0c.numel()
+    threshold = int(threshold)
+    stats = N.SolveStats()
+    rel = (c_double * (threshold + 1))()
+    abs_ = (c_double * (threshold + 1))()
+    result = torch.empty_like(x0c)
+    with torch.cuda.device(x0c.device):
+        stream = N.stream_ptr()
+        if isinstance(f, NativeOperator):
+            ws = f.graph.solver(threshold)
+            xtrace = torch.empty(threshold + 1, ws.stride, dtype=torch.float32, device=x0c.device) if keep else None
+            f.upload()
+            N.check(lib.psi_solver_broyden(ws.handle, f.graph.handle, f.kind, f.op, N.ptr(x0c), N.ptr(f.aux), threshold, float(eps),
+                                           N.ptr(result), byref(stats), rel, abs_, N.ptr(xtrace), stream), "psi_solver_broyden")
+        else:
+            ws = SolverWorkspace(numel, max(threshold, 1), x0c.device)
+            xtrace = torch.empty(threshold + 1, ws.stride, dtype=torch.float32, device=x0c.device) if keep else None
+            try:
+                N.check(lib.psi_broyden_begin(ws.handle, N.ptr(x0c), threshold, float(eps), N.ptr(xtrace), stream), "psi_broyden_begin")
+                # the iterate lives in the workspace; expose it to f as a tensor view without copying
+                xview = _as_tensor(lib.psi_broyden_x(ws.handle), numel, x0c.device).view(shape)
+                fx = N.f32(f(xview.clone()).detach())
+                N.check(lib.psi_broyden_first(ws.handle, N.ptr(fx), stream), "psi_broyden_first")
+                done = c_int(0)
+                n = 0
+                while n < threshold and not done.value:
+                    fx = N.f32(f(xview.clone()).detach())
+                    N.check(lib.psi_broyden_step(ws.handle, N.ptr(fx), byref(done), stream), "psi_broyden_step")
+                    n += 1
+                N.check(lib.psi_broyden_finish(ws.handle, N.ptr(result), byref(stats), rel, abs_, stream), "psi_broyden_finish")
+            finally:
+                torch.cuda.current_stream().synchronize()
+                ws.close()
+        trace = _trace_views(xtrace, int(stats.steps_run) + 1, numel, shape)
+    return _result_dict(result, stats, rel, abs_, trace, eps, threshold)
+
+
+def _as_tensor(dev_ptr: int, numel: int, device) -> torch.Tensor:
+    """zero-copy fp32 view of extension-owned device memory (valid while the workspace lives)."""
+    class _Holder:
+        pass
+    h = _Holder()
+    h.__cuda_array_interface__ = {"shape": (numel,), "typestr": "<f4", "data": (int(dev_ptr), False), "version": 2}
+    return torch.as_tensor(h, device=device)
+
+
+def forward_iteration(f: Callable, z0: torch.Tensor, eps: float = 1.e-5, threshold: int = 50) -> dict:
+    """Picard iteration z ← f(z) with rel = ‖z_prev − z‖/‖z‖ (reference solver.py:301-341)."""
+    _require_cuda(z0)
+    lib = N.load()
+    z0c = N.f32(z0.detach())
+    threshold = int(threshold)
+    if isinstance(f, NativeOperator) and f.op == N.OP_LAYER:
+        stats = N.SolveStats()
+        rel = (c_double * (threshold + 1))()
+        abs_ = (c_double * (threshold + 1))()
+        result = torch.empty_like(z0c)
+        with torch.cuda.device(z0c.device):
+            ws = f.graph.solver(threshold)
+            f.upload()
+            N.check(lib.psi_solver_picard(ws.handle, f.graph.handle, f.kind, N.ptr(z0c), N.ptr(f.aux), threshold, float(eps), N.ptr(result),
+                                          byref(stats), rel, abs_, N.stream_ptr()), "psi_solver_picard")
+        n = int(stats.f_evals)
+        out = _result_dict(result, stats, list(rel)[:n], list(abs_)[:n], [], eps, threshold)
+        out.pop("prot_break")
+        return out
+    # generic operator: the loop is two torch reductions per step; kept on the device (no .item()), as in the reference
+    z_prev, z = z0c, f(z0c)
+    abs_tr = [torch.linalg.norm(z_prev - z)]
+    rel_tr = [abs_tr[-1] / torch.linalg.norm(z)]
+    trace = [z0c, z]
+    it = 0
+    while rel_tr[-1] > eps and it < threshold:
+        z_prev, z = z, f(z)
+        it += 1
+        abs_tr.append(torch.linalg.norm(z_prev - z))
+        rel_tr.append(abs_tr[-1] / torch.linalg.norm(z))
+        trace.append(z)
+    return {"result": z, "lowest": rel_tr[-1], "abs_trace": abs_tr, "rel_trace": rel_tr, "xest_trace": trace, "nstep": it,
+            "eps": eps, "threshold": threshold}
+
+
+def anderson(f: Callable, x0: torch.Tensor, m: int = 2, lam: float = 1e-4, threshold: int = 50, eps: float = 1e-3,
+             stop_mode: str = "rel", beta: float = 1.0, **kwargs) -> dict:
+    """Anderson acceleration (reference solver.py:215-293); native loop for :class:`LayerOperator`."""
+    if stop_mode != "rel":
+        raise NotImplementedError("psi_gnn_b200.solver.anderson: only stop_mode='rel'")
+    _require_cuda(x0)
+    if not (isinstance(f, NativeOperator) and f.op == N.OP_LAYER):
+        raise NotImplementedError("psi_gnn_b200.solver.anderson: runs on the fused layer operator only "
+                                  "(pass the LayerOperator DeepEquilibrium builds)")
+    lib = N.load()
+    x0c = N.f32(x0.detach())
+    threshold = int(threshold)
+    stats = N.SolveStats()
+    rel = (c_double * (threshold + 1))()
+    abs_ = (c_double * (threshold + 1))()
+    result = torch.empty_like(x0c)
+    with torch.cuda.device(x0c.device):
+        ws = f.graph.solver(threshold)
+        f.upload()
+        N.check(lib.psi_solver_anderson(ws.handle, f.graph.handle, f.kind, N.ptr(x0c), N.ptr(f.aux), int(m), float(lam), threshold,
+                                        float(eps), float(beta), N.ptr(result), byref(stats), rel, abs_, N.stream_ptr()),
+                "psi_solver_anderson")
+    n = max(threshold - 2, 0)
+    return _result_dict(result, stats, list(rel)[:n], list(abs_)[:n], [], eps, threshold)
+
+
+def newton(f, z0, eps, threshold):
+    raise NotImplementedError("psi_gnn_b200.solver.newton: the reference's dense-Jacobian toy solver (solver.py:343-366) is "
+                              "not part of the accelerated path")

@@ -1,0 +1,165 @@
+"""Packing of ``nn.Module`` parameters into the layer-constant block of ``csrc/weights.cuh``.
+
+The block is a flat fp32 vector in the exact field order of ``struct LayerWeights``; fields a layer
+variant does not use stay zero.  Key names are the reference's ``state_dict`` keys
+(dirichlet/psignn/model.py:263-277, mixed/psignn/model.py:196-214, dirichlet/dss/model.py:59-104,
+dirichlet/dsgps/model.py:48-131), so shipped checkpoints pack without renaming.
+"""
+from __future__ import annotations
+
+from typing import Dict, Mapping, Optional
+
+import torch
+
+D = 10
+# (field name, number of floats) in struct order
+_EDGE = [("W1i", D * D), ("W1j", D * D), ("W1a", D * 3), ("b1", D), ("W2", D * D), ("b2", D)]
+FIELDS = (
+    [("to." + n, s) for n, s in _EDGE] + [("from." + n, s) for n, s in _EDGE] + [("neu." + n, s) for n, s in _EDGE]
+    + [("gate_w", 33), ("gate_b", 1),
+       ("up_W1", D * 33), ("up_b1", D), ("up_W2", D * D), ("up_b2", D),
+       ("un_W1", D * 25), ("un_b1", D), ("un_W2", D * D), ("un_b2", D),
+       ("ln_g", D), ("ln_b", D),
+       ("gz_W", D * 32), ("gz_b", D), ("gr_W", D * 32), ("gr_b", D), ("gc_W", D * 32), ("gc_b", D),
+       ("enc_W1", D), ("enc_b1", D), ("enc_W2", D * D), ("enc_b2", D),
+       ("dec_W1", D * D), ("dec_b1", D), ("dec_W2", D), ("dec_b2", 1),
+       ("dss_alpha", 1), ("pad", 2)]
+)
+OFFSETS: Dict[str, int] = {}
+_o = 0
+for _n, _s in FIELDS:
+    OFFSETS[_n] = _o
+    _o += _s
+TOTAL_FLOATS = _o          # 3168; checked against psi_weights_floats() at load time
+
+
+def _put(blob: torch.Tensor, name: str, t: torch.Tensor, rows: Optional[int] = None, width: Optional[int] = None):
+    """write ``t`` ([rows, k] with k <= width, or a vector) into field ``name`` (row pitch ``width``)."""
+    off = OFFSETS[name]
+    t = t.detach().to(blob.dtype)
+    if rows is None:
+        blob[off:off + t.numel()] = t.reshape(-1)
+    else:
+        view = blob[off:off + rows * width].view(rows, width)
+        view[:, :t.shape[1]] = t
+
+
+def _edge(blob: torch.Tensor, slot: str, P: Mapping[str, torch.Tensor], prefix: str):
+    """``Phi`` edge MLP: Linear(2d+A, d) → ReLU → Linear(d, d); first layer split by input block."""
+    W1 = P[prefix + ".0.weight"]
+    _put(blob, slot + ".W1i", W1[:, :D], D, D)
+    _put(blob, slot + ".W1j", W1[:, D:2 * D], D, D)
+    _put(blob, slot + ".W1a", W1[:, 2 * D:], D, 3)
+    _put(blob, slot + ".b1", P[prefix + ".0.bias"])
+    _put(blob, slot + ".W2", P[prefix + ".2.weight"], D, D)
+    _put(blob, slot + ".b2", P[prefix + ".2.bias"])
+
+
+def _autoencoder(blob: torch.Tensor, P: Mapping[str, torch.Tensor], prefix: str = "autoencoder"):
+    e, d = prefix + ".encoder.mlp.mlp", prefix + ".decoder.mlp.mlp"
+    if e + ".0.weight" in P:
+        _put(blob, "enc_W1", P[e + ".0.weight"].reshape(-1))
+        _put(blob, "enc_b1", P[e + ".0.bias"])
+        _put(blob, "enc_W2", P[e + ".2.weight"], D, D)
+        _put(blob, "enc_b2", P[e + ".2.bias"])
+    if d + ".0.weight" in P:
+        _decoder(blob, P, d)
+
+
+def _decoder(blob: torch.Tensor, P: Mapping[str, torch.Tensor], d: str):
+    _put(blob, "dec_W1", P[d + ".0.weight"], D, D)
+    _put(blob, "dec_b1", P[d + ".0.bias"])
+    _put(blob, "dec_W2", P[d + ".2.weight"].reshape(-1))
+    _put(blob, "dec_b2", P[d + ".2.bias"])
+
+
+def _check(P: Mapping[str, torch.Tensor], key: str):
+    if P[key].shape[0] != D:
+        raise RuntimeError("psi_gnn_b200: the native kernels are built for latent_dim = 10 (got %d)" % P[key].shape[0])
+
+
+def pack_psignn(P: Mapping[str, torch.Tensor], mixed: bool, device, f_prefix: str = "deqdss.f", layer: int = 0) -> torch.Tensor:
+    """PSI-GNN layer (+ autoencoder if present in ``P``)."""
+    blob = torch.zeros(TOTAL_FLOATS, dtype=torch.float32, device=device)
+    f = f_prefix
+    _check(P, f"{f}.phi_to_list.{layer}.mlp.mlp.2.weight")
+    _edge(blob, "to", P, f"{f}.phi_to_list.{layer}.mlp.mlp")
+    _edge(blob, "from", P, f"{f}.phi_from_list.{layer}.mlp.mlp")
+    _put(blob, "gate_w", P[f"{f}.alpha.0.weight"].reshape(-1))
+    _put(blob, "gate_b", P[f"{f}.alpha.0.bias"])
+    _put(blob, "up_W1", P[f"{f}.update_list.{layer}.mlp.0.weight"], D, 33)
+    _put(blob, "up_b1", P[f"{f}.update_list.{layer}.mlp.0.bias"])
+    _put(blob, "up_W2", P[f"{f}.update_list.{layer}.mlp.2.weight"], D, D)
+    _put(blob, "up_b2", P[f"{f}.update_list.{layer}.mlp.2.bias"])
+    _put(blob, "ln_g", P[f"{f}.laynorm.weight"])
+    _put(blob, "ln_b", P[f"{f}.laynorm.bias"])
+    if mixed:
+        _edge(blob, "neu", P, f"{f}.phi_neumann.mlp.mlp")
+        _put(blob, "un_W1", P[f"{f}.update_neumann.mlp.0.weight"], D, 25)
+        _put(blob, "un_b1", P[f"{f}.update_neumann.mlp.0.bias"])
+        _put(blob, "un_W2", P[f"{f}.update_neumann.mlp.2.weight"], D, D)
+        _put(blob, "un_b2", P[f"{f}.update_neumann.mlp.2.bias"])
+    _autoencoder(blob, P)
+    return blob
+
+
+def pack_dss(P: Mapping[str, torch.Tensor], k: int, alpha: float, device) -> torch.Tensor:
+    """k-th DSS layer: Phi_to/Phi_from (edge attr = normalised a_ij), Psi, Decoder_k (dirichlet/dss/model.py:83-104)."""
+    blob = torch.zeros(TOTAL_FLOATS, dtype=torch.float32, device=device)
+    _check(P, f"phi_to_list.{k}.mlp.mlp.2.weight")
+    _edge(blob, "to", P, f"phi_to_list.{k}.mlp.mlp")
+    _edge(blob, "from", P, f"phi_from_list.{k}.mlp.mlp")
+    _put(blob, "up_W1", P[f"psi_list.{k}.mlp.mlp.0.weight"], D, 33)
+    _put(blob, "up_b1", P[f"psi_list.{k}.mlp.mlp.0.bias"])
+    _put(blob, "up_W2", P[f"psi_list.{k}.mlp.mlp.2.weight"], D, D)
+    _put(blob, "up_b2", P[f"psi_list.{k}.mlp.mlp.2.bias"])
+    if f"decoder_list.{k}.mlp.mlp.0.weight" in P:
+        _decoder(blob, P, f"decoder_list.{k}.mlp.mlp")
+    blob[OFFSETS["dss_alpha"]] = float(alpha)
+    return blob
+
+
+def pack_dsgps(P: Mapping[str, torch.Tensor], device) -> torch.Tensor:
+    """DSGPS recurrent step: Phi_to/Phi_from + z_k, r_k, correction gates (dirichlet/dsgps/model.py:110-131)."""
+    blob = torch.zeros(TOTAL_FLOATS, dtype=torch.float32, device=device)
+    _check(P, "phi_to.mlp.mlp.2.weight")
+    _edge(blob, "to", P, "phi_to.mlp.mlp")
+    _edge(blob, "from", P, "phi_from.mlp.mlp")
+    for slot, key in (("gz", "z_k"), ("gr", "r_k"), ("gc", "correction")):
+        _put(blob, slot + "_W", P[f"{key}.mlp.0.weight"], D, 32)
+        _put(blob, slot + "_b", P[f"{key}.mlp.0.bias"])
+    _autoencoder(blob, P)
+    return blob
+
+
+def named_tensors(module: torch.nn.Module, prefix: str = "") -> Dict[str, torch.Tensor]:
+    """parameters of ``module`` keyed like its ``state_dict`` (optionally under ``prefix``)."""
+    return {(prefix + k): v for k, v in module.named_parameters()}
+
+
+def version_key(P: Mapping[str, torch.Tensor]):
+    """changes whenever a parameter is replaced or modified in place (optimizer step, load_state_dict)."""
+    return tuple((k, v.data_ptr(), v._version) for k, v in P.items())
+
+
+# ---- the process-wide constant bank ---------------------------------------------------------------------
+_UPLOADED = {}      # device index -> key of the block currently in __constant__ memory
+
+
+def upload(blob: torch.Tensor, key) -> None:
+    """stream-ordered copy of a packed block into the layer-constant bank unless ``key`` is already resident."""
+    from . import _native as N
+    dev = blob.device.index if blob.device.index is not None else torch.cuda.current_device()
+    if _UPLOADED.get(dev) == key:
+        return
+    lib = N.load()
+    if lib.psi_weights_floats() != TOTAL_FLOATS:
+        raise RuntimeError("psi_gnn_b200: weights.py layout (%d floats) does not match the extension (%d)"
+                           % (TOTAL_FLOATS, lib.psi_weights_floats()))
+    with torch.cuda.device(blob.device):
+        N.check(lib.psi_weights_upload(N.ptr(blob), TOTAL_FLOATS, N.stream_ptr()), "psi_weights_upload")
+    _UPLOADED[dev] = key
+
+
+def invalidate() -> None:
+    _UPLOADED.clear()

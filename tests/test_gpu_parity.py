@@ -1,0 +1,359 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (ctypes) and through the drop-in modules, against
+the golden vectors produced by the unmodified reference (tests/golden, oracle/make_golden.py).
+
+Tolerances follow SURVEY §8c: rel L2 ≤ 1e-5 for single applications (f, VJP, residual, encoder/decoder) and for
+teacher-forced quasi-Newton steps (against the fp64 evaluation of the reference formulas on the same fp32 inputs, with
+the reference's own fp32 deviation as floor); free-running solves are compared on the early trajectory, the stopping
+statistics and the converged solution band.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import Golden, rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+TOL = 1e-5
+
+
+def _kind(g):
+    from psi_gnn_b200 import _native as N
+    return N.KIND_MIXED if g.mixed else N.KIND_DIRICHLET
+
+
+def test_extension_loaded():
+    from psi_gnn_b200 import _native as N
+    assert N.load().psi_version() >= 100
+
+
+def test_layer_forward_matches_reference(golden):
+    m = golden.model(DEV)
+    b = golden.batch(DEV)
+    h0 = golden.t("h0", DEV)
+    with torch.no_grad():
+        f1 = m.deqdss.f(h0, h0, b)
+        f2 = m.deqdss.f(f1, h0, b)
+    assert rel_err(f1, golden.t("f1")) <= TOL
+    assert rel_err(f2, golden.t("f2")) <= TOL
+    # Dirichlet rows are copied, not computed: bit-exact
+    t = b.tags.reshape(b.num_nodes, -1)
+    d = (t[:, 0] if t.shape[1] == 1 else t[:, 1]) == 1
+    assert torch.equal(f1[d], h0[d])
+
+
+def test_layer_forward_deterministic(golden):
+    m = golden.model(DEV)
+    b = golden.batch(DEV)
+    h0 = golden.t("h0", DEV)
+    with torch.no_grad():
+        a = m.deqdss.f(h0, h0, b)
+        c = m.deqdss.f(h0, h0, b)
+    assert torch.equal(a, c)          # segmented sums, no atomics
+
+
+def test_encoder_decoder(golden):
+    m = golden.model(DEV)
+    b = golden.batch(DEV)
+    h0 = m._encode_native(b.x)
+    assert rel_err(h0, golden.t("h0")) <= TOL
+    u = m._decode_native(golden.t("fw_result", DEV))
+    assert rel_err(u, golden.t("u")) <= TOL
+
+
+def test_residual(golden):
+    m = golden.model(DEV)
+    b = golden.batch(DEV)
+    r = m.residual_loss(golden.t("u", DEV), b)
+    assert abs(r.item() - float(golden["residual"])) <= 1e-5 * abs(float(golden["residual"]))
+    rx = m.residual_loss(b.x, b)
+    assert abs(rx.item() - float(golden["residual_x"])) <= 1e-5 * abs(float(golden["residual_x"]))
+
+
+def test_residual_backward(golden):
+    m = golden.model(DEV)
+    b = golden.batch(DEV)
+    u = golden.t("u", DEV).clone().requires_grad_()
+    m.residual_loss(u, b).backward()
+    row, col = b.edge_index
+    u2 = golden.t("u", DEV).double().requires_grad_()
+    Au = torch.zeros_like(u2).index_add(0, row, b.a_ij.double().reshape(-1, 1) * u2[col])
+    ((Au - b.y.double()) ** 2).mean().backward()
+    assert rel_err(u.grad, u2.grad) <= TOL
+
+
+def test_vjp_matches_reference(golden):
+    from psi_gnn_b200.solver import VjpOperator
+    m = golden.model(DEV)
+    b = golden.batch(DEV)
+    y = golden.t("vjp_y", DEV)
+    op = VjpOperator(m.deqdss.f, golden.t("f2", DEV), b, torch.zeros_like(y))
+    out = op(y)
+    assert rel_err(out, golden.t("vjp_out")) <= TOL
+    # + grad term
+    g = torch.randn_like(y)
+    op2 = VjpOperator(m.deqdss.f, golden.t("f2", DEV), b, g)
+    assert rel_err(op2(y) - g, golden.t("vjp_out")) <= 2 * TOL
+
+
+def test_vjp_is_transpose_of_torch_jvp(golden):
+    """⟨Jᵀy, w⟩ = ⟨y, J w⟩ with J w from a central finite difference of the CUDA layer in the direction w (fp32: loose)."""
+    from psi_gnn_b200.solver import VjpOperator
+    m = golden.model(DEV)
+    b = golden.batch(DEV)
+    h0, H = golden.t("h0", DEV), golden.t("f2", DEV)
+    y = golden.t("vjp_y", DEV)
+    w = torch.randn_like(H)
+    op = VjpOperator(m.deqdss.f, H, b, torch.zeros_like(y))
+    lhs = (op(y).double() * w.double()).sum()
+    # torch differentiable path of the drop-in module (autograd) as independent check of the same operator
+    Hr = H.clone().requires_grad_()
+    with torch.enable_grad():
+        out = m.deqdss.f(Hr, h0, b)
+    rhs = (torch.autograd.grad(out, Hr, y)[0].double() * w.double()).sum()
+    assert abs(lhs - rhs) <= 1e-4 * abs(rhs) + 1e-6
+
+
+def test_forced_quasi_newton_steps(golden_small):
+    """Teacher-forced rank-one updates with the production kernels vs the reference formulas in fp64 on the same inputs."""
+    import ctypes
+    from psi_gnn_b200 import _native as N
+    from psi_gnn_b200.solver import SolverWorkspace
+    g = golden_small
+    lib = N.load()
+    for n in [int(s) for s in g["forced_steps"]]:
+        pre = "forced%d_" % n
+        x, gx, xn, gn = (g.t(pre + k, DEV) for k in ("x", "gx", "xnew", "gnew"))
+        U, V = g.t(pre + "U", DEV).contiguous(), g.t(pre + "V", DEV).contiguous()
+        numel = x.numel()
+        ws = SolverWorkspace(numel, 64, torch.device(DEV))
+        u, v, upd = torch.empty_like(x), torch.empty_like(x), torch.empty_like(x)
+        N.check(lib.psi_broyden_forced_step(ws.handle, n, N.ptr(x), N.ptr(gx), N.ptr(xn), N.ptr(gn), N.ptr(U), N.ptr(V),
+                                            N.ptr(u), N.ptr(v), N.ptr(upd), N.stream_ptr()), "forced")
+        torch.cuda.synchronize()
+        for name, got in (("u", u), ("v", v), ("upd", upd)):
+            truth = g.t(pre + name + "64")
+            ref32 = g.t(pre + name + "32")
+            floor = rel_err(ref32, truth)
+            e = rel_err(got, truth)
+            assert e <= max(TOL, 2 * floor), (n, name, e, floor)
+        ws.close()
+
+
+def test_forward_solve_free_running(golden):
+    m = golden.model(DEV)
+    b = golden.batch(DEV)
+    h0 = golden.t("h0", DEV)
+    out = m.deqdss.inference(h0, b, keep_trace=True)
+    ref_rel = golden["fw_rel_trace"]
+    ref_steps = int(golden["fw_steps_run"])
+    # early trajectory: the first iterates agree to fp32 accuracy
+    for i, key in ((1, "fw_x1"), (2, "fw_x2"), (3, "fw_x3")):
+        assert rel_err(out["xest_trace"][i], golden.t(key)) <= 1e-4
+    k = min(15, ref_steps, out["steps_run"])
+    got = np.asarray(out["rel_trace"][:k])
+    assert np.all(np.abs(got - ref_rel[:k]) <= 2e-2 * ref_rel[:k] + 1e-9)
+    # stopping statistics
+    eps = float(golden["cfg.fw_tol"])
+    assert out["lowest"] < eps
+    assert not out["prot_break"]
+    assert abs(out["nstep"] - int(golden["fw_nstep"])) <= max(3, int(0.25 * int(golden["fw_nstep"])))
+    assert len(out["rel_trace"]) == int(golden["cfg.fw_thres"]) + 1
+    # the fixed point itself: both are eps-accurate solutions of the same contraction
+    u = m._decode_native(out["result"])
+    assert rel_err(u, golden.t("u")) <= 5e-3
+    r = m.residual_loss(u, b).item()
+    assert abs(r - float(golden["residual"])) <= 0.05 * float(golden["residual"]) + 1e-7
+    # and it is a fixed point of the CUDA layer to the requested tolerance
+    with torch.no_grad():
+        fx = m.deqdss.f(out["result"], h0, b)
+    assert float((fx - out["result"]).norm() / fx.norm()) < 1.5 * eps
+
+
+def test_model_inference_matches_reference(golden):
+    m = golden.model(DEV)
+    b = golden.batch(DEV)
+    u = m.inference(b)
+    assert u.shape == (b.num_nodes, 1)
+    assert rel_err(u, golden.t("u")) <= 5e-3
+
+
+def test_broyden_generic_callable_matches_fused(golden):
+    """The step API driven by a Python callable takes the same steps as the fused loop."""
+    from psi_gnn_b200 import solver as S
+    m = golden.model(DEV)
+    b = golden.batch(DEV)
+    h0 = golden.t("h0", DEV)
+    op = S.LayerOperator(m.deqdss.f, h0, b)
+    thr = 40
+    a = S.broyden(op, h0, threshold=thr, eps=1e-30)
+    c = S.broyden(lambda H: op(H), h0, threshold=thr, eps=1e-30)
+    assert a["steps_run"] == c["steps_run"] == thr
+    assert np.allclose(a["rel_trace"][:10], c["rel_trace"][:10], rtol=1e-3)
+    assert rel_err(a["result"], c["result"]) < 1e-2
+
+
+def test_picard_matches_reference(golden):
+    from psi_gnn_b200 import solver as S
+    m = golden.model(DEV)
+    b = golden.batch(DEV)
+    h0 = golden.t("h0", DEV)
+    out = S.forward_iteration(S.LayerOperator(m.deqdss.f, h0, b), h0, eps=1e-4, threshold=60)
+    assert out["nstep"] == int(golden["picard_nstep"])
+    ref = golden["picard_rel_trace"]
+    got = np.asarray(out["rel_trace"])
+    assert got.shape == ref.shape
+    assert np.all(np.abs(got - ref) <= 1e-3 * ref + 1e-9)
+    assert rel_err(out["result"], golden.t("picard_result")) <= 1e-4
+
+
+def test_anderson_matches_reference(golden):
+    from psi_gnn_b200 import solver as S
+    m = golden.model(DEV)
+    b = golden.batch(DEV)
+    h0 = golden.t("h0", DEV)
+    out = S.anderson(S.LayerOperator(m.deqdss.f, h0, b), h0, m=2, threshold=60, eps=1e-4)
+    ref = golden["anderson_rel_trace"]
+    got = np.asarray(out["rel_trace"])
+    assert got.shape == ref.shape
+    k = 8
+    assert np.all(np.abs(got[:k] - ref[:k]) <= 2e-2 * ref[:k] + 1e-9)
+    assert out["lowest"] < 1e-4 or float(golden["anderson_lowest"]) >= 1e-4
+    assert rel_err(out["result"], golden.t("anderson_result")) <= 1e-2
+
+
+def test_training_step_matches_reference(golden, monkeypatch):
+    from psi_gnn_b200 import model as PM
+    m = golden.model(DEV)
+    b = golden.batch(DEV)
+    v = golden.t("train_v", DEV)
+    monkeypatch.setattr(PM.torch, "randn", lambda *a, **k: v.clone())
+    m.train()
+    m.zero_grad()
+    u, loss_dic = m(b)
+    loss = loss_dic["residual_loss"].mean() + 1.0 * loss_dic["jacobian_loss"].mean() + loss_dic["encoder_loss"].mean() + \
+        loss_dic["autoencoder_loss"].mean()
+    loss.backward()
+    monkeypatch.undo()
+    assert rel_err(u.detach(), golden.t("train_u")) <= 5e-3
+    for k in ("residual_loss", "jacobian_loss", "encoder_loss", "autoencoder_loss", "mse_loss", "mse_dirichlet"):
+        ref = float(golden["train_loss." + k])
+        assert abs(loss_dic[k].item() - ref) <= 0.05 * abs(ref) + 1e-7, k
+    bw = m.deqdss.last_backward
+    assert bw is not None and bw["lowest"] < 50 * float(golden["cfg.bw_tol"]) + float(golden["train_bw_lowest"])
+    assert rel_err(bw["result"], golden.t("train_bw_result")) <= 2e-2
+    # parameter gradients: cosine similarity + norm (the backward solve amplifies fp32 noise by 1/(1−ρ))
+    gs, rs = [], []
+    for k, p in m.named_parameters():
+        gs.append((p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1).double().cpu())
+        rs.append(golden.t("train_grad." + k).reshape(-1).double())
+    gvec, rvec = torch.cat(gs), torch.cat(rs)
+    cos = float((gvec @ rvec) / (gvec.norm() * rvec.norm()))
+    assert cos > 0.999, cos
+    assert abs(float(gvec.norm() / rvec.norm()) - 1) < 0.05
+
+
+# ---- edge cases ------------------------------------------------------------------------------------------------
+def _tiny_graph(device, n, edges, mixed=False):
+    from psi_gnn_b200.synthetic import GraphData
+    ei = torch.tensor(edges, dtype=torch.long, device=device).t().contiguous() if edges else torch.zeros(2, 0, dtype=torch.long, device=device)
+    nnz = ei.shape[1]
+    gen = torch.Generator().manual_seed(7)
+    b = GraphData(x=torch.zeros(n, 1, device=device), edge_index=ei,
+                  edge_attr=torch.randn(nnz, 3, generator=gen).to(device), a_ij=torch.randn(nnz, 1, generator=gen).to(device),
+                  y=torch.randn(n, 1, generator=gen).to(device), sol=torch.zeros(n, 1, device=device),
+                  prb_data=torch.randn(n, 2, generator=gen).to(device), tags=torch.zeros(n, 1, device=device))
+    b.num_nodes = n
+    return b
+
+
+def _cpu_f(m, h, h0, b):
+    """independent evaluation of the same layer with torch ops in fp64 on the CPU (module's differentiable path semantics)"""
+    import copy
+    from psi_gnn_b200.synthetic import GraphData
+    m64 = copy.deepcopy(m).double()
+    bc = GraphData()
+    for k in b.keys():
+        t = getattr(b, k)
+        setattr(bc, k, t.double() if t.is_floating_point() else t)
+    bc.num_nodes = b.num_nodes
+    with torch.enable_grad():
+        hh = h.double().requires_grad_()
+        return m64.deqdss.f._forward_torch(hh, h0.double(), bc).detach()
+
+
+def test_empty_graph():
+    g = Golden("dirichlet_seed0")
+    m = g.model(DEV)
+    b = _tiny_graph(DEV, 0, [])
+    h = torch.zeros(0, 10, device=DEV)
+    with torch.no_grad():
+        out = m.deqdss.f(h, h, b)
+    assert out.shape == (0, 10)
+    res = m.deqdss.inference(h, b)
+    assert res["result"].shape == (0, 10)
+
+
+def test_isolated_and_ragged_nodes():
+    """nodes without edges, a hub with degree 40 (ragged slices), self loops only, duplicate edges."""
+    g = Golden("dirichlet_seed0")
+    m = g.model(DEV)
+    n = 70
+    edges = [(i, i) for i in range(n)]
+    edges += [(0, j) for j in range(1, 41)] + [(j, 0) for j in range(1, 41)]        # hub
+    edges += [(50, 51), (51, 50), (50, 51)]                                         # duplicate edge
+    edges += [(64, 33), (33, 64)]                                                   # crosses a 32-node slice boundary
+    b = _tiny_graph(DEV, n, edges)
+    b.tags[5] = 1.0
+    b.tags[64] = 1.0
+    gen = torch.Generator().manual_seed(3)
+    h = torch.randn(n, 10, generator=gen).to(DEV)
+    h0 = torch.randn(n, 10, generator=gen).to(DEV)
+    with torch.no_grad():
+        out = m.deqdss.f(h, h0, b)
+    ref = _cpu_f(m.cpu(), h.cpu(), h0.cpu(), b.to("cpu"))
+    assert rel_err(out, ref) <= TOL
+
+
+def test_cpu_tensors_fail_loudly():
+    g = Golden("dirichlet_seed0")
+    m = g.model("cpu")
+    b = g.batch("cpu")
+    with pytest.raises(RuntimeError):
+        m.inference(b)
+    with pytest.raises(RuntimeError):
+        m.deqdss.f(g.t("h0"), g.t("h0"), b)
+
+
+# ---- size-independent properties at full size ----------------------------------------------------------------------
+def test_large_mesh_properties():
+    """C3-sized batch (256 × ~500 nodes): determinism, Dirichlet clamp, LayerNorm statistics of the free rows, and
+    ⟨Jᵀy, w⟩ = ⟨y, Jw⟩ between the VJP kernels and the autograd path."""
+    from psi_gnn_b200 import synthetic
+    from psi_gnn_b200.solver import VjpOperator
+    g = Golden("dirichlet_ckpt")
+    m = g.model(DEV)
+    one = synthetic.make_batch(8, seed0=100)
+    b = synthetic.collate([one] * 32).to(DEV)           # 256 graphs
+    with torch.no_grad():
+        h0 = m._encode_native(b.x)
+        f1 = m.deqdss.f(h0, h0, b)
+        f1b = m.deqdss.f(h0, h0, b)
+    assert torch.equal(f1, f1b)
+    d = b.tags.reshape(-1) == 1
+    assert torch.equal(f1[d], h0[d])
+    free = f1[~d]
+    gamma, beta = m.deqdss.f.laynorm.weight, m.deqdss.f.laynorm.bias
+    z = (free - beta) / gamma
+    assert float(z.mean(1).abs().max()) < 1e-4
+    # replicated graphs give replicated outputs (no cross-talk between graphs of a batch)
+    n1 = one.num_nodes
+    assert torch.equal(f1[:n1], f1[n1:2 * n1])
+    y, w = torch.randn_like(f1), torch.randn_like(f1)
+    op = VjpOperator(m.deqdss.f, f1, b, torch.zeros_like(y))
+    lhs = (op(y).double() * w.double()).sum()
+    Hr = f1.clone().requires_grad_()
+    with torch.enable_grad():
+        out = m.deqdss.f(Hr, h0, b)
+    rhs = (torch.autograd.grad(out, Hr, y)[0].double() * w.double()).sum()
+    assert abs(lhs - rhs) <= 1e-4 * abs(rhs) + 1e-5
