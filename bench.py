@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""bench.py — PSI-GNN training-step hot path (forward Broyden solve + implicit-adjoint backward solve) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--workload c3|c4|c1]
+
+One step = one training step of ``ModelDEQDSS`` on one batch through the drop-in module API: encoder → no-grad forward
+fixed-point solve → differentiable f(H*) + Jacobian regulariser → decoder → losses → ``loss.backward()`` (implicit
+backward solve inside the hook) → gradient all-reduce (N>1) → clip → two Adam steps.  Default workload = BASELINE.json
+config 3 (256 synthetic ~500-node Poisson meshes per GPU, Dirichlet), weights = the reference's shipped checkpoint
+(tests/golden/dirichlet_ckpt.npz).  Prints ONE JSON line (see README / DESIGN.md §6 for the keys).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+import warnings
+
+warnings.filterwarnings("ignore")
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (family, graphs per GPU, mesh size h, description)
+    "c1": ("dirichlet", 32, 0.075, "C1: PSI-GNN dirichlet training step, batch of 32 synthetic ~500-node 2D triangle Poisson meshes"),
+    "c3": ("dirichlet", 256, 0.075, "C3: PSI-GNN dirichlet training step (Broyden forward + implicit-adjoint backward), batch 256 synthetic ~500-node meshes per GPU"),
+    "c4": ("mixed", 256, 0.037, "C4: PSI-GNN mixed Dirichlet/Neumann training step, batch 256 synthetic ~2k-node meshes per GPU"),
+}
+LR = 1e-6            # end-of-training learning rate (both arms)
+CLIP = 0.1           # launch_local.sh --gradient_clip
+JAC_WEIGHT = 1.0     # launch_local.sh --jac_weight
+
+
+def load_params(family):
+    z = np.load(os.path.join(ROOT, "tests", "golden", "%s_ckpt.npz" % family))
+    P = {k[6:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("param.")}
+    cfg = dict(latent_dim=10, hidden_dim=10, n_layers=1, fw_tol=float(z["cfg.fw_tol"]), fw_thres=int(z["cfg.fw_thres"]),
+               bw_tol=float(z["cfg.bw_tol"]), bw_thres=int(z["cfg.bw_thres"]), path_logs=None)
+    return P, cfg
+
+
+def make_batch(family, n_graphs, h, seed0):
+    from psi_gnn_b200 import synthetic
+    return synthetic.make_batch(n_graphs, seed0=seed0, h=h, mixed=(family == "mixed"), solve=False)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# =====================================================================================================================
+# native arm
+# =====================================================================================================================
+def run_native(args):
+    import torch.distributed as dist
+    from psi_gnn_b200 import _native, parallel
+    from psi_gnn_b200 import model as PM
+
+    rank = int(os.environ.get("RANK", 0))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _native.load()                                              # fail loudly if the extension is missing
+    family, n_graphs, h, desc = WORKLOADS[args.workload]
+    if args.graphs:
+        n_graphs = args.graphs
+    P, cfg = load_params(family)
+    if family == "mixed":
+        from psi_gnn_b200.mixed.psignn import model as M
+        from psi_gnn_b200.mixed.psignn.utilities import solver as S
+    else:
+        from psi_gnn_b200.dirichlet.psignn import model as M
+        from psi_gnn_b200.dirichlet.psignn.utilities import solver as S
+    cfg["solver"] = S.broyden
+    model = M.ModelDEQDSS(cfg)
+    model.load_state_dict(P)
+    model = model.to(dev).train()
+    params = [p for p in model.parameters()]
+    opt_deq = torch.optim.Adam(model.deqdss.parameters(), lr=LR)
+    opt_ae = torch.optim.Adam(model.autoencoder.parameters(), lr=LR)
+
+    host_batch = make_batch(family, n_graphs, h, seed0=rank * n_graphs).pin_memory()
+    dev_batch = host_batch.to(dev)
+    N, nnz = host_batch.num_nodes, host_batch.edge_index.shape[1]
+    h2d = host_batch.nbytes()
+    flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)      # 256 MB > 126 MB L2
+
+    stats = {"fw_steps": 0, "bw_steps": 0, "fw_evals": 0, "bw_evals": 0, "launches": 0}
+
+    def train_step(batch, read_loss):
+        opt_ae.zero_grad(set_to_none=True)
+        opt_deq.zero_grad(set_to_none=True)
+        _, ld = model(batch)
+        loss = ld["residual_loss"].mean() + JAC_WEIGHT * ld["jacobian_loss"].mean() + ld["encoder_loss"].mean() + ld["autoencoder_loss"].mean()
+        loss.backward()
+        parallel.allreduce_gradients(params, world)
+        torch.nn.utils.clip_grad_norm_(params, CLIP)
+        opt_deq.step()
+        opt_ae.step()
+        fw, bw = model.deqdss.last_forward, model.deqdss.last_backward
+        stats["fw_steps"] += fw["steps_run"]; stats["bw_steps"] += bw["steps_run"]
+        stats["fw_evals"] += fw["f_evals"]; stats["bw_evals"] += bw["f_evals"]
+        # native launches: both solves + vjp_prepare (1) + residual (2) + Aᵀr (1)
+        stats["launches"] += fw["launches"] + bw["launches"] + 4
+        return loss.item() if read_loss else None
+
+    def e2e_step():
+        b = host_batch.to(dev, non_blocking=True)               # pinned host → device copy of the step's inputs
+        return train_step(b, True)                              # includes the graph re-layout and the D2H read of the loss
+
+    def timed(fn, k):
+        """K steps, each bracketed by CUDA events on the current stream, L2 flushed between steps (outside the brackets)"""
+        evs = []
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        for _ in range(k):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = sum(a.elapsed_time(b) for a, b in evs)
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident arm --------------------------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        train_step(dev_batch, False)
+    ws = PM.graph_of(dev_batch, model.deqdss.f.kind).solver(max(cfg["fw_thres"], cfg["bw_thres"]))
+    ws.profile(True)
+    for k in stats:
+        stats[k] = 0
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_total = timed(lambda: train_step(dev_batch, False), args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    prof = ws.profile_read()
+    ws.profile(False)
+    run_stats = dict(stats)
+    # ---- end-to-end arm (host buffers, H2D + re-layout + D2H inside the timed region) --------------------------
+    for _ in range(2):
+        e2e_step()
+    ms_e2e = timed(e2e_step, args.steps)
+
+    g = PM.graph_of(dev_batch, model.deqdss.f.kind)
+    E = g.num_offdiag
+    lists = 3 if family == "mixed" else 2
+    sec = ms_total / 1e3
+    graphs_s = world * n_graphs * args.steps / sec
+    iters = run_stats["fw_steps"] + run_stats["bw_steps"]
+    evals = run_stats["fw_evals"] + run_stats["bw_evals"]
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    dom = max(prof, key=lambda k: prof[k]["ms"])
+    d = prof[dom]
+    achieved = d["bytes"] / max(d["ms"], 1e-9) / 1e6            # GB/s
+    kernels = {k: {"launches": v["launches"], "ms_total": round(v["ms"], 3), "avg_us": round(1e3 * v["ms"] / max(v["launches"], 1), 2),
+                   "alg_GBps": round(v["bytes"] / max(v["ms"], 1e-9) / 1e6, 1), "frac_of_peak": round(v["bytes"] / max(v["ms"], 1e-9) / 1e6 / peak, 4)}
+               for k, v in prof.items()}
+    out = {
+        "metric": "PSI-GNN solve graphs/s (training step: Broyden forward solve + implicit-adjoint backward solve)",
+        "value": round(graphs_s, 2), "unit": "graphs/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": round(ms_total / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic P1-FEM Poisson meshes (seeded generator); weights = reference shipped checkpoint",
+        "config": {"workload": desc, "graphs_per_gpu": n_graphs, "nodes_per_gpu": N, "nnz_per_gpu": nnz, "offdiag_edges_per_gpu": E,
+                   "solver": "broyden", "fw_tol": cfg["fw_tol"], "fw_thres": cfg["fw_thres"], "bw_tol": cfg["bw_tol"], "bw_thres": cfg["bw_thres"],
+                   "jac_weight": JAC_WEIGHT, "lr": LR, "parallelism": "graph-sharded dp%d, one NCCL all-reduce of the flat gradient per step" % world,
+                   "l2": "256 MB buffer written between timed steps; the U/V history (GBs) exceeds the 126 MB L2 anyway"},
+        "iterations_per_s": round(world * iters / sec, 1),
+        "edge_msg_updates_per_s": round(world * evals * lists * E / sec, 1),
+        "solver_steps_per_step": {"forward": run_stats["fw_steps"] / args.steps, "backward": run_stats["bw_steps"] / args.steps},
+        "gpu_launches": run_stats["launches"],
+        "e2e": {"value": round(world * n_graphs * args.steps / (ms_e2e / 1e3), 2), "unit": "graphs/s", "ms_per_step": round(ms_e2e / args.steps, 3),
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+        "roofline": {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                     "traffic": None, "peak_source": peak_src, "avg_launch_us": round(1e3 * d["ms"] / max(d["launches"], 1), 2),
+                     "alg_bytes_per_launch": round(d["bytes"] / max(d["launches"], 1), 1)},
+        "kernels": kernels,
+        "clocks": clocks,
+    }
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline(args, family, h, budget_s=25.0)
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# =====================================================================================================================
+# CPU arm: the oracle port of the reference's training step (the reference itself is Python that needs PyG/torch_sparse and
+# /root/reference, neither of which exists on the GPU box)
+# =====================================================================================================================
+def cpu_step_fn(family, h, sample_graphs):
+    from oracle import psignn_oracle as O
+    P, cfg = load_params(family)
+    batch = make_batch(family, sample_graphs, h, seed0=0)
+    params = {k: v.clone() for k, v in P.items()}
+    plist = [torch.nn.Parameter(v) for v in params.values()]
+    opt = torch.optim.Adam(plist, lr=LR)
+    gen = torch.Generator().manual_seed(0)
+
+    def step():
+        cur = {k: p.detach() for k, p in zip(params.keys(), plist)}
+        v = torch.randn(batch.num_nodes, 10, generator=gen)
+        out = O.training_forward_backward(cur, batch, cfg["fw_thres"], cfg["fw_tol"], cfg["bw_thres"], cfg["bw_tol"], v,
+                                          jac_weight=JAC_WEIGHT, mixed=(family == "mixed"))
+        for k, p in zip(params.keys(), plist):
+            p.grad = out["grads"][k]
+        torch.nn.utils.clip_grad_norm_(plist, CLIP)
+        opt.step()
+        fw_steps = len(out["fw"]["xest_trace"]) - 1
+        bw_steps = len(out["bw"]["xest_trace"]) - 1
+        return fw_steps, bw_steps
+
+    return step, batch
+
+
+def cpu_baseline(args, family, h, budget_s):
+    torch.set_flush_denormal(True)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sample = 8
+    step, batch = cpu_step_fn(family, h, sample)
+    step()                                                      # warm-up (library initialisation)
+    t0 = time.perf_counter()
+    n, its = 0, 0
+    while n < 1 or (time.perf_counter() - t0) < budget_s * 0.5:
+        fw, bw = step()
+        n += 1
+        its += fw + bw
+        if time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return {"value": round(sample * n / dt, 4), "unit": "graphs/s", "cores": torch.get_num_threads(), "kind": "port",
+            "iterations_per_s": round(its / dt, 2),
+            "sample": "%d training steps on a batch of %d of the workload's meshes (N=%d nodes), oracle port of the reference "
+                      "training step, torch %s CPU, %d threads" % (n, sample, batch.num_nodes, torch.__version__, torch.get_num_threads())}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    torch.set_flush_denormal(True)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    family, n_graphs, h, desc = WORKLOADS[args.workload]
+    sample = 8
+    step, batch = cpu_step_fn(family, h, sample)
+    for _ in range(max(1, min(args.warmup, 1))):               # one warm-up pass is enough on the CPU (no clocks to ramp)
+        step()
+    t0 = time.perf_counter()
+    its = 0
+    for _ in range(args.steps):
+        fw, bw = step()
+        its += fw + bw
+    dt = time.perf_counter() - t0
+    val = sample * args.steps / dt
+    sample_txt = ("each step = one training step on a batch of %d of the workload's meshes (N=%d nodes); oracle port of the reference "
+                  "(the Python reference needs PyG/torch_sparse and cannot travel to the GPU box)" % (sample, batch.num_nodes))
+    out = {"impl": "reference", "metric": "PSI-GNN solve graphs/s (training step: Broyden forward solve + implicit-adjoint backward solve)",
+           "value": round(val, 4), "unit": "graphs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": 1,
+           "ms_per_step": round(1e3 * dt / args.steps, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+           "data": "synthetic P1-FEM Poisson meshes (seeded generator); weights = reference shipped checkpoint",
+           "config": {"workload": desc, "sample_graphs_per_step": sample},
+           "iterations_per_s": round(its / dt, 2),
+           "cpu_baseline": {"value": round(val, 4), "unit": "graphs/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample_txt},
+           "e2e": {"value": round(val, 4), "unit": "graphs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--graphs", type=int, default=0, help="override graphs per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -45,6 +45,8 @@ SIGNATURES = {
     "psi_solver_destroy": (c_int, [c_void_p]),
     "psi_solver_bytes": (c_int64, [c_void_p]),
     "psi_solver_stride": (c_int64, [c_void_p]),
+    "psi_solver_profile": (c_int, [c_void_p, c_int]),
+    "psi_solver_profile_read": (c_int, [c_void_p, POINTER(c_double)]),
     "psi_solver_broyden": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_double, c_void_p,
                                    POINTER(SolveStats), POINTER(c_double), POINTER(c_double), c_void_p, c_void_p]),
     "psi_broyden_begin": (c_int, [c_void_p, c_void_p, c_int, c_double, c_void_p, c_void_p]),

@@ -284,6 +284,8 @@ extern "C" int psi_decode(int64_t num_nodes, const float* dev_h, float* dev_u, v
 // ================================================================================================
 // solver workspace
 // ================================================================================================
+#define PROF_CLASSES 4   // 0 operator (layer / VJP pair), 1 k_qn_dots, 2 k_qn_axpy, 3 k_qn_fin2
+
 struct psi_solver {
     int64_t numel = 0, stride = 0;        // stride = numel rounded up to whole QN_CHUNKs (tail kept at zero)
     int cap = 0;                          // largest threshold the workspace can hold
@@ -301,7 +303,43 @@ struct psi_solver {
     // state of the step API
     int threshold = 0; double eps = 0.0; int n = 0; int launches = 0; int f_evals = 0; bool active = false;
     float* xtrace = nullptr; int norm_blocks = 0;
+    // optional per-kernel-class timing with CUDA events on the launching stream (psi_solver_profile)
+    int profile = 0;
+    std::vector<cudaEvent_t> ev;          // [((step * PROF_CLASSES) + cls) * 2 + {begin,end}]
+    std::vector<double> ev_bytes;         // algorithmic bytes of the launch(es) bracketed by the pair
+    double prof_ms[PROF_CLASSES] = {0, 0, 0, 0}, prof_bytes[PROF_CLASSES] = {0, 0, 0, 0};
+    int64_t prof_launches[PROF_CLASSES] = {0, 0, 0, 0};
+    double op_bytes = 0.0;                // algorithmic bytes of one operator evaluation of the current solve
 };
+
+static void prof_begin(psi_solver* s, int step, int cls, double bytes, cudaStream_t st) {
+    if (!s->profile) return;
+    const size_t i = ((size_t)step * PROF_CLASSES + cls) * 2;
+    if (i + 1 >= s->ev.size()) return;
+    s->ev_bytes[i / 2] = bytes;
+    cudaEventRecord(s->ev[i], st);
+}
+static void prof_end(psi_solver* s, int step, int cls, cudaStream_t st) {
+    if (!s->profile) return;
+    const size_t i = ((size_t)step * PROF_CLASSES + cls) * 2;
+    if (i + 1 >= s->ev.size()) return;
+    cudaEventRecord(s->ev[i + 1], st);
+}
+// fold the event pairs of steps 0..last_step into the running totals (stream must be synchronised)
+static void prof_collect(psi_solver* s, int last_step) {
+    if (!s->profile) return;
+    for (int step = 0; step <= last_step; ++step)
+        for (int cls = 0; cls < PROF_CLASSES; ++cls) {
+            const size_t i = ((size_t)step * PROF_CLASSES + cls) * 2;
+            if (i + 1 >= s->ev.size() || s->ev_bytes[i / 2] < 0.0) continue;
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, s->ev[i], s->ev[i + 1]) == cudaSuccess) {
+                s->prof_ms[cls] += ms; s->prof_bytes[cls] += s->ev_bytes[i / 2]; s->prof_launches[cls] += 1;
+            }
+        }
+    (void)cudaGetLastError();
+    std::fill(s->ev_bytes.begin(), s->ev_bytes.end(), -1.0);
+}
 
 static int solver_alloc(psi_solver* s, void** p, size_t bytes) {
     PSI_CK(cudaMalloc(p, bytes));
@@ -361,12 +399,33 @@ extern "C" int psi_solver_destroy(psi_solver_t* s) {
         if (s->hist.V[i]) cudaFree(s->hist.V[i]);
     }
     if (s->h_ctrl) cudaFreeHost(s->h_ctrl);
+    for (cudaEvent_t e : s->ev) cudaEventDestroy(e);
     delete s;
     return 0;
 }
 
 extern "C" int64_t psi_solver_bytes(const psi_solver_t* s) { return s ? s->bytes : 0; }
 extern "C" int64_t psi_solver_stride(const psi_solver_t* s) { return s ? s->stride : 0; }
+
+extern "C" int psi_solver_profile(psi_solver_t* s, int enable) {
+    if (s == nullptr) PSI_FAIL("psi_solver_profile: null solver");
+    if (enable && s->ev.empty()) {
+        const size_t n = (size_t)(s->cap + 2) * PROF_CLASSES * 2;
+        s->ev.resize(n);
+        for (size_t i = 0; i < n; ++i) PSI_CK(cudaEventCreate(&s->ev[i]));
+        s->ev_bytes.assign(n / 2, -1.0);
+    }
+    s->profile = enable ? 1 : 0;
+    if (enable)
+        for (int c = 0; c < PROF_CLASSES; ++c) { s->prof_ms[c] = 0; s->prof_bytes[c] = 0; s->prof_launches[c] = 0; }
+    return 0;
+}
+
+extern "C" int psi_solver_profile_read(const psi_solver_t* s, double out[12]) {
+    if (s == nullptr || out == nullptr) PSI_FAIL("psi_solver_profile_read: null argument");
+    for (int c = 0; c < PROF_CLASSES; ++c) { out[3 * c] = (double)s->prof_launches[c]; out[3 * c + 1] = s->prof_ms[c]; out[3 * c + 2] = s->prof_bytes[c]; }
+    return 0;
+}
 
 // make sure history vector index k (0-based) has storage
 static int hist_ensure(psi_solver* s, int k) {
@@ -417,7 +476,10 @@ static int qn_update(psi_solver* s, int n, int norm_blocks, cudaStream_t st) {
     if (hist_ensure(s, n - 1)) return -1;
     if (nhist > 0) {
         dim3 grid(s->num_chunks, (nhist + QN_KTILE - 1) / QN_KTILE);
+        const double vec = (double)s->numel * 4.0;
+        prof_begin(s, n, 1, (2.0 * nhist + 3.0) * vec, st);
         k_qn_dots<<<grid, QN_THREADS, 0, st>>>(s->hist, nhist, s->dx, s->dg, s->g, s->partial, s->num_chunks, &s->ctrl->done);
+        prof_end(s, n, 1, st);
         PSI_CK_LAUNCH();
         s->launches += 1;
     }
@@ -426,12 +488,16 @@ static int qn_update(psi_solver* s, int n, int norm_blocks, cudaStream_t st) {
                                           s->rel_trace, s->abs_trace, n, s->eps, 1e3 * PSI_D, s->threshold);
     PSI_CK_LAUNCH();
     const size_t sh = (size_t)3 * std::max(nhist, 1) * sizeof(float);
+    prof_begin(s, n, 2, (2.0 * nhist + 6.0) * (double)s->numel * 4.0, st);
     k_qn_axpy<<<s->axpy_ctas, QN_THREADS, sh, st>>>(s->hist, nhist, n, s->coef, s->cap, s->dx, s->dg, s->g, s->x, s->best, s->partial2,
                                                     s->num_chunks, s->ctrl);
+    prof_end(s, n, 2, st);
     PSI_CK_LAUNCH();
     float* xt = s->xtrace ? s->xtrace + (int64_t)(n + 1) * s->stride : nullptr;
     if (n >= s->threshold) xt = nullptr;
+    prof_begin(s, n, 3, 7.0 * (double)s->numel * 4.0, st);
     k_qn_fin2<<<s->axpy_ctas, QN_THREADS, 0, st>>>(s->hist, n, s->dx, s->g, s->x, s->partial2, s->axpy_ctas, xt, s->ctrl, s->num_chunks);
+    prof_end(s, n, 3, st);
     PSI_CK_LAUNCH();
     s->launches += 3;
     return 0;
@@ -447,6 +513,20 @@ static int qn_finish(psi_solver* s, float* result, psi_solve_stats_t* stats, dou
     if (qn_poll(s, st)) return -1;
     const QnCtrl& c = *s->h_ctrl;
     const int ran = c.nstep;
+    // the last executed step stopped before its rank-one update unless it ran out of steps: its axpy/fin2 pairs are no-ops
+    if (s->profile) {
+        const int stopped = (c.stop_reason != 0) ? ran : ran + 1;
+        for (int cls = 2; cls < PROF_CLASSES; ++cls) {
+            const size_t i = ((size_t)stopped * PROF_CLASSES + cls);
+            if (stopped <= s->cap + 1 && i < s->ev_bytes.size()) s->ev_bytes[i] = -1.0;
+        }
+        for (int step = ran + 1; step <= s->cap + 1; ++step)
+            for (int cls = 0; cls < PROF_CLASSES; ++cls) {
+                const size_t i = ((size_t)step * PROF_CLASSES + cls);
+                if (i < s->ev_bytes.size()) s->ev_bytes[i] = -1.0;
+            }
+        prof_collect(s, ran);
+    }
     if (result != nullptr && s->numel > 0)
         PSI_CK(cudaMemcpyAsync(result, s->best, s->numel * sizeof(float), cudaMemcpyDeviceToDevice, st));
     if (stats != nullptr) {
@@ -476,13 +556,29 @@ static int qn_finish(psi_solver* s, float* result, psi_solve_stats_t* stats, dou
 
 static int op_eval(psi_solver* s, psi_graph* g, int kind, int op, const float* aux, float* out, cudaStream_t st) {
     SolverEpi E{s->g, s->dg, s->norm_part, &s->ctrl->done};
+    const int step = s->f_evals;          // evaluation 0 yields g_0, evaluation n belongs to step n
     s->f_evals += 1;
+    int rc;
+    prof_begin(s, step, 0, s->op_bytes, st);
     if (op == PSI_OP_LAYER) {
         s->launches += 1;
-        return launch_layer<true>(g, kind, s->x, aux, out, E, st);
+        rc = launch_layer<true>(g, kind, s->x, aux, out, E, st);
+    } else {
+        s->launches += 2;
+        rc = launch_vjp<true>(g, kind, s->x, aux, out, E, st);
     }
-    s->launches += 2;
-    return launch_vjp<true>(g, kind, s->x, aux, out, E, st);
+    prof_end(s, step, 0, st);
+    return rc;
+}
+
+// algorithmic bytes of one operator evaluation inside a solve: every array the kernel must touch once
+static double operator_bytes(const psi_graph* g, int kind, int op) {
+    const double N = (double)g->N, E = (double)g->E, Nd = (double)g->n_dir;
+    const int lists = (kind == PSI_KIND_MIXED) ? 3 : 2;
+    if (op == PSI_OP_LAYER)   // h read + tag + prb + 2 slice offsets/32 ; records 16 B per edge per list ; h0 on Dirichlet rows ; epilogue g, δg
+        return N * (40.0 + 1.0 + 4.0 * g->prb_dim + 0.5) + lists * E * 16.0 + Nd * 40.0 + N * 120.0 + (kind == PSI_KIND_MIXED ? N * 8.0 : 0.0);
+    // VJP: phase A 253 B read + 120 B written per node; phase B {j, mask} 8 B per edge per list + S̄ 80 + D 40 + grad 40 + y 40 + epilogue 120
+    return N * (253.0 + 120.0) + 2.0 * E * 8.0 + N * (80.0 + 40.0 + 40.0 + 40.0 + 120.0);
 }
 
 extern "C" int psi_solver_broyden(psi_solver_t* s, psi_graph_t* g, int kind, int op, const float* dev_x0, const float* dev_aux,
@@ -497,6 +593,7 @@ extern "C" int psi_solver_broyden(psi_solver_t* s, psi_graph_t* g, int kind, int
     if (g->N > 0 && dev_aux == nullptr && !(op == PSI_OP_LAYER && kind == PSI_KIND_DSS)) PSI_FAIL("psi_solver_broyden: null aux (h0 / grad)");
     cudaStream_t st = as_stream(stream);
     if (qn_begin(s, dev_x0, threshold, eps, dev_xtrace, st)) return -1;
+    s->op_bytes = operator_bytes(g, kind, op);
     const int norm_blocks = (int)node_grid(g->N);
     if (g->N > 0) {
         if (op_eval(s, g, kind, op, dev_aux, nullptr, st)) return -1;        // g_0 = op(x_0) − x_0

@@ -150,9 +150,11 @@ def test_forward_solve_free_running(golden):
     # early trajectory: the first iterates agree to fp32 accuracy
     for i, key in ((1, "fw_x1"), (2, "fw_x2"), (3, "fw_x3")):
         assert rel_err(out["xest_trace"][i], golden.t(key)) <= 1e-4
-    k = min(15, ref_steps, out["steps_run"])
+    # the secant updates amplify fp32 reordering noise chaotically after ~10-30 steps (the reference itself
+    # moves by O(1) in the residual trace under an edge permutation), so only the first 10 steps are held tight
+    k = min(10, ref_steps, out["steps_run"])
     got = np.asarray(out["rel_trace"][:k])
-    assert np.all(np.abs(got - ref_rel[:k]) <= 2e-2 * ref_rel[:k] + 1e-9)
+    assert np.all(np.abs(got - ref_rel[:k]) <= 1e-3 * ref_rel[:k] + 1e-9)
     # stopping statistics
     eps = float(golden["cfg.fw_tol"])
     assert out["lowest"] < eps

@@ -1,0 +1,118 @@
+"""CPU: host-side logic — the C-ABI library loads and exports every symbol the header declares, the weight packing
+matches the struct layout, the drop-in modules keep the reference's state_dict keys, and nothing silently runs on CPU."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, Golden
+
+
+def test_library_exports_every_declared_symbol():
+    from psi_gnn_b200 import _native as N
+    from psi_gnn_b200 import build as B
+    B.build()
+    lib = ctypes.CDLL(N.lib_path())
+    header = open(os.path.join(ROOT, "include", "psignn_b200.h")).read()
+    body = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(psi_[a-z0-9_]+)\s*\(", body))
+    assert len(declared) >= 25
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert declared == set(N.SIGNATURES), declared ^ set(N.SIGNATURES)
+    assert lib.psi_version() >= 100
+
+
+def test_weight_block_layout():
+    from psi_gnn_b200 import _native as N
+    from psi_gnn_b200 import weights as W
+    assert N.load().psi_weights_floats() == W.TOTAL_FLOATS == 3168
+    g = Golden("mixed_seed0")
+    P = g.params()
+    blob = W.pack_psignn(P, True, "cpu")
+    o = W.OFFSETS
+    W1 = P["deqdss.f.phi_from_list.0.mlp.mlp.0.weight"]
+    assert torch.equal(blob[o["from.W1j"]:o["from.W1j"] + 100].view(10, 10), W1[:, 10:20])
+    assert torch.equal(blob[o["from.W1a"]:o["from.W1a"] + 30].view(10, 3), W1[:, 20:23])
+    up = P["deqdss.f.update_list.0.mlp.0.weight"]
+    assert torch.equal(blob[o["up_W1"]:o["up_W1"] + 330].view(10, 33), up)
+    un = P["deqdss.f.update_neumann.mlp.0.weight"]
+    assert torch.equal(blob[o["un_W1"]:o["un_W1"] + 250].view(10, 25), un)
+    assert torch.equal(blob[o["dec_W2"]:o["dec_W2"] + 10], P["autoencoder.decoder.mlp.mlp.2.weight"].reshape(-1))
+    # dirichlet: prb width 2 → the 33rd column of the gate/update rows stays zero
+    gd = Golden("dirichlet_seed0")
+    bd = W.pack_psignn(gd.params(), False, "cpu")
+    assert float(bd[o["up_W1"]:o["up_W1"] + 330].view(10, 33)[:, 32].abs().max()) == 0.0
+    assert float(bd[o["neu.W1i"]:o["gate_w"]].abs().max()) == 0.0
+
+
+def test_state_dict_keys_match_reference_checkpoints(golden):
+    m = golden.model("cpu")
+    assert set(m.state_dict().keys()) == set(golden.params().keys())
+    n_params = sum(p.numel() for p in m.parameters())
+    assert n_params == (2175 if golden.mixed else 1444)       # reference logs/model_config.csv
+
+
+def test_constructor_signatures():
+    import inspect
+    from psi_gnn_b200.dirichlet.psignn import model as M
+    from psi_gnn_b200.dirichlet.psignn.utilities import solver as S
+    assert list(inspect.signature(M.Function.__init__).parameters)[1:] == ["n_layers", "latent_dim", "edge_features_dim",
+                                                                            "second_member_dim", "activation"]
+    assert list(inspect.signature(M.DeepEquilibrium.__init__).parameters)[1:] == ["function", "config_deq"]
+    assert list(inspect.signature(S.broyden).parameters)[:7] == ["f", "x0", "threshold", "eps", "stop_mode", "ls", "name"]
+    assert list(inspect.signature(S.anderson).parameters)[:8] == ["f", "x0", "m", "lam", "threshold", "eps", "stop_mode", "beta"]
+    assert list(inspect.signature(S.forward_iteration).parameters) == ["f", "z0", "eps", "threshold"]
+
+
+def test_no_cpu_fallback(golden):
+    m = golden.model("cpu")
+    b = golden.batch("cpu")
+    h0 = golden.t("h0")
+    with pytest.raises(RuntimeError):
+        m.inference(b)
+    with pytest.raises(RuntimeError):
+        m.deqdss.f(h0, h0, b)
+    with pytest.raises(RuntimeError):
+        m.residual_loss(golden.t("u"), b)
+    from psi_gnn_b200 import solver as S
+    with pytest.raises(RuntimeError):
+        S.broyden(lambda x: x, h0, threshold=3, eps=1e-3)
+    with pytest.raises(RuntimeError):
+        S.forward_iteration(lambda x: x, h0)
+
+
+def test_product_never_imports_oracle():
+    import subprocess
+    import sys
+    code = ("import sys; sys.path.insert(0, %r); import psi_gnn_b200.model, psi_gnn_b200.solver, psi_gnn_b200.graph, "
+            "psi_gnn_b200.dirichlet.psignn.model, psi_gnn_b200.mixed.psignn.model; "
+            "assert not any(k == 'oracle' or k.startswith('oracle.') for k in sys.modules), 'oracle imported'") % ROOT
+    subprocess.run([sys.executable, "-c", code], check=True)
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "psi_gnn_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_synthetic_generator_contract():
+    from psi_gnn_b200 import synthetic
+    b = synthetic.make_batch(2, seed0=3, h=0.15)
+    n, nnz = b.num_nodes, b.edge_index.shape[1]
+    assert b.x.shape == (n, 1) and b.y.shape == (n, 1) and b.prb_data.shape == (n, 2) and b.tags.shape == (n, 1)
+    assert b.edge_attr.shape == (nnz, 3) and b.a_ij.shape == (nnz, 1) and b.edge_index.dtype == torch.int64
+    # Dirichlet rows of A hold only the diagonal (bc.apply), so A u = b there means u = g
+    row, col = b.edge_index
+    d = torch.where(b.tags.reshape(-1) == 1)[0]
+    for i in d[:5].tolist():
+        sel = row == i
+        assert int(sel.sum()) == 1 and int(col[sel][0]) == i and float(b.a_ij[sel][0]) == 1.0
+    parts = synthetic.split_graphs(b, 2)
+    assert sum(p.num_nodes for p in parts) == n
+    m = synthetic.make_batch(1, seed0=3, h=0.15, mixed=True)
+    assert m.tags.shape[1] == 3 and m.prb_data.shape[1] == 3 and m.unit_normal_vector.shape == (m.num_nodes, 2)
+    assert float(m.tags.sum(1).min()) == 1.0 and float(m.tags.sum(1).max()) == 1.0
