@@ -29,7 +29,7 @@ class NativeGraph:
             raise RuntimeError("psi_gnn_b200: edge_index must have shape [2, nnz]")
         nnz = int(edge_index.shape[1])
         ei = edge_index.contiguous()
-        attr = N.f32(edge_attr.reshape(nnz, -1))
+        attr = N.f32(edge_attr.reshape(nnz, -1)) if nnz > 0 else torch.zeros(0, 3, dtype=torch.float32, device=ei.device)
         aij = N.f32(a_ij.reshape(-1)) if a_ij is not None else None
         if aij is not None and aij.numel() != nnz:
             raise RuntimeError("psi_gnn_b200: a_ij must have one entry per edge")
@@ -40,19 +40,16 @@ class NativeGraph:
         self.num_nodes = int(num_nodes)
         self.handle = c_void_p()
         with torch.cuda.device(self.device):
-            N.check(lib.psi_graph_create(byref(self.handle), self.num_nodes, nnz, N.ptr(ei), N.ptr(attr), int(attr.shape[1]) if nnz else 3,
+            N.check(lib.psi_graph_create(byref(self.handle), self.num_nodes, nnz, N.ptr(ei), N.ptr(attr), int(attr.shape[1]),
                                          N.ptr(aij), N.ptr(tg), int(tg.shape[1]) if tg is not None else 1, N.ptr(pr),
                                          int(pr.shape[1]) if pr is not None else 0, N.ptr(nr), N.stream_ptr()), "psi_graph_create")
         info = (c_int64 * 8)()
         N.check(lib.psi_graph_info(self.handle, info), "psi_graph_info")
         self.num_offdiag, self.nnz, self.num_dirichlet, self.num_neumann = int(info[1]), int(info[2]), int(info[3]), int(info[4])
         self.slots_to, self.slots_from, self.bytes = int(info[5]), int(info[6]), int(info[7])
-        self._solver = None          # lazily created workspace shared by the forward and backward solves
 
     def __del__(self):
         try:
-            if self._solver is not None:
-                self._solver.close()
             if self.handle:
                 N.load().psi_graph_destroy(self.handle)
                 self.handle = c_void_p()
@@ -99,12 +96,10 @@ class NativeGraph:
         return out
 
     def solver(self, threshold: int):
-        from .solver import SolverWorkspace
-        if self._solver is None or self._solver.cap < threshold:
-            if self._solver is not None:
-                self._solver.close()
-            self._solver = SolverWorkspace(self.num_nodes * 10, max(threshold, 1), self.device)
-        return self._solver
+        """the solver workspace for this graph's size, taken from a process-wide pool keyed by (device, numel): batches of
+        a data loader have a few distinct sizes, and re-allocating GBs of U/V history per batch would dominate the step"""
+        from .solver import workspace_for
+        return workspace_for(self.num_nodes * 10, threshold, self.device)
 
 
 def _cache_slot(batch):

@@ -369,8 +369,9 @@ class _ModelBase(nn.Module):
         self.mse_loss = nn.MSELoss()
 
     def _dirichlet_index(self, batch):
-        t = batch.tags
-        return torch.where((t if t.dim() == 1 or t.shape[1] == 1 else t[:, 1:2]) == 1)[0]
+        # monitoring quantity, kept literally: on the 3-column one-hot tags of the mixed family this selects every node
+        # (mixed/psignn/model.py:87), on the 1-column Dirichlet tags the boundary nodes (dirichlet/psignn/model.py:87)
+        return torch.where(batch.tags == 1)[0]
 
     def forward(self, batch):
         loss_dic = {}

@@ -65,6 +65,36 @@ class SolverWorkspace:
         return int(N.load().psi_solver_bytes(self.handle))
 
 
+_POOL = {}           # (device index, numel) -> SolverWorkspace ; bounded by POOL_MAX_BYTES (least recently used evicted)
+_POOL_ORDER = []
+POOL_MAX_BYTES = 64 << 30
+
+
+def workspace_for(numel: int, threshold: int, device) -> SolverWorkspace:
+    device = torch.device(device)
+    key = (device.index if device.index is not None else torch.cuda.current_device(), int(numel))
+    ws = _POOL.get(key)
+    if ws is None or ws.cap < threshold:
+        if ws is not None:
+            ws.close()
+        ws = SolverWorkspace(numel, max(int(threshold), 1), device)
+        _POOL[key] = ws
+    if key in _POOL_ORDER:
+        _POOL_ORDER.remove(key)
+    _POOL_ORDER.append(key)
+    while len(_POOL_ORDER) > 1 and sum(w.nbytes for w in _POOL.values()) > POOL_MAX_BYTES:
+        old = _POOL_ORDER.pop(0)
+        _POOL.pop(old).close()
+    return ws
+
+
+def release_workspaces():
+    for ws in _POOL.values():
+        ws.close()
+    _POOL.clear()
+    _POOL_ORDER.clear()
+
+
 class NativeOperator:
     """Base class of the operators whose solves run entirely inside the extension."""
     graph = None

@@ -135,6 +135,10 @@ def test_forced_quasi_newton_steps(golden_small):
             truth = g.t(pre + name + "64")
             ref32 = g.t(pre + name + "32")
             floor = rel_err(ref32, truth)
+            if name == "upd":
+                # the kernels return δx = (x + update) − x, the reference's own delta_x (solver.py:89-94): its rounding is
+                # half an ulp of x per component, i.e. 2⁻²⁴·‖x‖/‖update‖ relative to the update
+                floor = max(floor, 2.0 ** -24 * float(xn.double().norm() / truth.norm()))
             e = rel_err(got, truth)
             assert e <= max(TOL, 2 * floor), (n, name, e, floor)
         ws.close()
@@ -269,19 +273,11 @@ def _tiny_graph(device, n, edges, mixed=False):
     return b
 
 
-def _cpu_f(m, h, h0, b):
-    """independent evaluation of the same layer with torch ops in fp64 on the CPU (module's differentiable path semantics)"""
-    import copy
-    from psi_gnn_b200.synthetic import GraphData
-    m64 = copy.deepcopy(m).double()
-    bc = GraphData()
-    for k in b.keys():
-        t = getattr(b, k)
-        setattr(bc, k, t.double() if t.is_floating_point() else t)
-    bc.num_nodes = b.num_nodes
-    with torch.enable_grad():
-        hh = h.double().requires_grad_()
-        return m64.deqdss.f._forward_torch(hh, h0.double(), bc).detach()
+def _cpu_f(g, h, h0, b):
+    """independent fp64 CPU evaluation of the same layer by the oracle (the checker)"""
+    from oracle import psignn_oracle as O
+    P64 = {k: v.double() for k, v in g.params().items()}
+    return O.f_dirichlet(P64, h.double().cpu(), h0.double().cpu(), b.to("cpu").double())
 
 
 def test_empty_graph():
@@ -313,7 +309,7 @@ def test_isolated_and_ragged_nodes():
     h0 = torch.randn(n, 10, generator=gen).to(DEV)
     with torch.no_grad():
         out = m.deqdss.f(h, h0, b)
-    ref = _cpu_f(m.cpu(), h.cpu(), h0.cpu(), b.to("cpu"))
+    ref = _cpu_f(g, h, h0, b)
     assert rel_err(out, ref) <= TOL
 
 
