@@ -205,13 +205,75 @@ def make_fixture(family: str, weights: str, n_graphs: int, seed0: int, h: float,
         os.path.getsize(path) / 1024))
 
 
+def make_baseline_fixture(family: str, n_graphs: int, seed0: int, h: float, name: str):
+    """DSS / DSGPS ``inference`` of the unmodified reference with the shipped checkpoints (config 2)."""
+    model_mod, _, _ = ref_shim.load_reference(family)
+    ck = ref_shim.load_checkpoint(ref_shim.CHECKPOINTS[family], family)
+    cfg = dict(ck["hyperparameters"])
+    batch = synthetic.make_batch(n_graphs, seed0=seed0, h=h)
+    dss = family.endswith("dss")
+    if dss:
+        batch = synthetic.to_dss(batch)
+        model = model_mod.DeepStatisticalSolver(cfg)
+    else:
+        model = model_mod.ModelDSGPS(cfg)
+    model.load_state_dict(ck["state_dict"])
+    torch.set_flush_denormal(True)
+    fx = {}
+    for k in batch.keys():
+        fx["batch." + k] = getattr(batch, k).numpy()
+    fx["batch.num_nodes"] = np.int64(batch.num_nodes)
+    for k, v in model.state_dict().items():
+        fx["param." + k] = v.numpy()
+    fx["cfg.k"] = np.int64(cfg["k"])
+    fx["cfg.alpha"] = np.float64(cfg["alpha"])
+    with torch.no_grad():
+        u = model.inference(batch)
+        fx["u"] = u.numpy()
+        # one layer in isolation (layer 0 from a non-trivial state)
+        gen = torch.Generator().manual_seed(99)
+        H = 0.1 * torch.randn(batch.num_nodes, 10, generator=gen)
+        if dss:
+            to = model.phi_to_list[3](H, batch.edge_index, batch.a_ij_norm)
+            fr = model.phi_from_list[3](H, batch.edge_index, batch.a_ij_norm)
+            out = H + cfg["alpha"] * model.psi_list[3](torch.cat([H, to, fr, batch.b_prime_norm], 1))
+            fx["layer_index"] = np.int64(3)
+        else:
+            H0 = model.autoencoder.encoder(batch.x)
+            to = model.phi_to(H, batch.edge_index, batch.edge_attr)
+            fr = model.phi_from(H, batch.edge_index, batch.edge_attr)
+            c = torch.cat([H, to, fr, batch.prb_data], 1)
+            out = H + model.z_k(c) * model.correction(torch.cat([model.r_k(c) * H, to, fr, batch.prb_data], 1))
+            d = torch.where(batch.tags == 1)[0]
+            out[d, :] = H0[d, :]
+            fx["layer_h0"] = H0.numpy()
+        fx["layer_in"] = H.numpy()
+        fx["layer_out"] = out.numpy()
+    # the oracle restatement must agree with the reference here too
+    P = {k: v for k, v in model.state_dict().items()}
+    with torch.no_grad():
+        ou = O.dss_inference(P, batch, cfg["k"], cfg["alpha"]) if dss else O.dsgps_inference(P, batch, cfg["k"])
+    assert float((ou - u).norm() / u.norm()) < 1e-5, "oracle != reference (%s)" % family
+    os.makedirs(OUT, exist_ok=True)
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **fx)
+    print("%-28s N=%d nnz=%d |u|=%.3e -> %s (%.0f kB)" % (name, batch.num_nodes, batch.edge_index.shape[1], float(u.norm()),
+                                                        os.path.relpath(path, ROOT), os.path.getsize(path) / 1024))
+
+
 def main():
+    if "--baselines-only" in sys.argv:
+        make_baseline_fixture("dirichlet/dss", 2, 30, 0.09, "dss_ckpt")
+        make_baseline_fixture("dirichlet/dsgps", 2, 30, 0.09, "dsgps_ckpt")
+        return
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     make_fixture("dirichlet/psignn", "ckpt", 3, 0, 0.075, "dirichlet_ckpt", forced=())
     make_fixture("dirichlet/psignn", "ckpt", 1, 20, 0.11, "dirichlet_ckpt_small", train=False, forced=(2, 5, 20, 40))
     make_fixture("dirichlet/psignn", "seed0", 2, 10, 0.11, "dirichlet_seed0")
     make_fixture("mixed/psignn", "ckpt", 3, 0, 0.075, "mixed_ckpt", forced=())
     make_fixture("mixed/psignn", "seed0", 2, 10, 0.11, "mixed_seed0")
+    make_baseline_fixture("dirichlet/dss", 2, 30, 0.09, "dss_ckpt")
+    make_baseline_fixture("dirichlet/dsgps", 2, 30, 0.09, "dsgps_ckpt")
 
 
 if __name__ == "__main__":

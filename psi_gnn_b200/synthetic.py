@@ -335,6 +335,29 @@ def make_mesh(seed: int, h: float = 0.075, R: float = 1.0, mixed: bool = False,
     return data
 
 
+# dirichlet/dss/utilities/reader.py:63-67 ---------------------------------------
+DSS_NORM = dict(aij_mean=-0.5838, aij_std=0.0924, b_mean=(0.0002, 0.1435, -0.0006), b_std=(0.0507, 0.3506, 3.2935))
+
+
+def to_dss(data: GraphData) -> GraphData:
+    """The same problem in the DSS reader's layout (dirichlet/dataset/generate_data.py:100-128 ``add_dss_variable`` +
+    dirichlet/dss/utilities/reader.py:69-93): A' = A with the diagonal removed (Dirichlet rows become empty),
+    b' = [b, 0, 0] with Dirichlet rows [0, 1, g]; ``x = sol``; edge feature = normalised a_ij."""
+    row, col = data.edge_index
+    keep = row != col
+    ei = data.edge_index[:, keep].contiguous()
+    a = data.a_ij[keep].contiguous()
+    is_dir = data.tags.reshape(-1) == 1
+    b = data.y.reshape(-1)
+    bp = torch.stack([torch.where(is_dir, torch.zeros_like(b), b), is_dir.to(b.dtype), torch.where(is_dir, b, torch.zeros_like(b))], 1)
+    out = GraphData(x=data.sol.clone(), edge_index=ei, a_ij=a, a_ij_norm=(a - DSS_NORM["aij_mean"]) / DSS_NORM["aij_std"],
+                    b_prime=bp, b_prime_norm=(bp - torch.tensor(DSS_NORM["b_mean"], dtype=b.dtype)) / torch.tensor(DSS_NORM["b_std"], dtype=b.dtype),
+                    pos=data.pos, tags=data.tags, sol=data.sol)
+    out.num_nodes = data.num_nodes
+    out.num_graphs = getattr(data, "num_graphs", 1)
+    return out
+
+
 def collate(graphs: Sequence[GraphData]) -> GraphData:
     """``Batch.from_data_list`` semantics: concatenate on dim 0, offset ``edge_index``."""
     graphs = list(graphs)

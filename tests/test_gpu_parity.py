@@ -355,3 +355,60 @@ def test_large_mesh_properties():
         out = m.deqdss.f(Hr, h0, b)
     rhs = (torch.autograd.grad(out, Hr, y)[0].double() * w.double()).sum()
     assert abs(lhs - rhs) <= 1e-4 * abs(rhs) + 1e-5
+
+
+# ---- DSS / DSGPS baselines on the shared layer kernel (config 2) ------------------------------------------------------
+def _baseline(name):
+    g = Golden(name)
+    z = g.z
+    cfg = dict(latent_dim=10, k=int(z["cfg.k"]), alpha=float(z["cfg.alpha"]), gamma=0.9)
+    if name.startswith("dss"):
+        from psi_gnn_b200.dirichlet.dss import model as M
+        m = M.DeepStatisticalSolver(cfg)
+    else:
+        from psi_gnn_b200.dirichlet.dsgps import model as M
+        m = M.ModelDSGPS(cfg)
+    m.load_state_dict(g.params())
+    from psi_gnn_b200.synthetic import GraphData
+    b = GraphData()
+    for k in z.files:
+        if k.startswith("batch.") and k != "batch.num_nodes":
+            setattr(b, k[6:], g.t(k, DEV))
+    b.num_nodes = int(z["batch.num_nodes"])
+    return g, m.to(DEV), b
+
+
+def test_dss_inference_matches_reference():
+    g, m, b = _baseline("dss_ckpt")
+    u = m.inference(b)
+    assert rel_err(u, g.t("u")) <= TOL
+
+
+def test_dss_single_layer_matches_reference():
+    from psi_gnn_b200 import _native as N, weights as W
+    from psi_gnn_b200.graph import graph_of
+    g, m, b = _baseline("dss_ckpt")
+    k = int(g["layer_index"])
+    blob = W.pack_dss(g.params(DEV), k, float(g["cfg.alpha"]), DEV)
+    W.upload(blob, ("test-dss", k))
+    out = graph_of(b, N.KIND_DSS).layer_forward(N.KIND_DSS, g.t("layer_in", DEV), None)
+    assert rel_err(out, g.t("layer_out")) <= TOL
+    # the increment itself (α = 1e-3 hides errors in H + α·Ψ): compare Ψ = (out − in)/α to 1e-4
+    inc = (out - g.t("layer_in", DEV)).double().cpu()
+    ref = (g.t("layer_out") - g.t("layer_in")).double()
+    assert float((inc - ref).norm() / ref.norm()) <= 1e-3
+
+
+def test_dsgps_inference_matches_reference():
+    g, m, b = _baseline("dsgps_ckpt")
+    u = m.inference(b)
+    assert rel_err(u, g.t("u")) <= 5 * TOL          # 30 recurrent steps
+
+
+def test_dsgps_single_layer_matches_reference():
+    from psi_gnn_b200 import _native as N, weights as W
+    from psi_gnn_b200.graph import graph_of
+    g, m, b = _baseline("dsgps_ckpt")
+    W.upload(W.pack_dsgps(g.params(DEV), DEV), ("test-dsgps",))
+    out = graph_of(b, N.KIND_DSGPS).layer_forward(N.KIND_DSGPS, g.t("layer_in", DEV), g.t("layer_h0", DEV))
+    assert rel_err(out, g.t("layer_out")) <= TOL
