@@ -11,6 +11,7 @@
 #include "vjp.cuh"
 #include "broyden.cuh"
 #include "anderson.cuh"
+#include "qn_tma.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -290,6 +291,7 @@ struct psi_solver {
     int64_t numel = 0, stride = 0;        // stride = numel rounded up to whole QN_CHUNKs (tail kept at zero)
     int cap = 0;                          // largest threshold the workspace can hold
     int num_chunks = 0, axpy_ctas = 0, norm_cap = 0;
+    int dots_chunks = 0, tma_ctas = 0;    // 2048-element chunks of pass 1; persistent CTAs (one per SM) of the TMA kernels
     float *x = nullptr, *g = nullptr, *dg = nullptr, *dx = nullptr, *best = nullptr, *fx = nullptr;
     float *partial = nullptr, *partial2 = nullptr, *coef = nullptr, *norm_part = nullptr;
     QnCtrl* ctrl = nullptr;               // device
@@ -353,10 +355,23 @@ extern "C" int psi_solver_create(psi_solver_t** out, int64_t numel, int max_thre
     if (numel < 0 || max_threshold < 1) PSI_FAIL("psi_solver_create: bad size");
     psi_solver* s = new psi_solver();
     s->numel = numel;
-    s->stride = round_up64(numel > 0 ? numel : 1, QN_CHUNK);
+    s->stride = round_up64(numel > 0 ? numel : 1, 4096);
     s->cap = max_threshold;
     s->num_chunks = (int)(s->stride / QN_CHUNK);
     s->axpy_ctas = std::min(s->num_chunks, QN_AXPY_MAX_CTAS);
+    s->dots_chunks = (int)(s->stride / DOTS_CH);
+    {
+        int dev = 0, sms = PSI_NUM_SMS_B200;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = PSI_NUM_SMS_B200;
+        s->tma_ctas = std::min(sms, QN_AXPY_MAX_CTAS);
+        static bool attr_done = false;
+        if (!attr_done) {
+            cudaFuncSetAttribute(k_qn_dots_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dots_tma_smem());
+            cudaFuncSetAttribute(k_qn_axpy_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)axpy_tma_smem(4096));
+            attr_done = true;
+        }
+    }
     s->norm_cap = std::max((int)node_grid(numel / PSI_D + 1), s->num_chunks) + 1;
     const size_t vb = s->stride * sizeof(float);
     int rc = 0;
@@ -366,7 +381,7 @@ extern "C" int psi_solver_create(psi_solver_t** out, int64_t numel, int max_thre
     rc |= solver_alloc(s, (void**)&s->dx, vb);
     rc |= solver_alloc(s, (void**)&s->best, vb);
     rc |= solver_alloc(s, (void**)&s->fx, vb);
-    rc |= solver_alloc(s, (void**)&s->partial, (size_t)3 * s->cap * s->num_chunks * sizeof(float));
+    rc |= solver_alloc(s, (void**)&s->partial, (size_t)3 * s->cap * s->dots_chunks * sizeof(float));
     rc |= solver_alloc(s, (void**)&s->partial2, (size_t)2 * QN_AXPY_MAX_CTAS * sizeof(float));
     rc |= solver_alloc(s, (void**)&s->coef, (size_t)3 * s->cap * sizeof(float));
     rc |= solver_alloc(s, (void**)&s->norm_part, (size_t)2 * s->norm_cap * sizeof(float));
@@ -475,28 +490,27 @@ static int qn_update(psi_solver* s, int n, int norm_blocks, cudaStream_t st) {
     const int nhist = n - 1;
     if (hist_ensure(s, n - 1)) return -1;
     if (nhist > 0) {
-        dim3 grid(s->num_chunks, (nhist + QN_KTILE - 1) / QN_KTILE);
         const double vec = (double)s->numel * 4.0;
         prof_begin(s, n, 1, (2.0 * nhist + 3.0) * vec, st);
-        k_qn_dots<<<grid, QN_THREADS, 0, st>>>(s->hist, nhist, s->dx, s->dg, s->g, s->partial, s->num_chunks, &s->ctrl->done);
+        k_qn_dots_tma<<<s->tma_ctas, TMA_THREADS, dots_tma_smem(), st>>>(s->hist, nhist, s->dx, s->dg, s->g, s->partial, s->dots_chunks,
+                                                                         &s->ctrl->done);
         prof_end(s, n, 1, st);
         PSI_CK_LAUNCH();
         s->launches += 1;
     }
     const int fin_blocks = std::max(1, std::min(64, (nhist * 3 + 7) / 8));
-    k_qn_fin1<<<fin_blocks, 256, 0, st>>>(nhist, s->partial, s->num_chunks, s->coef, s->cap, s->norm_part, norm_blocks, s->ctrl,
+    k_qn_fin1<<<fin_blocks, 256, 0, st>>>(nhist, s->partial, s->dots_chunks, s->coef, s->cap, s->norm_part, norm_blocks, s->ctrl,
                                           s->rel_trace, s->abs_trace, n, s->eps, 1e3 * PSI_D, s->threshold);
     PSI_CK_LAUNCH();
-    const size_t sh = (size_t)3 * std::max(nhist, 1) * sizeof(float);
     prof_begin(s, n, 2, (2.0 * nhist + 6.0) * (double)s->numel * 4.0, st);
-    k_qn_axpy<<<s->axpy_ctas, QN_THREADS, sh, st>>>(s->hist, nhist, n, s->coef, s->cap, s->dx, s->dg, s->g, s->x, s->best, s->partial2,
-                                                    s->num_chunks, s->ctrl);
+    k_qn_axpy_tma<<<s->tma_ctas, TMA_THREADS, axpy_tma_smem(nhist), st>>>(s->hist, nhist, n, s->coef, s->cap, s->dx, s->dg, s->g, s->x, s->best,
+                                                                         s->partial2, (s->numel + 3) / 4, s->ctrl);
     prof_end(s, n, 2, st);
     PSI_CK_LAUNCH();
     float* xt = s->xtrace ? s->xtrace + (int64_t)(n + 1) * s->stride : nullptr;
     if (n >= s->threshold) xt = nullptr;
     prof_begin(s, n, 3, 7.0 * (double)s->numel * 4.0, st);
-    k_qn_fin2<<<s->axpy_ctas, QN_THREADS, 0, st>>>(s->hist, n, s->dx, s->g, s->x, s->partial2, s->axpy_ctas, xt, s->ctrl, s->num_chunks);
+    k_qn_fin2<<<s->axpy_ctas, QN_THREADS, 0, st>>>(s->hist, n, s->dx, s->g, s->x, s->partial2, s->tma_ctas, xt, s->ctrl, s->num_chunks);
     prof_end(s, n, 3, st);
     PSI_CK_LAUNCH();
     s->launches += 3;

@@ -1,0 +1,253 @@
+// qn_tma.cuh — the two history-streaming kernels of the Broyden update as TMA-fed persistent kernels.
+//
+// The U/V history (2·n vectors of N·d floats) is read twice per step and dominates HBM traffic.  Both
+// passes are pure streams with no reuse, so the job is to keep enough bytes in flight per SM independent of register
+// pressure: one persistent CTA per SM, a producer warp issuing 1-D bulk copies (cp.async.bulk → UBLKCP) of U_k / V_k tiles
+// into a shared-memory ring, full/empty mbarriers per stage, eight consumer warps doing the FMAs out of shared memory.
+//   pass 1  k_qn_dots_tma : a = Uᵀδx, c = Vᵀδg, e = Vᵀg        work item = (2048-element chunk, range of 32 history vectors)
+//   pass 2  k_qn_axpy_tma : v = −δx + V·a, w = U·c, t = U·e      each CTA owns an equal contiguous element range (±16 B)
+// Summation orders are fixed (xor-shuffle tree, then warps in order, then chunks in order): results are deterministic.
+#pragma once
+#include "common.cuh"
+#include "broyden.cuh"
+
+#define TMA_CONSUMERS 256                    // 8 consumer warps
+#define TMA_THREADS (TMA_CONSUMERS + 32)     // + 1 producer warp
+#define DOTS_CH 2048                         // elements per chunk (8 KB per vector)
+#define DOTS_STAGES 12                       // 12 × (8 KB U + 8 KB V) = 192 KB
+#define DOTS_KR 32                           // history vectors per work item
+#define DOTS_KB 8                            // ks per cross-warp reduction batch
+#define AXPY_TILE 1024                       // max elements per tile (4 KB per vector)
+#define AXPY_STAGES 20                       // 20 × (4 KB U + 4 KB V) = 160 KB
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+// 1-D bulk copy global → shared, completion signalled on an mbarrier (bytes multiple of 16, both addresses 16-byte aligned)
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(TMA_CONSUMERS) : "memory"); }
+
+struct TmaRing {
+    uint64_t* full;
+    uint64_t* empty;
+};
+
+// ---- pass 1 ---------------------------------------------------------------------------------------------------------
+// partial[(k*3+q)*num_chunks + chunk], num_chunks = stride / DOTS_CH
+__global__ void __launch_bounds__(TMA_THREADS, 1)
+k_qn_dots_tma(QnHistory H, int nhist, const float* __restrict__ dx, const float* __restrict__ dg, const float* __restrict__ g,
+              float* __restrict__ partial, int num_chunks, const int* __restrict__ done) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* ring = reinterpret_cast<float*>(smem_raw);                                   // [STAGES][2][DOTS_CH]
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)DOTS_STAGES * 2 * DOTS_CH * sizeof(float));
+    uint64_t* empty = full + DOTS_STAGES;
+    float* red = reinterpret_cast<float*>(empty + DOTS_STAGES);                         // [2][DOTS_KB][3][8]
+    if (*done) return;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int s = 0; s < DOTS_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], TMA_CONSUMERS / 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int kranges = (nhist + DOTS_KR - 1) / DOTS_KR;
+    const int items = num_chunks * kranges;
+    if (warp == TMA_CONSUMERS / 32) {
+        // ---- producer ----
+        if (lane == 0) {
+            uint32_t fill = 0;
+            for (int item = blockIdx.x; item < items; item += gridDim.x) {
+                const int c = item % num_chunks, r = item / num_chunks;
+                const int k0 = r * DOTS_KR, k1 = min(nhist, k0 + DOTS_KR);
+                const int64_t e0 = (int64_t)c * DOTS_CH;
+                for (int k = k0; k < k1; ++k, ++fill) {
+                    const uint32_t s = fill % DOTS_STAGES, use = fill / DOTS_STAGES;
+                    if (use > 0) mbar_wait(&empty[s], (use - 1) & 1);
+                    mbar_expect_tx(&full[s], 2 * DOTS_CH * sizeof(float));
+                    float* dst = ring + (size_t)s * 2 * DOTS_CH;
+                    bulk_g2s(dst, hist_u(H, k) + e0, DOTS_CH * sizeof(float), &full[s]);
+                    bulk_g2s(dst + DOTS_CH, hist_v(H, k) + e0, DOTS_CH * sizeof(float), &full[s]);
+                }
+            }
+        }
+        return;
+    }
+    // ---- consumers ----
+    uint32_t fill = 0;
+    int buf = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        const int c = item % num_chunks, r = item / num_chunks;
+        const int k0 = r * DOTS_KR, k1 = min(nhist, k0 + DOTS_KR);
+        const int64_t e0 = (int64_t)c * DOTS_CH;
+        const float4* pdx = reinterpret_cast<const float4*>(dx + e0);
+        const float4* pdg = reinterpret_cast<const float4*>(dg + e0);
+        const float4* pg = reinterpret_cast<const float4*>(g + e0);
+        const float4 dx0 = __ldg(pdx + tid), dx1 = __ldg(pdx + tid + TMA_CONSUMERS);
+        const float4 dg0 = __ldg(pdg + tid), dg1 = __ldg(pdg + tid + TMA_CONSUMERS);
+        const float4 g0 = __ldg(pg + tid), g1 = __ldg(pg + tid + TMA_CONSUMERS);
+        for (int kb0 = k0; kb0 < k1; kb0 += DOTS_KB) {
+            const int nb = min(DOTS_KB, k1 - kb0);
+            for (int kk = 0; kk < nb; ++kk, ++fill) {
+                const uint32_t s = fill % DOTS_STAGES, use = fill / DOTS_STAGES;
+                mbar_wait(&full[s], use & 1);
+                const float4* su = reinterpret_cast<const float4*>(ring + (size_t)s * 2 * DOTS_CH);
+                const float4* sv = su + DOTS_CH / 4;
+                const float4 u0 = su[tid], u1 = su[tid + TMA_CONSUMERS];
+                const float4 v0 = sv[tid], v1 = sv[tid + TMA_CONSUMERS];
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[s]);
+                float a = dot4(u1, dx1, dot4(u0, dx0, 0.f));
+                float cc = dot4(v1, dg1, dot4(v0, dg0, 0.f));
+                float e = dot4(v1, g1, dot4(v0, g0, 0.f));
+                a = warp_sum(a); cc = warp_sum(cc); e = warp_sum(e);
+                if (lane == 0) {
+                    float* rp = red + ((buf * DOTS_KB + kk) * 3) * 8 + warp;
+                    rp[0] = a; rp[8] = cc; rp[16] = e;
+                }
+            }
+            consumer_bar();
+            if (tid < nb * 3) {
+                const int kk = tid / 3, q = tid % 3;
+                const float* rp = red + ((buf * DOTS_KB + kk) * 3 + q) * 8;
+                float sum = 0.f;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) sum += rp[w];
+                partial[((int64_t)(kb0 + kk) * 3 + q) * num_chunks + c] = sum;
+            }
+            buf ^= 1;
+        }
+    }
+}
+
+// ---- pass 2 ---------------------------------------------------------------------------------------------------------
+// Each CTA owns float4 range [q0, q1) of the vectors, split into equal tiles of ≤ AXPY_TILE floats.
+__global__ void __launch_bounds__(TMA_THREADS, 1)
+k_qn_axpy_tma(QnHistory H, int nhist, int n, const float* __restrict__ coef, int cap, float* __restrict__ dx_upd, float* __restrict__ dg_t,
+              const float* __restrict__ g, const float* __restrict__ x, float* __restrict__ best_x, float* __restrict__ partial2,
+              int64_t total4, const QnCtrl* __restrict__ ctrl) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* ring = reinterpret_cast<float*>(smem_raw);                                   // [STAGES][2][AXPY_TILE]
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)AXPY_STAGES * 2 * AXPY_TILE * sizeof(float));
+    uint64_t* empty = full + AXPY_STAGES;
+    float* s_red = reinterpret_cast<float*>(empty + AXPY_STAGES);                       // [2][8]
+    float* s_coef = s_red + 16;                                                         // [3][nhist]
+    const int improved = ctrl->improved, done = ctrl->done;
+    if (done && !improved) return;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t per = (total4 + gridDim.x - 1) / gridDim.x;
+    const int64_t q0 = min(total4, (int64_t)blockIdx.x * per), q1 = min(total4, q0 + per);
+    if (improved) {                        // lowest_xest = x_est.clone()  (solver.py:172)
+        for (int64_t q = q0 + tid; q < q1; q += TMA_THREADS)
+            reinterpret_cast<float4*>(best_x)[q] = reinterpret_cast<const float4*>(x)[q];
+    }
+    if (done) return;
+    if (tid == 0) {
+        for (int s = 0; s < AXPY_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], TMA_CONSUMERS / 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < nhist; i += TMA_THREADS) {
+        s_coef[i] = coef[i];
+        s_coef[nhist + i] = coef[cap + i];
+        s_coef[2 * nhist + i] = coef[2 * cap + i];
+    }
+    __syncthreads();
+    const int64_t len4 = q1 - q0;
+    const int ntiles = (int)((len4 * 4 + AXPY_TILE - 1) / AXPY_TILE);
+    const int tile4 = ntiles > 0 ? (int)((len4 + ntiles - 1) / ntiles) : 0;            // ≤ AXPY_TILE/4 float4 per tile
+    if (warp == TMA_CONSUMERS / 32) {
+        if (lane == 0) {
+            uint32_t fill = 0;
+            for (int t = 0; t < ntiles; ++t) {
+                const int64_t t0 = q0 + (int64_t)t * tile4;
+                const uint32_t bytes = (uint32_t)(min((int64_t)tile4, q1 - t0) * 16);
+                for (int k = 0; k < nhist; ++k, ++fill) {
+                    const uint32_t s = fill % AXPY_STAGES, use = fill / AXPY_STAGES;
+                    if (use > 0) mbar_wait(&empty[s], (use - 1) & 1);
+                    mbar_expect_tx(&full[s], 2 * bytes);
+                    float* dst = ring + (size_t)s * 2 * AXPY_TILE;
+                    bulk_g2s(dst, hist_u(H, k) + t0 * 4, bytes, &full[s]);
+                    bulk_g2s(dst + AXPY_TILE, hist_v(H, k) + t0 * 4, bytes, &full[s]);
+                }
+            }
+        }
+        return;
+    }
+    float* vn_dst = hist_v(H, n - 1);
+    float* un_dst = hist_u(H, n - 1);
+    float acc0 = 0.f, acc1 = 0.f;
+    uint32_t fill = 0;
+    for (int t = 0; t < ntiles; ++t) {
+        const int64_t t0 = q0 + (int64_t)t * tile4;
+        const int cnt4 = (int)min((int64_t)tile4, q1 - t0);
+        const bool active = tid < cnt4;
+        float4 av = make_float4(0.f, 0.f, 0.f, 0.f), aw = av, at = av;
+        for (int k = 0; k < nhist; ++k, ++fill) {
+            const uint32_t s = fill % AXPY_STAGES, use = fill / AXPY_STAGES;
+            mbar_wait(&full[s], use & 1);
+            if (active) {
+                const float4* su = reinterpret_cast<const float4*>(ring + (size_t)s * 2 * AXPY_TILE);
+                const float4 u = su[tid], v = su[AXPY_TILE / 4 + tid];
+                const float a = s_coef[k], c = s_coef[nhist + k], e = s_coef[2 * nhist + k];
+                av.x = fmaf(a, v.x, av.x); av.y = fmaf(a, v.y, av.y); av.z = fmaf(a, v.z, av.z); av.w = fmaf(a, v.w, av.w);
+                aw.x = fmaf(c, u.x, aw.x); aw.y = fmaf(c, u.y, aw.y); aw.z = fmaf(c, u.z, aw.z); aw.w = fmaf(c, u.w, aw.w);
+                at.x = fmaf(e, u.x, at.x); at.y = fmaf(e, u.y, at.y); at.z = fmaf(e, u.z, at.z); at.w = fmaf(e, u.w, at.w);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
+        }
+        if (active) {
+            const int64_t q = t0 + tid;
+            const float4 vdx = reinterpret_cast<const float4*>(dx_upd)[q];
+            const float4 vdg = reinterpret_cast<const float4*>(dg_t)[q];
+            const float4 vg = reinterpret_cast<const float4*>(g)[q];
+            // vT = −δx + Σ a_k V_k  (rmatvec, solver.py:104)
+            float4 vn = make_float4(-vdx.x + av.x, -vdx.y + av.y, -vdx.z + av.z, -vdx.w + av.w);
+            acc0 = dot4(vn, vdg, acc0);                                       // ⟨vT, δg⟩ uses the un-scrubbed vT (solver.py:187)
+            // vT[vT != vT] = 0  (solver.py:188)
+            vn.x = (vn.x != vn.x) ? 0.f : vn.x; vn.y = (vn.y != vn.y) ? 0.f : vn.y;
+            vn.z = (vn.z != vn.z) ? 0.f : vn.z; vn.w = (vn.w != vn.w) ? 0.f : vn.w;
+            acc1 = dot4(vn, vg, acc1);                                        // V[n-1]ᵀ g_n for the new update
+            // numerator of u:  δx − matvec(δg) = δx − (−δg + Σ c_k U_k)   (solver.py:114,187)
+            const float4 un = make_float4(vdx.x - (-vdg.x + aw.x), vdx.y - (-vdg.y + aw.y), vdx.z - (-vdg.z + aw.z), vdx.w - (-vdg.w + aw.w));
+            reinterpret_cast<float4*>(vn_dst)[q] = vn;
+            reinterpret_cast<float4*>(un_dst)[q] = un;
+            reinterpret_cast<float4*>(dx_upd)[q] = at;                        // t = Σ e_k U_k, finished in k_qn_fin2
+        }
+    }
+    acc0 = warp_sum(acc0);
+    acc1 = warp_sum(acc1);
+    if (lane == 0) { s_red[warp] = acc0; s_red[8 + warp] = acc1; }
+    consumer_bar();
+    if (tid == 0) {
+        float a = 0.f, b = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) { a += s_red[w]; b += s_red[8 + w]; }
+        partial2[blockIdx.x] = a;
+        partial2[gridDim.x + blockIdx.x] = b;
+    }
+}
+
+static inline size_t dots_tma_smem() { return (size_t)DOTS_STAGES * 2 * DOTS_CH * 4 + 2 * DOTS_STAGES * 8 + 2 * DOTS_KB * 3 * 8 * 4; }
+static inline size_t axpy_tma_smem(int nhist) { return (size_t)AXPY_STAGES * 2 * AXPY_TILE * 4 + 2 * AXPY_STAGES * 8 + 16 * 4 + (size_t)3 * (nhist > 0 ? nhist : 1) * 4; }
