@@ -67,15 +67,16 @@ class DeepStatisticalSolver(nn.Module):
         self.psi_list = nn.ModuleList([Psi([3 * d + 3, d, d], nn.ReLU()) for _ in range(k)])
         self.decoder_list = nn.ModuleList([DecoderDSS([d, d, 1], nn.ReLU()) for _ in range(k)])
         self.mse_loss = nn.MSELoss()
-        self._blobs = (None, None)
+        self._blobs = (None, None, None)
 
     def _packed(self, device):
         P = W.named_tensors(self)
         key = (W.version_key(P), str(device))
         if self._blobs[0] != key:
             with torch.no_grad():
-                self._blobs = (key, [W.pack_dss(P, k, self.config["alpha"], device) for k in range(self.config["k"])])
-        return key, self._blobs[1]
+                self._blobs = (key, [W.pack_dss(P, k, self.config["alpha"], device) for k in range(self.config["k"])],
+                               [W.next_serial() for _ in range(self.config["k"])])
+        return self._blobs[2], self._blobs[1]
 
     def inference(self, batch):
         if not batch.edge_index.is_cuda:
@@ -84,10 +85,10 @@ class DeepStatisticalSolver(nn.Module):
             raise NotImplementedError("psi_gnn_b200: the fused kernel is built for latent_dim=10")
         g = graph_of(batch, N.KIND_DSS)
         dev = batch.edge_index.device
-        key, blobs = self._packed(dev)
+        serials, blobs = self._packed(dev)
         H = torch.zeros(g.num_nodes, W.D, dtype=torch.float32, device=dev)
         for k in range(self.config["k"]):
-            W.upload(blobs[k], (id(self), key, k))
+            W.upload(blobs[k], serials[k])
             H = g.layer_forward(N.KIND_DSS, H, None)
         return _decode(H)                         # Decoder_{k-1} travels in the last layer's block
 
@@ -118,7 +119,7 @@ class ModelDSGPS(nn.Module):
         self.correction = MLPActivation([3 * d + 2, d], nn.Tanh())
         self.autoencoder = Autoencoder([1, d, d], nn.ReLU())
         self.mse_loss = nn.MSELoss()
-        self._blob = (None, None)
+        self._blob = (None, None, None)
 
     def inference(self, batch, k=None):
         if not batch.edge_index.is_cuda:
@@ -128,11 +129,11 @@ class ModelDSGPS(nn.Module):
         g = graph_of(batch, N.KIND_DSGPS)
         dev = batch.edge_index.device
         P = W.named_tensors(self)
-        key = (id(self), W.version_key(P), str(dev))
+        key = (W.version_key(P), str(dev))
         if self._blob[0] != key:
             with torch.no_grad():
-                self._blob = (key, W.pack_dsgps(P, dev))
-        W.upload(self._blob[1], key)
+                self._blob = (key, W.pack_dsgps(P, dev), W.next_serial())
+        W.upload(self._blob[1], self._blob[2])
         x = N.f32(batch.x.reshape(-1))
         H0 = torch.empty(x.numel(), W.D, dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):

@@ -33,8 +33,8 @@ class NativeGraph:
         aij = N.f32(a_ij.reshape(-1)) if a_ij is not None else None
         if aij is not None and aij.numel() != nnz:
             raise RuntimeError("psi_gnn_b200: a_ij must have one entry per edge")
-        tg = N.f32(tags.reshape(num_nodes, -1)) if tags is not None else None
-        pr = N.f32(prb.reshape(num_nodes, -1)) if prb is not None else None
+        tg = N.f32(tags.reshape(num_nodes, tags.shape[-1] if tags.dim() > 1 else 1)) if tags is not None else None
+        pr = N.f32(prb.reshape(num_nodes, prb.shape[-1] if prb.dim() > 1 else 1)) if prb is not None else None
         nr = N.f32(normals.reshape(num_nodes, 2)) if normals is not None else None
         self.device = ei.device
         self.num_nodes = int(num_nodes)

@@ -147,7 +147,7 @@ class _FunctionBase(nn.Module):
             self.phi_neumann = Phi_from(ch, activation)
             self.update_neumann = MLP([2 * latent_dim + second_member_dim + 2, latent_dim, latent_dim], activation)
         self._autoencoder_ref = None          # set by ModelDEQDSS so that encoder/decoder kernels share the block
-        self._pack_cache = (None, None)
+        self._pack_cache = (None, None, None)
 
     # ---- native plumbing ---------------------------------------------------------------------------------
     def _check_native(self):
@@ -171,11 +171,11 @@ class _FunctionBase(nn.Module):
 
     def upload_weights(self, device):
         P = self._named()
-        key = (id(self), W.version_key(P), str(device))
+        key = (W.version_key(P), str(device))
         if self._pack_cache[0] != key:
             with torch.no_grad():
-                self._pack_cache = (key, W.pack_psignn(P, self.kind == N.KIND_MIXED, device))
-        W.upload(self._pack_cache[1], key)
+                self._pack_cache = (key, W.pack_psignn(P, self.kind == N.KIND_MIXED, device), W.next_serial())
+        W.upload(self._pack_cache[1], self._pack_cache[2])
 
     # ---- forward --------------------------------------------------------------------------------------------
     def forward(self, h, h_initial, batch):

@@ -144,6 +144,13 @@ def version_key(P: Mapping[str, torch.Tensor]):
 
 # ---- the process-wide constant bank ---------------------------------------------------------------------
 _UPLOADED = {}      # device index -> key of the block currently in __constant__ memory
+_SERIAL = [0]
+
+
+def next_serial() -> int:
+    """unique identity of a packed block (object ids / data pointers can be recycled by the allocator, a counter cannot)"""
+    _SERIAL[0] += 1
+    return _SERIAL[0]
 
 
 def upload(blob: torch.Tensor, key) -> None:
