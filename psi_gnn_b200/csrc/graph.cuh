@@ -196,8 +196,10 @@ static int build_sell(int64_t N, int64_t nnz, const int64_t* ei, const float* at
     k_graph_ptr<<<(unsigned)((N + 1 + 255) / 256), 256, 0, st>>>(nnz, (int)N, skeys, ptr);
     PSI_CK_LAUNCH();
     PSI_CK(cudaMemsetAsync(slice_recs, 0, (num_slices + 1) * sizeof(int64_t), st));
-    k_graph_slice_width<<<(unsigned)((num_slices * 32 + 255) / 256), 256, 0, st>>>((int)N, num_slices, ptr, slice_recs);
-    PSI_CK_LAUNCH();
+    if (num_slices > 0) {
+        k_graph_slice_width<<<(unsigned)((num_slices * 32 + 255) / 256), 256, 0, st>>>((int)N, num_slices, ptr, slice_recs);
+        PSI_CK_LAUNCH();
+    }
     PSI_CK(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, slice_recs, slice_off, num_slices + 1, st));
     int64_t total = 0;
     int kept = 0;

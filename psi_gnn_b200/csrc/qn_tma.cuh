@@ -17,8 +17,8 @@
 #define DOTS_STAGES 12                       // 12 × (8 KB U + 8 KB V) = 192 KB
 #define DOTS_KR 32                           // history vectors per work item
 #define DOTS_KB 8                            // ks per cross-warp reduction batch
-#define AXPY_TILE 1024                       // max elements per tile (4 KB per vector)
-#define AXPY_STAGES 20                       // 20 × (4 KB U + 4 KB V) = 160 KB
+#define AXPY_TILE 2048                       // max elements per tile (8 KB per vector), two float4 per consumer thread
+#define AXPY_STAGES 11                       // 11 × (8 KB U + 8 KB V) = 176 KB
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -201,39 +201,49 @@ k_qn_axpy_tma(QnHistory H, int nhist, int n, const float* __restrict__ coef, int
     for (int t = 0; t < ntiles; ++t) {
         const int64_t t0 = q0 + (int64_t)t * tile4;
         const int cnt4 = (int)min((int64_t)tile4, q1 - t0);
-        const bool active = tid < cnt4;
-        float4 av = make_float4(0.f, 0.f, 0.f, 0.f), aw = av, at = av;
+        const bool act0 = tid < cnt4, act1 = tid + TMA_CONSUMERS < cnt4;
+        float4 av[2], aw[2], at[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) { av[j] = make_float4(0.f, 0.f, 0.f, 0.f); aw[j] = av[j]; at[j] = av[j]; }
         for (int k = 0; k < nhist; ++k, ++fill) {
             const uint32_t s = fill % AXPY_STAGES, use = fill / AXPY_STAGES;
             mbar_wait(&full[s], use & 1);
-            if (active) {
-                const float4* su = reinterpret_cast<const float4*>(ring + (size_t)s * 2 * AXPY_TILE);
-                const float4 u = su[tid], v = su[AXPY_TILE / 4 + tid];
-                const float a = s_coef[k], c = s_coef[nhist + k], e = s_coef[2 * nhist + k];
-                av.x = fmaf(a, v.x, av.x); av.y = fmaf(a, v.y, av.y); av.z = fmaf(a, v.z, av.z); av.w = fmaf(a, v.w, av.w);
-                aw.x = fmaf(c, u.x, aw.x); aw.y = fmaf(c, u.y, aw.y); aw.z = fmaf(c, u.z, aw.z); aw.w = fmaf(c, u.w, aw.w);
-                at.x = fmaf(e, u.x, at.x); at.y = fmaf(e, u.y, at.y); at.z = fmaf(e, u.z, at.z); at.w = fmaf(e, u.w, at.w);
-            }
+            const float4* su = reinterpret_cast<const float4*>(ring + (size_t)s * 2 * AXPY_TILE);
+            const float a = s_coef[k], c = s_coef[nhist + k], e = s_coef[2 * nhist + k];
+            float4 u[2], v[2];
+            // rows beyond cnt4 hold stale ring data: they are read (harmless) but never stored
+            u[0] = su[tid]; u[1] = su[tid + TMA_CONSUMERS];
+            v[0] = su[AXPY_TILE / 4 + tid]; v[1] = su[AXPY_TILE / 4 + tid + TMA_CONSUMERS];
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[s]);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                av[j].x = fmaf(a, v[j].x, av[j].x); av[j].y = fmaf(a, v[j].y, av[j].y); av[j].z = fmaf(a, v[j].z, av[j].z); av[j].w = fmaf(a, v[j].w, av[j].w);
+                aw[j].x = fmaf(c, u[j].x, aw[j].x); aw[j].y = fmaf(c, u[j].y, aw[j].y); aw[j].z = fmaf(c, u[j].z, aw[j].z); aw[j].w = fmaf(c, u[j].w, aw[j].w);
+                at[j].x = fmaf(e, u[j].x, at[j].x); at[j].y = fmaf(e, u[j].y, at[j].y); at[j].z = fmaf(e, u[j].z, at[j].z); at[j].w = fmaf(e, u[j].w, at[j].w);
+            }
         }
-        if (active) {
-            const int64_t q = t0 + tid;
-            const float4 vdx = reinterpret_cast<const float4*>(dx_upd)[q];
-            const float4 vdg = reinterpret_cast<const float4*>(dg_t)[q];
-            const float4 vg = reinterpret_cast<const float4*>(g)[q];
-            // vT = −δx + Σ a_k V_k  (rmatvec, solver.py:104)
-            float4 vn = make_float4(-vdx.x + av.x, -vdx.y + av.y, -vdx.z + av.z, -vdx.w + av.w);
-            acc0 = dot4(vn, vdg, acc0);                                       // ⟨vT, δg⟩ uses the un-scrubbed vT (solver.py:187)
-            // vT[vT != vT] = 0  (solver.py:188)
-            vn.x = (vn.x != vn.x) ? 0.f : vn.x; vn.y = (vn.y != vn.y) ? 0.f : vn.y;
-            vn.z = (vn.z != vn.z) ? 0.f : vn.z; vn.w = (vn.w != vn.w) ? 0.f : vn.w;
-            acc1 = dot4(vn, vg, acc1);                                        // V[n-1]ᵀ g_n for the new update
-            // numerator of u:  δx − matvec(δg) = δx − (−δg + Σ c_k U_k)   (solver.py:114,187)
-            const float4 un = make_float4(vdx.x - (-vdg.x + aw.x), vdx.y - (-vdg.y + aw.y), vdx.z - (-vdg.z + aw.z), vdx.w - (-vdg.w + aw.w));
-            reinterpret_cast<float4*>(vn_dst)[q] = vn;
-            reinterpret_cast<float4*>(un_dst)[q] = un;
-            reinterpret_cast<float4*>(dx_upd)[q] = at;                        // t = Σ e_k U_k, finished in k_qn_fin2
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            if (j == 0 ? act0 : act1) {
+                const int64_t q = t0 + tid + j * TMA_CONSUMERS;
+                const float4 vdx = reinterpret_cast<const float4*>(dx_upd)[q];
+                const float4 vdg = reinterpret_cast<const float4*>(dg_t)[q];
+                const float4 vg = reinterpret_cast<const float4*>(g)[q];
+                // vT = −δx + Σ a_k V_k  (rmatvec, solver.py:104)
+                float4 vn = make_float4(-vdx.x + av[j].x, -vdx.y + av[j].y, -vdx.z + av[j].z, -vdx.w + av[j].w);
+                acc0 = dot4(vn, vdg, acc0);                                   // ⟨vT, δg⟩ uses the un-scrubbed vT (solver.py:187)
+                // vT[vT != vT] = 0  (solver.py:188)
+                vn.x = (vn.x != vn.x) ? 0.f : vn.x; vn.y = (vn.y != vn.y) ? 0.f : vn.y;
+                vn.z = (vn.z != vn.z) ? 0.f : vn.z; vn.w = (vn.w != vn.w) ? 0.f : vn.w;
+                acc1 = dot4(vn, vg, acc1);                                    // V[n-1]ᵀ g_n for the new update
+                // numerator of u:  δx − matvec(δg) = δx − (−δg + Σ c_k U_k)   (solver.py:114,187)
+                const float4 un = make_float4(vdx.x - (-vdg.x + aw[j].x), vdx.y - (-vdg.y + aw[j].y), vdx.z - (-vdg.z + aw[j].z),
+                                              vdx.w - (-vdg.w + aw[j].w));
+                reinterpret_cast<float4*>(vn_dst)[q] = vn;
+                reinterpret_cast<float4*>(un_dst)[q] = un;
+                reinterpret_cast<float4*>(dx_upd)[q] = at[j];                 // t = Σ e_k U_k, finished in k_qn_fin2
+            }
         }
     }
     acc0 = warp_sum(acc0);
