@@ -29,6 +29,26 @@ extern thread_local std::string g_psi_err;
 
 #define PSI_CK_LAUNCH() PSI_CK(cudaGetLastError())
 
+// Stream-ordered allocation from the device's default memory pool (kept cached: release threshold = max), so that the
+// per-batch graph re-layout does not pay cudaMalloc/cudaFree device synchronisations.
+static inline cudaError_t psi_malloc_async(void** p, size_t bytes, cudaStream_t st) {
+    static thread_local int pool_ready_dev = -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (pool_ready_dev != dev) {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            uint64_t thr = UINT64_MAX;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
+        pool_ready_dev = dev;
+    }
+    return cudaMallocAsync(p, bytes > 0 ? bytes : 16, st);
+}
+static inline void psi_free_async(void* p, cudaStream_t st) {
+    if (p) cudaFreeAsync(p, st);
+}
+
 static inline int64_t round_up64(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
 
 // ---- row access: a latent row is 10 contiguous floats (40 B, 8-byte aligned) -----------------

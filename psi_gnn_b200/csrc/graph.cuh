@@ -175,19 +175,19 @@ static int build_sell(int64_t N, int64_t nnz, const int64_t* ei, const float* at
     void* tmp = nullptr;
     size_t tmp_bytes = 0, tmp2 = 0;
     const int64_t nn = nnz > 0 ? nnz : 1;
-    PSI_CK(cudaMalloc(&keys, nn * sizeof(int)));
-    PSI_CK(cudaMalloc(&vals, nn * sizeof(int)));
-    PSI_CK(cudaMalloc(&skeys, nn * sizeof(int)));
-    PSI_CK(cudaMalloc(&svals, nn * sizeof(int)));
-    PSI_CK(cudaMalloc(&ptr, (N + 2) * sizeof(int)));
-    PSI_CK(cudaMalloc(&slice_recs, (num_slices + 1) * sizeof(int64_t)));
-    PSI_CK(cudaMalloc(&slice_off, (num_slices + 1) * sizeof(int64_t)));
+    PSI_CK(psi_malloc_async((void**)&keys, nn * sizeof(int), st));
+    PSI_CK(psi_malloc_async((void**)&vals, nn * sizeof(int), st));
+    PSI_CK(psi_malloc_async((void**)&skeys, nn * sizeof(int), st));
+    PSI_CK(psi_malloc_async((void**)&svals, nn * sizeof(int), st));
+    PSI_CK(psi_malloc_async((void**)&ptr, (N + 2) * sizeof(int), st));
+    PSI_CK(psi_malloc_async((void**)&slice_recs, (num_slices + 1) * sizeof(int64_t), st));
+    PSI_CK(psi_malloc_async((void**)&slice_off, (num_slices + 1) * sizeof(int64_t), st));
     int end_bit = 1;
     while ((1ll << end_bit) <= N) ++end_bit;   // keys in [0, N]
     PSI_CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, skeys, vals, svals, (int)nnz, 0, end_bit, st));
     PSI_CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp2, slice_recs, slice_off, num_slices + 1, st));
     if (tmp2 > tmp_bytes) tmp_bytes = tmp2;
-    PSI_CK(cudaMalloc(&tmp, tmp_bytes > 0 ? tmp_bytes : 16));
+    PSI_CK(psi_malloc_async(&tmp, tmp_bytes, st));
     if (nnz > 0) {
         k_graph_keys<<<(unsigned)((nnz + 255) / 256), 256, 0, st>>>(nnz, (int)N, ei, by_col ? 1 : 0, msg ? 1 : 0, keys, vals);
         PSI_CK_LAUNCH();
@@ -208,7 +208,7 @@ static int build_sell(int64_t N, int64_t nnz, const int64_t* ei, const float* at
     PSI_CK(cudaStreamSynchronize(st));
     const size_t rec_bytes = msg ? sizeof(int4) : sizeof(int2);
     void* recs = nullptr;
-    PSI_CK(cudaMalloc(&recs, (total > 0 ? total : 1) * rec_bytes));
+    PSI_CK(psi_malloc_async(&recs, (total > 0 ? total : 1) * rec_bytes, st));
     PSI_CK(cudaMemsetAsync(recs, 0xFF, (total > 0 ? total : 1) * rec_bytes, st));   // j = -1 everywhere
     if (N > 0 && nnz > 0) {
         if (msg)
@@ -219,8 +219,8 @@ static int build_sell(int64_t N, int64_t nnz, const int64_t* ei, const float* at
                                                                          slice_off, (int2*)recs);
         PSI_CK_LAUNCH();
     }
-    PSI_CK(cudaStreamSynchronize(st));
-    cudaFree(keys); cudaFree(vals); cudaFree(skeys); cudaFree(svals); cudaFree(ptr); cudaFree(slice_recs); cudaFree(tmp);
+    psi_free_async(keys, st); psi_free_async(vals, st); psi_free_async(skeys, st); psi_free_async(svals, st); psi_free_async(ptr, st);
+    psi_free_async(slice_recs, st); psi_free_async(tmp, st);
     out->recs = recs; out->off = slice_off; out->slots = total; out->kept = kept;
     return 0;
 }

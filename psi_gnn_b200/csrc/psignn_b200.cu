@@ -41,7 +41,7 @@ static void graph_free(psi_graph* g) {
     void* ps[] = {g->p_recs_T, g->p_recs_F, g->p_recs_Ar, g->p_recs_Ac, g->p_off_T, g->p_off_F, g->p_off_Ar, g->p_off_Ac,
                   g->p_xm_T, g->p_xm_F, g->p_tag, g->p_prb, g->p_nrm, g->p_vjp, g->p_scratch};
     for (void* p : ps)
-        if (p) cudaFree(p);
+        if (p) psi_free_async(p, nullptr);      // legacy default stream: ordered after the work torch's default stream has queued
     delete g;
 }
 
@@ -75,7 +75,7 @@ extern "C" int psi_graph_create(psi_graph_t** out, int64_t num_nodes, int64_t nn
     }
     // node data
     unsigned long long* counts = nullptr;
-    if (cudaMalloc(&g->p_tag, N1) != cudaSuccess || cudaMalloc(&counts, 2 * sizeof(unsigned long long)) != cudaSuccess) {
+    if (psi_malloc_async(&g->p_tag, N1, st) != cudaSuccess || psi_malloc_async((void**)&counts, 2 * sizeof(unsigned long long), st) != cudaSuccess) {
         graph_free(g); PSI_FAIL("psi_graph_create: out of device memory");
     }
     cudaMemsetAsync(counts, 0, 2 * sizeof(unsigned long long), st);
@@ -83,19 +83,19 @@ extern "C" int psi_graph_create(psi_graph_t** out, int64_t num_nodes, int64_t nn
         k_graph_tags<<<(unsigned)((num_nodes + 255) / 256), 256, 0, st>>>((int)num_nodes, dev_tags, tag_dim, (uint8_t*)g->p_tag, counts);
     }
     if (prb_dim > 0) {
-        if (cudaMalloc(&g->p_prb, N1 * prb_dim * sizeof(float)) != cudaSuccess) { graph_free(g); PSI_FAIL("psi_graph_create: out of device memory"); }
+        if (psi_malloc_async(&g->p_prb, N1 * prb_dim * sizeof(float), st) != cudaSuccess) { graph_free(g); PSI_FAIL("psi_graph_create: out of device memory"); }
         if (num_nodes > 0) cudaMemcpyAsync(g->p_prb, dev_prb, num_nodes * prb_dim * sizeof(float), cudaMemcpyDeviceToDevice, st);
     }
     if (dev_normals != nullptr) {
-        if (cudaMalloc(&g->p_nrm, N1 * 2 * sizeof(float)) != cudaSuccess) { graph_free(g); PSI_FAIL("psi_graph_create: out of device memory"); }
+        if (psi_malloc_async(&g->p_nrm, N1 * 2 * sizeof(float), st) != cudaSuccess) { graph_free(g); PSI_FAIL("psi_graph_create: out of device memory"); }
         if (num_nodes > 0) cudaMemcpyAsync(g->p_nrm, dev_normals, num_nodes * 2 * sizeof(float), cudaMemcpyDeviceToDevice, st);
     }
     g->scratch_floats = 2 * (int64_t)node_grid(N1) + 8;
-    if (cudaMalloc(&g->p_scratch, g->scratch_floats * sizeof(float)) != cudaSuccess) { graph_free(g); PSI_FAIL("psi_graph_create: out of device memory"); }
+    if (psi_malloc_async((void**)&g->p_scratch, g->scratch_floats * sizeof(float), st) != cudaSuccess) { graph_free(g); PSI_FAIL("psi_graph_create: out of device memory"); }
     unsigned long long hc[2] = {0, 0};
     cudaMemcpyAsync(hc, counts, sizeof(hc), cudaMemcpyDeviceToHost, st);
     cudaError_t e = cudaStreamSynchronize(st);
-    cudaFree(counts);
+    psi_free_async(counts, st);
     if (e != cudaSuccess || (e = cudaGetLastError()) != cudaSuccess) {
         graph_free(g);
         PSI_FAIL(std::string("psi_graph_create: ") + cudaGetErrorString(e));
@@ -163,17 +163,17 @@ extern "C" int psi_layer_forward(const psi_graph_t* g, int kind, const float* de
     if (check_kind(g, kind)) return -1;
     if (g->N > 0 && (dev_h == nullptr || dev_out == nullptr)) PSI_FAIL("psi_layer_forward: null pointer");
     if (g->N > 0 && kind != PSI_KIND_DSS && dev_h0 == nullptr) PSI_FAIL("psi_layer_forward: null h0");
-    if (dev_h == dev_out) PSI_FAIL("psi_layer_forward: in-place application is not supported");
+    if (g->N > 0 && dev_h == dev_out) PSI_FAIL("psi_layer_forward: in-place application is not supported");
     return launch_layer<false>(g, kind, dev_h, dev_h0, dev_out, SolverEpi{nullptr, nullptr, nullptr, nullptr}, as_stream(stream));
 }
 
-static int vjp_alloc(psi_graph* g) {
+static int vjp_alloc(psi_graph* g, cudaStream_t st) {
     if (g->p_vjp != nullptr) return 0;
     const int64_t N = g->N > 0 ? g->N : 1;
     const int64_t floats = N * (10 + 1 + 1 + 10 + 30 + 1 + 20 + 10);
-    PSI_CK(cudaMalloc(&g->p_vjp, floats * sizeof(float)));
-    PSI_CK(cudaMalloc(&g->p_xm_T, (g->slots_T > 0 ? g->slots_T : 1) * sizeof(uint32_t)));
-    PSI_CK(cudaMalloc(&g->p_xm_F, (g->slots_F > 0 ? g->slots_F : 1) * sizeof(uint32_t)));
+    PSI_CK(psi_malloc_async(&g->p_vjp, floats * sizeof(float), st));
+    PSI_CK(psi_malloc_async(&g->p_xm_T, (g->slots_T > 0 ? g->slots_T : 1) * sizeof(uint32_t), st));
+    PSI_CK(psi_malloc_async(&g->p_xm_F, (g->slots_F > 0 ? g->slots_F : 1) * sizeof(uint32_t), st));
     float* p = (float*)g->p_vjp;
     VjpCacheDev& C = g->vjp;
     C.rhat = p; p += N * 10;
@@ -195,8 +195,8 @@ extern "C" int psi_vjp_prepare(psi_graph_t* g, int kind, const float* dev_hstar,
     if (check_kind(g, kind)) return -1;
     if (kind != PSI_KIND_DIRICHLET && kind != PSI_KIND_MIXED) PSI_FAIL("psi_vjp_prepare: VJP exists for the PSI-GNN layers only");
     if (g->N > 0 && dev_hstar == nullptr) PSI_FAIL("psi_vjp_prepare: null pointer");
-    if (vjp_alloc(g)) return -1;
     cudaStream_t st = as_stream(stream);
+    if (vjp_alloc(g, st)) return -1;
     if (g->N > 0) {
         PSI_CK(cudaMemsetAsync(g->p_xm_T, 0, (g->slots_T > 0 ? g->slots_T : 1) * sizeof(uint32_t), st));
         PSI_CK(cudaMemsetAsync(g->p_xm_F, 0, (g->slots_F > 0 ? g->slots_F : 1) * sizeof(uint32_t), st));
