@@ -244,7 +244,7 @@ def run_native(args):
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(args, family, h, budget_s=25.0)
-        print(json.dumps(out))
+        emit(out)
     if world > 1:
         dist.destroy_process_group()
 
@@ -329,10 +329,27 @@ def run_reference(args):
            "iterations_per_s": round(its / dt, 2),
            "cpu_baseline": {"value": round(val, 4), "unit": "graphs/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample_txt},
            "e2e": {"value": round(val, 4), "unit": "graphs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(out))
+    emit(out)
+
+
+_REAL_STDOUT = None
+
+
+def emit(obj):
+    """the ONE JSON line goes to the real stdout; everything else (NCCL banners, library chatter) was redirected to stderr"""
+    line = json.dumps(obj) + "\n"
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, line.encode())
+    else:
+        sys.stdout.write(line)
+        sys.stdout.flush()
 
 
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)

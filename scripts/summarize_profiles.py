@@ -1,0 +1,77 @@
+"""Turns the ncu outputs in gpurun_out/ into the tracked summaries under profiles/.
+
+    python scripts/summarize_profiles.py <tag> [launches.csv] [prof_a.ncu-rep prof_b.ncu-rep ...]
+"""
+import collections
+import csv
+import os
+import re
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__bytes_read.sum.per_second",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "launch__registers_per_thread", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct",
+        "smsp__inst_executed.sum", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "launch__waves_per_multiprocessor",
+        "launch__shared_mem_per_block_dynamic"]
+
+
+def launches(path, out):
+    lines = [l for l in open(path) if l.startswith('"')]
+    agg = collections.OrderedDict()
+    tot = 0.0
+    n = 0
+    for row in csv.DictReader(lines):
+        name = re.sub(r"<.*", "", row["Kernel Name"]).split("(")[0].replace("void ", "")
+        t = float(row["Metric Value"])
+        a = agg.setdefault(name, [0, 0.0])
+        a[0] += 1
+        a[1] += t
+        tot += t
+        n += 1
+    out.write("## Launch list (ncu --metrics gpu__time_duration.sum --clock-control none), %d launches, %.1f ms of kernel time\n\n" % (n, tot / 1e6))
+    out.write("Per-launch times under ncu are cold-cache and serialised: compare SHARES with bench.py's `kernels`, not absolutes.\n\n")
+    out.write("| kernel | launches | total ms | share | avg µs |\n|---|---:|---:|---:|---:|\n")
+    for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:24]:
+        out.write("| `%s` | %d | %.3f | %.2f %% | %.1f |\n" % (k[:80], v[0], v[1] / 1e6, 100 * v[1] / tot, v[1] / v[0] / 1e3))
+    out.write("\n")
+
+
+def full(path, out):
+    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units = rows[0], rows[1]
+    out.write("## `%s` (ncu --set full --clock-control none --import-source on)\n\n" % os.path.basename(path))
+    seen = set()
+    for r in rows[2:]:
+        name = r[hdr.index("Kernel Name")].split("(")[0]
+        grid, block = r[hdr.index("Grid Size")], r[hdr.index("Block Size")]
+        if (name, grid) in seen:
+            continue
+        seen.add((name, grid))
+        out.write("### `%s` grid %s block %s\n\n| metric | value |\n|---|---|\n" % (name, grid, block))
+        for k in KEYS:
+            if k in hdr:
+                out.write("| %s | %s %s |\n" % (k, r[hdr.index(k)], units[hdr.index(k)]))
+        rd = float(r[hdr.index("dram__bytes_read.sum")]) if "dram__bytes_read.sum" in hdr else 0
+        wr = float(r[hdr.index("dram__bytes_write.sum")]) if "dram__bytes_write.sum" in hdr else 0
+        out.write("| **traffic (read+write)** | %.4g %s |\n\n" % (rd + wr, units[hdr.index("dram__bytes_read.sum")]))
+
+
+def main():
+    tag = sys.argv[1]
+    os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
+    with open(os.path.join(ROOT, "profiles", tag + ".md"), "w") as out:
+        out.write("# ncu summary %s\n\nCommand: `python bench.py --steps 1 --warmup 1 --no-cpu-baseline` (C3, 1 × B200).\n\n" % tag)
+        for a in sys.argv[2:]:
+            if a.endswith(".csv"):
+                launches(a, out)
+            else:
+                full(a, out)
+    print("wrote profiles/%s.md" % tag)
+
+
+if __name__ == "__main__":
+    main()
