@@ -47,6 +47,7 @@ extern "C" {
 
 typedef struct psi_graph  psi_graph_t;    /* re-laid-out batch of meshes (destination-sorted, warp-sliced CSR) */
 typedef struct psi_solver psi_solver_t;   /* fixed-point solver workspace (iterate, residual, U/V history)      */
+typedef struct psi_comm   psi_comm_t;     /* NCCL communicator of a mesh-partitioned solve                      */
 
 /* result block of a solve (mirrors the dict returned by the reference solvers) */
 typedef struct psi_solve_stats {
@@ -82,6 +83,21 @@ int psi_graph_destroy(psi_graph_t* g);
 /* info[0]=N, [1]=E (off-diagonal edges), [2]=nnz, [3]=#dirichlet, [4]=#neumann,
  * [5]=slots 'to' list, [6]=slots 'from' list, [7]=bytes owned by the handle */
 int psi_graph_info(const psi_graph_t* g, int64_t info[8]);
+
+/* ---- mesh-partitioned solve (one large mesh split by node ranges over the ranks; replaces nothing in the reference, whose only
+ * parallelism is PyG DataParallel at dirichlet/psignn/main.py:106 — this is BASELINE config 5) ------------------------------------
+ * Local numbering of a rank: owned nodes [0, n_owned), then ghost nodes grouped by owning peer in the order of peer_ranks.
+ * The graph is created over owned + ghost nodes; after psi_graph_set_partition the operator produces the owned rows only, ghost rows
+ * of the iterate are refreshed from their owners before every operator evaluation (ncclSend/ncclRecv on the caller's stream), and the
+ * Broyden inner products and norms are all-reduced (2 small fp64 all-reduces per step).  NCCL is resolved with dlopen at run time. */
+int psi_comm_unique_id(char out[128]);                                   /* rank 0; broadcast the bytes to the other ranks */
+int psi_comm_create(psi_comm_t** out, int rank, int world, const char id[128]);
+int psi_comm_destroy(psi_comm_t* c);
+int psi_graph_set_partition(psi_graph_t* g, psi_comm_t* comm, int64_t n_owned, int n_peers, const int32_t* peer_ranks /* host */,
+                            const int64_t* send_counts /* host, rows per peer */, const int64_t* recv_counts /* host */,
+                            const int32_t* dev_send_index /* device: owned local rows to send, concatenated per peer */, void* stream);
+/* refresh the ghost rows of a [N, width] fp32 array (width 2, 10 or 20) from their owners */
+int psi_halo_exchange(psi_graph_t* g, float* dev_vec, int width, void* stream);
 
 /* ---- one application of the layer and its transpose-Jacobian --------------------------------- */
 int psi_layer_forward(const psi_graph_t* g, int kind, const float* dev_h, const float* dev_h0,

@@ -34,6 +34,11 @@ SIGNATURES = {
                                  c_void_p, c_int, c_void_p, c_void_p]),
     "psi_graph_destroy": (c_int, [c_void_p]),
     "psi_graph_info": (c_int, [c_void_p, POINTER(c_int64)]),
+    "psi_comm_unique_id": (c_int, [ctypes.c_char_p]),
+    "psi_comm_create": (c_int, [POINTER(c_void_p), c_int, c_int, ctypes.c_char_p]),
+    "psi_comm_destroy": (c_int, [c_void_p]),
+    "psi_graph_set_partition": (c_int, [c_void_p, c_void_p, c_int64, c_int, POINTER(c_int32), POINTER(c_int64), POINTER(c_int64), c_void_p, c_void_p]),
+    "psi_halo_exchange": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
     "psi_layer_forward": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "psi_vjp_prepare": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "psi_vjp_apply": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -4,9 +4,9 @@
 // (the whole batch is one vector of numel = N·d).  Inverse-Jacobian approximation B = −I + U Vᵀ.
 //
 // Per step n (after the operator kernel produced g_n, δg and the norm partials):
-//   pass 1  k_qn_dots : a = U[:n-1]ᵀδx, c = V[:n-1]ᵀδg, e = V[:n-1]ᵀg_n      reads U,V once   (solver.py:103,113)
+//   pass 1  k_qn_dots_tma : a = U[:n-1]ᵀδx, c = V[:n-1]ᵀδg, e = V[:n-1]ᵀg_n      reads U,V once   (solver.py:103,113)
 //           k_qn_fin1 : reduce partials; ‖g‖, rel; best/trace/stop rules on the device  (solver.py:162-183)
-//   pass 2  k_qn_axpy : v_n = −δx + V·a ; w = U·c ; t = U·e ; ⟨v_n,δg⟩, ⟨v_n,g_n⟩     reads U,V once   (solver.py:186-192)
+//   pass 2  k_qn_axpy_tma : v_n = −δx + V·a ; w = U·c ; t = U·e ; ⟨v_n,δg⟩, ⟨v_n,g_n⟩     reads U,V once   (solver.py:186-192)
 //           k_qn_fin2 : u_n = (δx − (−δg + w))/⟨v_n,δg⟩ ; update = −(−g_n + t + u_n⟨v_n,g_n⟩) ; x ← x + update
 // = 4(n−1) history vectors of traffic per step (the reference's op order costs 6n−4) while still forming
 // the reference's u_n, v_n, update_n from fresh dot products (no cached Vᵀg — that drifts).
@@ -17,7 +17,6 @@
 
 #define QN_CHUNK 1024            // elements per CTA-chunk (256 threads × float4)
 #define QN_THREADS 256
-#define QN_KTILE 8               // history vectors per CTA in pass 1
 #define QN_MAX_SLABS 16
 #define QN_AXPY_MAX_CTAS (PSI_NUM_SMS_B200 * 8)
 
@@ -58,53 +57,57 @@ __device__ __forceinline__ float dot4(const float4& a, const float4& b, float ac
     return acc;
 }
 
-// ---- pass 1: dot products against the history -------------------------------------------------------
-// grid (num_chunks, ceil((n-1)/QN_KTILE)); partial[(k*3+q)*num_chunks + chunk]
-__global__ void __launch_bounds__(QN_THREADS)
-k_qn_dots(QnHistory H, int nhist, const float* __restrict__ dx, const float* __restrict__ dg, const float* __restrict__ g,
-          float* __restrict__ partial, int num_chunks, const int* __restrict__ done) {
-    __shared__ float smem[3 * QN_KTILE * (QN_THREADS / 32)];
-    if (*done) return;
-    const int chunk = blockIdx.x;
-    const int64_t e0 = (int64_t)chunk * QN_CHUNK + threadIdx.x * 4;
-    const float4 vdx = *reinterpret_cast<const float4*>(dx + e0);
-    const float4 vdg = *reinterpret_cast<const float4*>(dg + e0);
-    const float4 vg = *reinterpret_cast<const float4*>(g + e0);
-    const int k0 = blockIdx.y * QN_KTILE;
-    float acc[3 * QN_KTILE];
-    float4 u[QN_KTILE], v[QN_KTILE];
+// pass 1 (k_qn_dots_tma) and pass 2 (k_qn_axpy_tma) live in qn_tma.cuh
+
+// stopping rules of the reference loop (solver.py:160-183), evaluated by one warp in double precision
+__device__ __forceinline__ void qn_decide(int lane, double n1, double n2, QnCtrl* __restrict__ ctrl, double* __restrict__ rel_trace,
+                                          double* __restrict__ abs_trace, int step, double eps, double protect, int threshold) {
+    // plateau rule needs max/min over the last 30 rel values (incl. this one)
+    double rel = 0.0, absd = 0.0;
+    bool finite = true;
+    if (lane == 0) {
+        const float na = (float)sqrt(n1), nb = (float)sqrt(n2);       // torch.norm(...) returns fp32
+        finite = isfinite(na) && isfinite(nb);
+        absd = (double)na;
+        rel = absd / ((double)nb + 1e-9);
+        rel_trace[step - 1] = rel;
+        abs_trace[step - 1] = absd;
+    }
+    rel = __shfl_sync(0xffffffffu, rel, 0);
+    __syncwarp();
+    double mx = -1.0, mn = 1e300;
+    if (step > 30) {
+        // 30 most recent entries: indices step-30 .. step-1 ; lane 0 holds the newest which may not be visible
+        // to other lanes through memory yet, so it is injected from the register.
+        if (lane < 30) {
+            const int idx = step - 30 + lane;
+            const double v = (idx == step - 1) ? rel : rel_trace[idx];
+            mx = v; mn = v;
+        }
 #pragma unroll
-    for (int kk = 0; kk < QN_KTILE; ++kk) {
-        const int k = k0 + kk;
-        if (k < nhist) {
-            u[kk] = ld4_stream(hist_u(H, k) + e0);
-            v[kk] = ld4_stream(hist_v(H, k) + e0);
-        } else {
-            u[kk] = make_float4(0.f, 0.f, 0.f, 0.f);
-            v[kk] = u[kk];
+        for (int o = 16; o > 0; o >>= 1) {
+            mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
         }
     }
-#pragma unroll
-    for (int kk = 0; kk < QN_KTILE; ++kk) {
-        acc[3 * kk + 0] = dot4(u[kk], vdx, 0.f);
-        acc[3 * kk + 1] = dot4(v[kk], vdg, 0.f);
-        acc[3 * kk + 2] = dot4(v[kk], vg, 0.f);
-    }
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int i = 0; i < 3 * QN_KTILE; ++i) {
-        const float s = warp_sum(acc[i]);
-        if (lane == 0) smem[i * (QN_THREADS / 32) + warp] = s;
-    }
-    __syncthreads();
-    if (threadIdx.x < 3 * QN_KTILE) {
-        const int i = threadIdx.x, kk = i / 3, q = i % 3, k = k0 + kk;
-        if (k < nhist) {
-            float s = 0.f;
-#pragma unroll
-            for (int w = 0; w < QN_THREADS / 32; ++w) s += smem[i * (QN_THREADS / 32) + w];
-            partial[((int64_t)k * 3 + q) * num_chunks + chunk] = s;
+    if (lane == 0) {
+        int improved = 0;
+        if (step == 1) ctrl->first_rel = rel;
+        if (rel < ctrl->best_rel) { ctrl->best_rel = rel; ctrl->best_step_rel = step; improved = 1; }
+        if (absd < ctrl->best_abs) { ctrl->best_abs = absd; ctrl->best_step_abs = step; }
+        ctrl->improved = improved;
+        ctrl->nstep = step;
+        int stop = 0;
+        if (rel < eps) stop = 1;
+        else if (rel < 3.0 * eps && step > 30 && mx / mn < 1.3) stop = 2;
+        else if (rel > ctrl->first_rel * protect) { stop = 3; ctrl->prot_break = 1; }
+        if (!finite && stop == 0) {
+            // NaN/Inf residual: every comparison above is false in the reference as well, the loop runs on
+            // to the threshold producing NaNs.  The outcome (best iterate so far) is unchanged by stopping now.
+            stop = 4;
         }
+        if (step >= threshold && stop == 0) stop = 5;      // while nstep < threshold
+        if (stop) { ctrl->stop_reason = stop; ctrl->done = 1; }
     }
 }
 
@@ -134,129 +137,61 @@ k_qn_fin1(int nhist, const float* __restrict__ partial, int num_chunks, float* _
         }
         n1 = warp_sum_d(n1);
         n2 = warp_sum_d(n2);
-        // plateau rule needs max/min over the last 30 rel values (incl. this one)
-        double rel = 0.0, absd = 0.0;
-        bool finite = true;
-        if (lane == 0) {
-            const float na = (float)sqrt(n1), nb = (float)sqrt(n2);       // torch.norm(...) returns fp32
-            finite = isfinite(na) && isfinite(nb);
-            absd = (double)na;
-            rel = absd / ((double)nb + 1e-9);
-            rel_trace[step - 1] = rel;
-            abs_trace[step - 1] = absd;
-        }
-        rel = __shfl_sync(0xffffffffu, rel, 0);
-        __syncwarp();
-        double mx = -1.0, mn = 1e300;
-        if (step > 30) {
-            // 30 most recent entries: indices step-30 .. step-1 ; lane 0 holds the newest which may not be visible
-            // to other lanes through memory yet, so it is injected from the register.
-            if (lane < 30) {
-                const int idx = step - 30 + lane;
-                const double v = (idx == step - 1) ? rel : rel_trace[idx];
-                mx = v; mn = v;
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-                mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-            }
-        }
-        if (lane == 0) {
-            int improved = 0;
-            if (step == 1) ctrl->first_rel = rel;
-            if (rel < ctrl->best_rel) { ctrl->best_rel = rel; ctrl->best_step_rel = step; improved = 1; }
-            if (absd < ctrl->best_abs) { ctrl->best_abs = absd; ctrl->best_step_abs = step; }
-            ctrl->improved = improved;
-            ctrl->nstep = step;
-            int stop = 0;
-            if (rel < eps) stop = 1;
-            else if (rel < 3.0 * eps && step > 30 && mx / mn < 1.3) stop = 2;
-            else if (rel > ctrl->first_rel * protect) { stop = 3; ctrl->prot_break = 1; }
-            if (!finite && stop == 0) {
-                // NaN/Inf residual: every comparison above is false in the reference as well, the loop runs on
-                // to the threshold producing NaNs.  The outcome (best iterate so far) is unchanged by stopping now.
-                stop = 4;
-            }
-            if (step >= threshold && stop == 0) stop = 5;      // while nstep < threshold
-            if (stop) { ctrl->stop_reason = stop; ctrl->done = 1; }
-        }
+        qn_decide(lane, n1, n2, ctrl, rel_trace, abs_trace, step, eps, protect, threshold);
     }
 }
 
-// ---- pass 2: low-rank axpys ------------------------------------------------------------------------------
-// persistent over chunks; partial2[q*gridDim.x + cta]
-__global__ void __launch_bounds__(QN_THREADS)
-k_qn_axpy(QnHistory H, int nhist, int n, const float* __restrict__ coef, int cap, float* __restrict__ dx_upd /* in: δx, out: g − t */,
-          float* __restrict__ dg_t /* in: δg, out: unused */, const float* __restrict__ g, const float* __restrict__ x,
-          float* __restrict__ best_x, float* __restrict__ partial2, int num_chunks, const QnCtrl* __restrict__ ctrl) {
-    extern __shared__ float s_coef[];     // [3][nhist]
-    __shared__ float smem[2 * (QN_THREADS / 32)];
-    const int improved = ctrl->improved, done = ctrl->done;
-    if (done && !improved) return;
-    if (improved) {                        // lowest_xest = x_est.clone()  (solver.py:172)
-        for (int chunk = blockIdx.x; chunk < num_chunks; chunk += gridDim.x) {
-            const int64_t e0 = (int64_t)chunk * QN_CHUNK + threadIdx.x * 4;
-            *reinterpret_cast<float4*>(best_x + e0) = *reinterpret_cast<const float4*>(x + e0);
+// ---- mesh-partitioned variant: local sums → (NCCL all-reduce of the fp64 buffer) → coefficients + stop rules -------------
+// dbuf[row] = Σ_chunks partial[row], row = k*3+q ; dbuf[3·nhist] = Σ‖g‖² partials ; dbuf[3·nhist+1] = Σ‖f‖² partials
+__global__ void __launch_bounds__(256)
+k_qn_fin1_local(int nhist, const float* __restrict__ partial, int num_chunks, double* __restrict__ dbuf, const float* __restrict__ norm_part,
+                int norm_blocks, const QnCtrl* __restrict__ ctrl) {
+    if (ctrl->done) return;
+    const int lane = threadIdx.x & 31;
+    const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int row = gwarp; row < nhist * 3; row += nwarps) {
+        const float* p = partial + (int64_t)row * num_chunks;
+        double s = 0.0;
+        for (int i = lane; i < num_chunks; i += 32) s += (double)p[i];
+        s = warp_sum_d(s);
+        if (lane == 0) dbuf[row] = s;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < 32) {
+        double n1 = 0.0, n2 = 0.0;
+        for (int i = lane; i < norm_blocks; i += 32) {
+            n1 += (double)norm_part[i];
+            n2 += (double)norm_part[norm_blocks + i];
         }
+        n1 = warp_sum_d(n1);
+        n2 = warp_sum_d(n2);
+        if (lane == 0) { dbuf[3 * nhist] = n1; dbuf[3 * nhist + 1] = n2; }
     }
-    if (done) return;
-    for (int i = threadIdx.x; i < nhist; i += QN_THREADS) {
-        s_coef[i] = coef[i];
-        s_coef[nhist + i] = coef[cap + i];
-        s_coef[2 * nhist + i] = coef[2 * cap + i];
-    }
+}
+
+__global__ void __launch_bounds__(256)
+k_qn_fin1_global(int nhist, const double* __restrict__ dbuf, float* __restrict__ coef, int cap, QnCtrl* __restrict__ ctrl,
+                 double* __restrict__ rel_trace, double* __restrict__ abs_trace, int step, double eps, double protect, int threshold) {
+    if (ctrl->done) return;
+    __shared__ int was_done;
+    for (int row = threadIdx.x; row < nhist * 3; row += blockDim.x) coef[(row % 3) * cap + row / 3] = (float)dbuf[row];
+    if (threadIdx.x < 32) qn_decide(threadIdx.x, dbuf[3 * nhist], dbuf[3 * nhist + 1], ctrl, rel_trace, abs_trace, step, eps, protect, threshold);
+    (void)was_done;
+}
+
+// Σ of the pass-2 partials → sp[0] = ⟨v_n,δg⟩, sp[1] = ⟨v_n,g_n⟩ (local part, all-reduced before k_qn_fin2)
+__global__ void __launch_bounds__(256) k_qn_red2(const float* __restrict__ partial2, int p2_ctas, double* __restrict__ sp, const QnCtrl* __restrict__ ctrl) {
+    __shared__ double sm[16];
+    if (ctrl->done) return;
+    double a = 0.0, b = 0.0;
+    for (int i = threadIdx.x; i < p2_ctas; i += 256) { a += (double)partial2[i]; b += (double)partial2[p2_ctas + i]; }
+    a = warp_sum_d(a); b = warp_sum_d(b);
+    if ((threadIdx.x & 31) == 0) { sm[threadIdx.x >> 5] = a; sm[8 + (threadIdx.x >> 5)] = b; }
     __syncthreads();
-    float* vn_dst = hist_v(H, n - 1);
-    float* un_dst = hist_u(H, n - 1);
-    float acc[2] = {0.f, 0.f};
-    for (int chunk = blockIdx.x; chunk < num_chunks; chunk += gridDim.x) {
-        const int64_t e0 = (int64_t)chunk * QN_CHUNK + threadIdx.x * 4;
-        float4 av = make_float4(0.f, 0.f, 0.f, 0.f), aw = av, at = av;
-        int k = 0;
-        for (; k + 4 <= nhist; k += 4) {
-            float4 u[4], v[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                u[q] = ld4_stream(hist_u(H, k + q) + e0);
-                v[q] = ld4_stream(hist_v(H, k + q) + e0);
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const float a = s_coef[k + q], c = s_coef[nhist + k + q], e = s_coef[2 * nhist + k + q];
-                av.x = fmaf(a, v[q].x, av.x); av.y = fmaf(a, v[q].y, av.y); av.z = fmaf(a, v[q].z, av.z); av.w = fmaf(a, v[q].w, av.w);
-                aw.x = fmaf(c, u[q].x, aw.x); aw.y = fmaf(c, u[q].y, aw.y); aw.z = fmaf(c, u[q].z, aw.z); aw.w = fmaf(c, u[q].w, aw.w);
-                at.x = fmaf(e, u[q].x, at.x); at.y = fmaf(e, u[q].y, at.y); at.z = fmaf(e, u[q].z, at.z); at.w = fmaf(e, u[q].w, at.w);
-            }
-        }
-        for (; k < nhist; ++k) {
-            const float4 u = ld4_stream(hist_u(H, k) + e0);
-            const float4 v = ld4_stream(hist_v(H, k) + e0);
-            const float a = s_coef[k], c = s_coef[nhist + k], e = s_coef[2 * nhist + k];
-            av.x = fmaf(a, v.x, av.x); av.y = fmaf(a, v.y, av.y); av.z = fmaf(a, v.z, av.z); av.w = fmaf(a, v.w, av.w);
-            aw.x = fmaf(c, u.x, aw.x); aw.y = fmaf(c, u.y, aw.y); aw.z = fmaf(c, u.z, aw.z); aw.w = fmaf(c, u.w, aw.w);
-            at.x = fmaf(e, u.x, at.x); at.y = fmaf(e, u.y, at.y); at.z = fmaf(e, u.z, at.z); at.w = fmaf(e, u.w, at.w);
-        }
-        const float4 vdx = *reinterpret_cast<const float4*>(dx_upd + e0);
-        const float4 vdg = *reinterpret_cast<const float4*>(dg_t + e0);
-        const float4 vg = *reinterpret_cast<const float4*>(g + e0);
-        // vT = −δx + Σ a_k V_k  (rmatvec, solver.py:104)
-        float4 vn = make_float4(-vdx.x + av.x, -vdx.y + av.y, -vdx.z + av.z, -vdx.w + av.w);
-        acc[0] = dot4(vn, vdg, acc[0]);                                   // ⟨vT, δg⟩ uses the un-scrubbed vT (solver.py:187)
-        // vT[vT != vT] = 0  (solver.py:188)
-        vn.x = (vn.x != vn.x) ? 0.f : vn.x; vn.y = (vn.y != vn.y) ? 0.f : vn.y;
-        vn.z = (vn.z != vn.z) ? 0.f : vn.z; vn.w = (vn.w != vn.w) ? 0.f : vn.w;
-        acc[1] = dot4(vn, vg, acc[1]);                                    // V[n-1]ᵀ g_n for the new update
-        // numerator of u:  δx − matvec(δg) = δx − (−δg + Σ c_k U_k)   (solver.py:114,187)
-        const float4 un = make_float4(vdx.x - (-vdg.x + aw.x), vdx.y - (-vdg.y + aw.y), vdx.z - (-vdg.z + aw.z), vdx.w - (-vdg.w + aw.w));
-        *reinterpret_cast<float4*>(vn_dst + e0) = vn;
-        *reinterpret_cast<float4*>(un_dst + e0) = un;
-        *reinterpret_cast<float4*>(dx_upd + e0) = at;                     // t = Σ e_k U_k, finished in k_qn_fin2
-    }
-    block_sum<2, QN_THREADS / 32>(acc, smem);
     if (threadIdx.x == 0) {
-        partial2[blockIdx.x] = acc[0];
-        partial2[gridDim.x + blockIdx.x] = acc[1];
+        double sa = 0.0, sb = 0.0;
+        for (int w = 0; w < 8; ++w) { sa += sm[w]; sb += sm[8 + w]; }
+        sp[0] = sa; sp[1] = sb;
     }
 }
 
@@ -264,11 +199,17 @@ k_qn_axpy(QnHistory H, int nhist, int n, const float* __restrict__ coef, int cap
 __global__ void __launch_bounds__(QN_THREADS)
 k_qn_fin2(QnHistory H, int n, float* __restrict__ dx_upd /* in: t, out: δx of the next step */, const float* __restrict__ g,
           float* __restrict__ x, const float* __restrict__ partial2, int p2_ctas, float* __restrict__ xtrace_next,
-          QnCtrl* __restrict__ ctrl, int num_chunks) {
+          QnCtrl* __restrict__ ctrl, int num_chunks, const double* __restrict__ sp_global) {
     __shared__ double sm[2 * (QN_THREADS / 32)];
     __shared__ float s_sp[2];
     if (ctrl->done) return;
-    {   // every CTA reduces the pass-2 partials in the same fixed order → identical s, p everywhere
+    if (sp_global != nullptr) {   // mesh-partitioned solve: the sums were all-reduced over the ranks
+        if (threadIdx.x == 0) {
+            s_sp[0] = (float)sp_global[0]; s_sp[1] = (float)sp_global[1];
+            if (blockIdx.x == 0) { ctrl->s = sp_global[0]; ctrl->p = sp_global[1]; }
+        }
+        __syncthreads();
+    } else {   // every CTA reduces the pass-2 partials in the same fixed order → identical s, p everywhere
         double a = 0.0, b = 0.0;
         for (int i = threadIdx.x; i < p2_ctas; i += QN_THREADS) { a += (double)partial2[i]; b += (double)partial2[p2_ctas + i]; }
         a = warp_sum_d(a); b = warp_sum_d(b);

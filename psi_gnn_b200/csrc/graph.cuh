@@ -28,6 +28,7 @@ struct SellDev {
 
 struct GraphDev {
     int      N;
+    int      n_compute;         // rows the operator kernels produce: N, or the owned rows of a mesh partition (ghost rows follow)
     int      num_slices;
     int      prb_dim;
     SellDev  T, F, Ar, Ac;
@@ -64,6 +65,7 @@ struct psi_graph {
     void* p_tag = nullptr; void* p_prb = nullptr; void* p_nrm = nullptr;
     void* p_vjp = nullptr;
     float* p_scratch = nullptr;   // small per-graph scratch for residual partial sums
+    struct Partition* part = nullptr;   // set by psi_graph_set_partition (mesh-partitioned solve)
     int64_t scratch_floats = 0;
 };
 

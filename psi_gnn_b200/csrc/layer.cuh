@@ -291,7 +291,7 @@ k_layer_forward(GraphDev G, const float* __restrict__ h, const float* __restrict
     __shared__ float smem[2 * PSI_NODE_BLOCK / 32];
     if (EPI && *E.done) return;
     const int node = blockIdx.x * PSI_NODE_BLOCK + threadIdx.x;
-    const bool valid = node < G.N;
+    const bool valid = node < G.n_compute;
     float hi[PSI_D], fx[PSI_D];
     if (valid) {
         load_row(h, node, hi);

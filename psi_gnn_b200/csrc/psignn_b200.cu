@@ -12,8 +12,10 @@
 #include "broyden.cuh"
 #include "anderson.cuh"
 #include "qn_tma.cuh"
+#include "comm.cuh"
 
 #include <algorithm>
+#include <cstring>
 #include <cmath>
 #include <limits>
 #include <vector>
@@ -40,6 +42,11 @@ extern "C" int psi_weights_upload(const float* dev_blob, int n_floats, void* str
 static void graph_free(psi_graph* g) {
     void* ps[] = {g->p_recs_T, g->p_recs_F, g->p_recs_Ar, g->p_recs_Ac, g->p_off_T, g->p_off_F, g->p_off_Ar, g->p_off_Ac,
                   g->p_xm_T, g->p_xm_F, g->p_tag, g->p_prb, g->p_nrm, g->p_vjp, g->p_scratch};
+    if (g->part != nullptr) {
+        psi_free_async(g->part->send_index, nullptr);
+        psi_free_async(g->part->send_buf, nullptr);
+        delete g->part;
+    }
     for (void* p : ps)
         if (p) psi_free_async(p, nullptr);      // legacy default stream: ordered after the work torch's default stream has queued
     delete g;
@@ -103,6 +110,7 @@ extern "C" int psi_graph_create(psi_graph_t** out, int64_t num_nodes, int64_t nn
     g->n_dir = (int64_t)hc[0]; g->n_neu = (int64_t)hc[1];
     GraphDev& D = g->dev;
     D.N = (int)num_nodes;
+    D.n_compute = (int)num_nodes;
     D.num_slices = (int)((num_nodes + 31) / 32);
     D.prb_dim = prb_dim;
     D.T = SellDev{(const int4*)g->p_recs_T, nullptr, (const int64_t*)g->p_off_T, nullptr};
@@ -131,6 +139,76 @@ extern "C" int psi_graph_info(const psi_graph_t* g, int64_t info[8]) {
     return 0;
 }
 
+// ================================================================================================
+// communicator and mesh partition
+// ================================================================================================
+extern "C" int psi_comm_unique_id(char out[128]) {
+    NcclApi* api = nccl_api();
+    if (!api) PSI_FAIL("psi_comm_unique_id: NCCL is not available");
+    ncclUniqueId id;
+    PSI_NCCL(api->GetUniqueId(&id));
+    memcpy(out, id.internal, 128);
+    return 0;
+}
+
+extern "C" int psi_comm_create(psi_comm_t** out, int rank, int world, const char id[128]) {
+    if (out == nullptr) PSI_FAIL("psi_comm_create: null out");
+    *out = nullptr;
+    if (world < 1 || rank < 0 || rank >= world) PSI_FAIL("psi_comm_create: bad rank/world");
+    psi_comm* c = new psi_comm();
+    c->rank = rank; c->world = world;
+    if (world > 1) {
+        NcclApi* api = nccl_api();
+        if (!api) { delete c; PSI_FAIL("psi_comm_create: NCCL is not available"); }
+        ncclUniqueId uid;
+        memcpy(uid.internal, id, 128);
+        ncclResult_t r = api->CommInitRank(&c->comm, world, uid, rank);
+        if (r != 0) { delete c; PSI_FAIL(std::string("psi_comm_create: ncclCommInitRank -> ") + api->GetErrorString(r)); }
+    }
+    *out = c;
+    return 0;
+}
+
+extern "C" int psi_comm_destroy(psi_comm_t* c) {
+    if (c == nullptr) return 0;
+    if (c->comm != nullptr && nccl_api()) nccl_api()->CommDestroy(c->comm);
+    delete c;
+    return 0;
+}
+
+extern "C" int psi_graph_set_partition(psi_graph_t* g, psi_comm_t* comm, int64_t n_owned, int n_peers, const int32_t* peer_ranks,
+                                       const int64_t* send_counts, const int64_t* recv_counts, const int32_t* dev_send_index, void* stream) {
+    if (g == nullptr || comm == nullptr) PSI_FAIL("psi_graph_set_partition: null handle");
+    if (n_owned < 0 || n_owned > g->N || n_peers < 0) PSI_FAIL("psi_graph_set_partition: bad sizes");
+    cudaStream_t st = as_stream(stream);
+    Partition* P = new Partition();
+    P->comm = comm; P->n_owned = n_owned;
+    for (int i = 0; i < n_peers; ++i) {
+        P->peers.push_back(peer_ranks[i]);
+        P->send_off.push_back(P->total_send); P->recv_off.push_back(P->total_recv);
+        P->send_count.push_back(send_counts[i]); P->recv_count.push_back(recv_counts[i]);
+        P->total_send += send_counts[i]; P->total_recv += recv_counts[i];
+    }
+    if (n_owned + P->total_recv != g->N) { delete P; PSI_FAIL("psi_graph_set_partition: owned + ghost rows must equal the graph's node count"); }
+    if (P->total_send > 0) {
+        if (dev_send_index == nullptr) { delete P; PSI_FAIL("psi_graph_set_partition: null send index"); }
+        if (psi_malloc_async((void**)&P->send_index, P->total_send * sizeof(int32_t), st) != cudaSuccess ||
+            psi_malloc_async((void**)&P->send_buf, P->total_send * 20 * sizeof(float), st) != cudaSuccess) { delete P; PSI_FAIL("psi_graph_set_partition: out of device memory"); }
+        PSI_CK(cudaMemcpyAsync(P->send_index, dev_send_index, P->total_send * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+    }
+    if (g->part != nullptr) { psi_free_async(g->part->send_index, st); psi_free_async(g->part->send_buf, st); delete g->part; }
+    g->part = P;
+    g->dev.n_compute = (int)n_owned;
+    return 0;
+}
+
+// refresh the ghost rows of a [N, width] array from their owners (no-op for an unpartitioned graph)
+extern "C" int psi_halo_exchange(psi_graph_t* g, float* dev_vec, int width, void* stream) {
+    if (g == nullptr) PSI_FAIL("psi_halo_exchange: null graph");
+    if (width != 10 && width != 20 && width != 2) PSI_FAIL("psi_halo_exchange: width must be 2, 10 or 20");
+    return halo_exchange(g->part, dev_vec, width, nullptr, as_stream(stream));
+}
+
 static int check_kind(const psi_graph* g, int kind) {
     if (g == nullptr) PSI_FAIL("null graph handle");
     if (kind < 0 || kind > 3) PSI_FAIL("unknown layer kind");
@@ -147,8 +225,8 @@ static int check_kind(const psi_graph* g, int kind) {
 // ================================================================================================
 template <bool EPI>
 static int launch_layer(const psi_graph* g, int kind, const float* h, const float* h0, float* out, SolverEpi E, cudaStream_t st) {
-    if (g->N == 0) return 0;
-    const unsigned grid = node_grid(g->N);
+    if (g->dev.n_compute == 0) return 0;
+    const unsigned grid = node_grid(g->dev.n_compute);
     switch (kind) {
         case PSI_KIND_DIRICHLET: k_layer_forward<KIND_DIRICHLET, EPI><<<grid, PSI_NODE_BLOCK, 0, st>>>(g->dev, h, h0, out, E); break;
         case PSI_KIND_MIXED:     k_layer_forward<KIND_MIXED, EPI><<<grid, PSI_NODE_BLOCK, 0, st>>>(g->dev, h, h0, out, E); break;
@@ -305,6 +383,10 @@ struct psi_solver {
     // state of the step API
     int threshold = 0; double eps = 0.0; int n = 0; int launches = 0; int f_evals = 0; bool active = false;
     float* xtrace = nullptr; int norm_blocks = 0;
+    // active extent of the current solve: all of numel, or the owned rows of a mesh partition (ghost rows follow in x)
+    int64_t act_numel = 0, last_act = -1; int act_chunks = 0, act_dchunks = 0;
+    double* dbuf = nullptr;               // [3·cap + 8] fp64 sums all-reduced over the ranks of a partitioned solve
+    psi_comm* comm = nullptr;             // communicator of the current solve (nullptr: single rank)
     // optional per-kernel-class timing with CUDA events on the launching stream (psi_solver_profile)
     int profile = 0;
     std::vector<cudaEvent_t> ev;          // [((step * PROF_CLASSES) + cls) * 2 + {begin,end}]
@@ -386,6 +468,7 @@ extern "C" int psi_solver_create(psi_solver_t** out, int64_t numel, int max_thre
     rc |= solver_alloc(s, (void**)&s->coef, (size_t)3 * s->cap * sizeof(float));
     rc |= solver_alloc(s, (void**)&s->norm_part, (size_t)2 * s->norm_cap * sizeof(float));
     rc |= solver_alloc(s, (void**)&s->ctrl, sizeof(QnCtrl));
+    rc |= solver_alloc(s, (void**)&s->dbuf, (size_t)(3 * s->cap + 8) * sizeof(double));
     rc |= solver_alloc(s, (void**)&s->rel_trace, (size_t)(s->cap + 2) * sizeof(double));
     rc |= solver_alloc(s, (void**)&s->abs_trace, (size_t)(s->cap + 2) * sizeof(double));
     if (!rc && cudaMallocHost((void**)&s->h_ctrl, sizeof(QnCtrl)) != cudaSuccess) { g_psi_err = "psi_solver_create: pinned allocation failed"; rc = -1; }
@@ -406,7 +489,7 @@ extern "C" int psi_solver_create(psi_solver_t** out, int64_t numel, int max_thre
 extern "C" int psi_solver_destroy(psi_solver_t* s) {
     if (s == nullptr) return 0;
     void* ps[] = {s->x, s->g, s->dg, s->dx, s->best, s->fx, s->partial, s->partial2, s->coef, s->norm_part, s->ctrl,
-                  s->rel_trace, s->abs_trace, s->and_X, s->and_F, s->and_small};
+                  s->rel_trace, s->abs_trace, s->and_X, s->and_F, s->and_small, s->dbuf};
     for (void* p : ps)
         if (p) cudaFree(p);
     for (int i = 0; i < QN_MAX_SLABS; ++i) {
@@ -453,17 +536,37 @@ static int hist_ensure(psi_solver* s, int k) {
         const size_t b = (size_t)vecs * s->stride * sizeof(float);
         if (solver_alloc(s, (void**)&s->hist.U[s->slabs_alloc], b)) return -1;
         if (solver_alloc(s, (void**)&s->hist.V[s->slabs_alloc], b)) return -1;
+        // the padding beyond the active extent is read by the streaming kernels (times zero) and never written: keep it finite
+        PSI_CK(cudaMemset(s->hist.U[s->slabs_alloc], 0, b));
+        PSI_CK(cudaMemset(s->hist.V[s->slabs_alloc], 0, b));
         ++s->slabs_alloc;
     }
     return 0;
 }
 
 // ---- shared pieces of the Broyden loop ------------------------------------------------------------------
-static int qn_begin(psi_solver* s, const float* x0, int threshold, double eps, float* xtrace, cudaStream_t st) {
+static int qn_begin(psi_solver* s, const float* x0, int threshold, double eps, float* xtrace, cudaStream_t st, int64_t act_numel = -1,
+                    psi_comm* comm = nullptr) {
     if (s == nullptr) PSI_FAIL("null solver handle");
     if (threshold < 0 || threshold > s->cap) PSI_FAIL("threshold exceeds the solver workspace (psi_solver_create max_threshold)");
     if (s->numel > 0 && x0 == nullptr) PSI_FAIL("null x0");
     s->threshold = threshold; s->eps = eps; s->n = 0; s->launches = 0; s->f_evals = 0; s->xtrace = xtrace; s->active = true;
+    s->comm = (comm != nullptr && comm->world > 1) ? comm : nullptr;
+    s->act_numel = (act_numel < 0 || act_numel > s->numel) ? s->numel : act_numel;
+    s->act_chunks = (int)((s->act_numel + QN_CHUNK - 1) / QN_CHUNK);
+    s->act_dchunks = (int)((s->act_numel + DOTS_CH - 1) / DOTS_CH);
+    if (s->last_act != s->act_numel) {
+        // a different extent than the previous solve on this workspace: re-establish the zero padding the kernels rely on
+        const size_t vb = s->stride * sizeof(float);
+        PSI_CK(cudaMemsetAsync(s->g, 0, vb, st)); PSI_CK(cudaMemsetAsync(s->dg, 0, vb, st)); PSI_CK(cudaMemsetAsync(s->dx, 0, vb, st));
+        PSI_CK(cudaMemsetAsync(s->x, 0, vb, st)); PSI_CK(cudaMemsetAsync(s->best, 0, vb, st));
+        for (int i = 0; i < s->slabs_alloc; ++i) {
+            const int first = i * s->hist.slab_vecs;
+            const size_t b = (size_t)std::min(s->hist.slab_vecs, s->cap - first) * vb;
+            PSI_CK(cudaMemsetAsync(s->hist.U[i], 0, b, st)); PSI_CK(cudaMemsetAsync(s->hist.V[i], 0, b, st));
+        }
+        s->last_act = s->act_numel;
+    }
     k_qn_ctrl_init<<<1, 1, 0, st>>>(s->ctrl);
     PSI_CK_LAUNCH();
     if (s->numel > 0) {
@@ -479,7 +582,7 @@ static int qn_begin(psi_solver* s, const float* x0, int threshold, double eps, f
 // after g_0 is in s->g: update_0 = g_0, x_1 = x_0 + update_0
 static int qn_first(psi_solver* s, cudaStream_t st) {
     if (s->threshold == 0) return 0;
-    k_qn_first<<<s->axpy_ctas, QN_THREADS, 0, st>>>(s->dx, s->g, s->x, s->xtrace ? s->xtrace + s->stride : nullptr, s->num_chunks);
+    k_qn_first<<<s->axpy_ctas, QN_THREADS, 0, st>>>(s->dx, s->g, s->x, s->xtrace ? s->xtrace + s->stride : nullptr, s->act_chunks);
     PSI_CK_LAUNCH();
     s->launches += 1;
     return 0;
@@ -490,27 +593,46 @@ static int qn_update(psi_solver* s, int n, int norm_blocks, cudaStream_t st) {
     const int nhist = n - 1;
     if (hist_ensure(s, n - 1)) return -1;
     if (nhist > 0) {
-        const double vec = (double)s->numel * 4.0;
+        const double vec = (double)s->act_numel * 4.0;
         prof_begin(s, n, 1, (2.0 * nhist + 3.0) * vec, st);
-        k_qn_dots_tma<<<s->tma_ctas, TMA_THREADS, dots_tma_smem(), st>>>(s->hist, nhist, s->dx, s->dg, s->g, s->partial, s->dots_chunks,
+        k_qn_dots_tma<<<s->tma_ctas, TMA_THREADS, dots_tma_smem(), st>>>(s->hist, nhist, s->dx, s->dg, s->g, s->partial, s->act_dchunks,
                                                                          &s->ctrl->done);
         prof_end(s, n, 1, st);
         PSI_CK_LAUNCH();
         s->launches += 1;
     }
     const int fin_blocks = std::max(1, std::min(64, (nhist * 3 + 7) / 8));
-    k_qn_fin1<<<fin_blocks, 256, 0, st>>>(nhist, s->partial, s->dots_chunks, s->coef, s->cap, s->norm_part, norm_blocks, s->ctrl,
-                                          s->rel_trace, s->abs_trace, n, s->eps, 1e3 * PSI_D, s->threshold);
-    PSI_CK_LAUNCH();
-    prof_begin(s, n, 2, (2.0 * nhist + 6.0) * (double)s->numel * 4.0, st);
+    if (s->comm == nullptr) {
+        k_qn_fin1<<<fin_blocks, 256, 0, st>>>(nhist, s->partial, s->act_dchunks, s->coef, s->cap, s->norm_part, norm_blocks, s->ctrl,
+                                              s->rel_trace, s->abs_trace, n, s->eps, 1e3 * PSI_D, s->threshold);
+        PSI_CK_LAUNCH();
+    } else {
+        // mesh-partitioned: local fp64 sums → one all-reduce of 3(n−1)+2 doubles → coefficients and stop rules (identical on every rank)
+        k_qn_fin1_local<<<fin_blocks, 256, 0, st>>>(nhist, s->partial, s->act_dchunks, s->dbuf, s->norm_part, norm_blocks, s->ctrl);
+        PSI_CK_LAUNCH();
+        if (allreduce_f64(s->comm, s->dbuf, (size_t)3 * nhist + 2, st)) return -1;
+        k_qn_fin1_global<<<1, 256, 0, st>>>(nhist, s->dbuf, s->coef, s->cap, s->ctrl, s->rel_trace, s->abs_trace, n, s->eps, 1e3 * PSI_D,
+                                            s->threshold);
+        PSI_CK_LAUNCH();
+        s->launches += 1;
+    }
+    prof_begin(s, n, 2, (2.0 * nhist + 6.0) * (double)s->act_numel * 4.0, st);
     k_qn_axpy_tma<<<s->tma_ctas, TMA_THREADS, axpy_tma_smem(nhist), st>>>(s->hist, nhist, n, s->coef, s->cap, s->dx, s->dg, s->g, s->x, s->best,
-                                                                         s->partial2, (s->numel + 3) / 4, s->ctrl);
+                                                                         s->partial2, (s->act_numel + 3) / 4, s->ctrl);
     prof_end(s, n, 2, st);
     PSI_CK_LAUNCH();
     float* xt = s->xtrace ? s->xtrace + (int64_t)(n + 1) * s->stride : nullptr;
     if (n >= s->threshold) xt = nullptr;
-    prof_begin(s, n, 3, 7.0 * (double)s->numel * 4.0, st);
-    k_qn_fin2<<<s->axpy_ctas, QN_THREADS, 0, st>>>(s->hist, n, s->dx, s->g, s->x, s->partial2, s->tma_ctas, xt, s->ctrl, s->num_chunks);
+    double* sp = nullptr;
+    if (s->comm != nullptr) {
+        sp = s->dbuf + 3 * s->cap + 4;
+        k_qn_red2<<<1, 256, 0, st>>>(s->partial2, s->tma_ctas, sp, s->ctrl);
+        PSI_CK_LAUNCH();
+        if (allreduce_f64(s->comm, sp, 2, st)) return -1;
+        s->launches += 1;
+    }
+    prof_begin(s, n, 3, 7.0 * (double)s->act_numel * 4.0, st);
+    k_qn_fin2<<<s->axpy_ctas, QN_THREADS, 0, st>>>(s->hist, n, s->dx, s->g, s->x, s->partial2, s->tma_ctas, xt, s->ctrl, s->act_chunks, sp);
     prof_end(s, n, 3, st);
     PSI_CK_LAUNCH();
     s->launches += 3;
@@ -573,6 +695,7 @@ static int op_eval(psi_solver* s, psi_graph* g, int kind, int op, const float* a
     const int step = s->f_evals;          // evaluation 0 yields g_0, evaluation n belongs to step n
     s->f_evals += 1;
     int rc;
+    if (g->part != nullptr && halo_exchange(g->part, s->x, PSI_D, &s->ctrl->done, st)) return -1;
     prof_begin(s, step, 0, s->op_bytes, st);
     if (op == PSI_OP_LAYER) {
         s->launches += 1;
@@ -606,9 +729,10 @@ extern "C" int psi_solver_broyden(psi_solver_t* s, psi_graph_t* g, int kind, int
     if (g->N * PSI_D != s->numel) PSI_FAIL("psi_solver_broyden: solver workspace size does not match the graph");
     if (g->N > 0 && dev_aux == nullptr && !(op == PSI_OP_LAYER && kind == PSI_KIND_DSS)) PSI_FAIL("psi_solver_broyden: null aux (h0 / grad)");
     cudaStream_t st = as_stream(stream);
-    if (qn_begin(s, dev_x0, threshold, eps, dev_xtrace, st)) return -1;
+    if (g->part != nullptr && op != PSI_OP_LAYER) PSI_FAIL("psi_solver_broyden: the mesh-partitioned solve supports the layer operator");
+    if (qn_begin(s, dev_x0, threshold, eps, dev_xtrace, st, (int64_t)g->dev.n_compute * PSI_D, g->part ? g->part->comm : nullptr)) return -1;
     s->op_bytes = operator_bytes(g, kind, op);
-    const int norm_blocks = (int)node_grid(g->N);
+    const int norm_blocks = (int)node_grid(g->dev.n_compute);
     if (g->N > 0) {
         if (op_eval(s, g, kind, op, dev_aux, nullptr, st)) return -1;        // g_0 = op(x_0) − x_0
         if (qn_first(s, st)) return -1;
@@ -636,8 +760,8 @@ extern "C" const float* psi_broyden_x(const psi_solver_t* s) { return s ? s->x :
 static int qn_post(psi_solver* s, const float* fx, cudaStream_t st) {
     if (s->numel == 0) return 0;
     if (fx == nullptr) PSI_FAIL("null operator output");
-    s->norm_blocks = (int)((s->numel + QN_THREADS * 4 - 1) / (QN_THREADS * 4));
-    k_qn_post<<<s->norm_blocks, QN_THREADS, 0, st>>>(s->numel, fx, s->x, s->g, s->dg, s->norm_part, &s->ctrl->done);
+    s->norm_blocks = (int)((s->act_numel + QN_THREADS * 4 - 1) / (QN_THREADS * 4));
+    k_qn_post<<<s->norm_blocks, QN_THREADS, 0, st>>>(s->act_numel, fx, s->x, s->g, s->dg, s->norm_part, &s->ctrl->done);
     PSI_CK_LAUNCH();
     s->launches += 1;
     s->f_evals += 1;

@@ -129,6 +129,13 @@ def graph_of(batch, kind: int) -> NativeGraph:
         g = NativeGraph(n, ei, batch.edge_attr, batch.a_ij, batch.tags, batch.prb_data, batch.unit_normal_vector)
     else:
         g = NativeGraph(n, ei, batch.edge_attr, batch.a_ij, batch.tags, batch.prb_data)
+    part = getattr(batch, "partition", None)
+    if part is not None and part.world > 1:
+        # one rank's share of a partitioned mesh (psi_gnn_b200/partition.py): bind the halo lists and the communicator
+        from . import partition as PT
+        if part.comm is None:
+            part.comm = PT.Communicator(ei.device)
+        PT.attach(g, part, part.comm)
     if slot is not None:
         slot[key] = (g, (ei.data_ptr(), tuple(ei.shape), ei.device))
     return g

@@ -419,7 +419,11 @@ class _ModelBase(nn.Module):
             raise RuntimeError("psi_gnn_b200: CUDA tensors required — there is no CPU path")
         h_initial = self._encode_native(batch.x)
         out = self.deqdss.inference(h_initial, batch)
-        return self._decode_native(out["result"])
+        u = self._decode_native(out["result"])
+        part = getattr(batch, "partition", None)
+        if part is not None and part.world > 1:
+            return u[:part.n_owned]          # one rank's share of a partitioned mesh: the owned rows (ghost rows are stale)
+        return u
 
     def iterative_inference(self, batch):
         """Decode every Broyden iterate (reference dirichlet model.py:109-155; it indexes the tuple returned by

@@ -80,7 +80,7 @@ class GraphData:
         out.__dict__.update({k: v for k, v in self.__dict__.items() if not k.startswith("_psi")})
         for k in self.keys():
             setattr(out, k, getattr(self, k).to(device, non_blocking=non_blocking))
-        return out
+        return out          # non-tensor attributes (num_nodes, partition, …) travel by reference
 
     def pin_memory(self) -> "GraphData":
         out = GraphData()

@@ -414,3 +414,19 @@ def test_dsgps_single_layer_matches_reference():
     W.upload(W.pack_dsgps(g.params(DEV), DEV), W.next_serial())
     out = graph_of(b, N.KIND_DSGPS).layer_forward(N.KIND_DSGPS, g.t("layer_in", DEV), g.t("layer_h0", DEV))
     assert rel_err(out, g.t("layer_out")) <= TOL
+
+
+@pytest.mark.timeout(600)
+def test_mesh_partitioned_solve_two_gpus():
+    """BASELINE config 5 at test size: one mesh split over 2 ranks (halo exchange + all-reduced inner products) must follow the
+    single-GPU solve.  Needs 2 GPUs; on a 1-GPU box the host logic is covered by tests/test_multi_gloo.py."""
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from conftest import ROOT
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", os.path.join(ROOT, "tests", "multi_gpu", "partitioned_solve.py"), "20000"]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=550)
+    assert p.returncode == 0 and "PARTITIONED_OK" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]

@@ -69,3 +69,47 @@ def test_graph_sharded_gradient_allreduce_gloo():
     for p in procs:
         p.join(timeout=30)
     assert sorted(res) == [(0, "ok"), (1, "ok")], res
+
+
+def test_mesh_partition_reproduces_global_layer():
+    """host logic of the mesh partition: on every rank's local graph (owned + ghost rows) the layer evaluated by the oracle
+    equals the global evaluation on the owned rows, and the exchange lists are mutually consistent."""
+    import numpy as np
+    from conftest import Golden
+    from oracle import psignn_oracle as O
+    from psi_gnn_b200 import partition, synthetic
+    g = Golden("dirichlet_ckpt")
+    P = g.params()
+    mesh = synthetic.make_mesh(5, h=0.06)
+    gen = torch.Generator().manual_seed(0)
+    h = torch.randn(mesh.num_nodes, 10, generator=gen)
+    h0 = torch.randn(mesh.num_nodes, 10, generator=gen)
+    with torch.no_grad():
+        ref = O.f_dirichlet(P, h, h0, mesh)
+        ref_res = O.residual_vector(mesh.sol, mesh)
+    world = 3
+    parts = partition.partition_mesh(mesh, world)
+    assert sorted(np.concatenate([p.owned_global for p in parts]).tolist()) == list(range(mesh.num_nodes))
+    for p in parts:
+        loc = p.local
+        nodes = torch.from_numpy(np.concatenate([p.owned_global, p.ghost_global]))
+        assert loc.num_nodes == p.n_owned + p.n_ghost == nodes.numel()
+        with torch.no_grad():
+            out = O.f_dirichlet(P, h[nodes], h0[nodes], loc)
+            res = O.residual_vector(mesh.sol[nodes], loc)
+        own = torch.from_numpy(p.owned_global)
+        assert float((out[:p.n_owned] - ref[own]).abs().max()) <= 1e-5
+        assert float((res[:p.n_owned] - ref_res[own]).abs().max()) <= 1e-4 * float(ref_res.abs().max())
+        # exchange lists: what I send to q is exactly q's ghost segment owned by me, in q's order
+        off = 0
+        for q, cnt in zip(p.peers, p.send_counts):
+            mine = p.owned_global[p.send_index[off:off + cnt]]
+            off += cnt
+            other = parts[q]
+            roff = 0
+            for qq, rc in zip(other.peers, other.recv_counts):
+                if qq == p.rank:
+                    assert rc == cnt and np.array_equal(other.ghost_global[roff:roff + rc], mine)
+                roff += rc
+    single = partition.partition_mesh(mesh, world, rank=1)[0]
+    assert np.array_equal(single.owned_global, parts[1].owned_global) and np.array_equal(single.send_index, parts[1].send_index)
