@@ -31,8 +31,11 @@ WORKLOADS = {
     # name: (family, graphs per GPU, mesh size h, description)
     "c1": ("dirichlet", 32, 0.075, "C1: PSI-GNN dirichlet training step, batch of 32 synthetic ~500-node 2D triangle Poisson meshes"),
     "c3": ("dirichlet", 256, 0.075, "C3: PSI-GNN dirichlet training step (Broyden forward + implicit-adjoint backward), batch 256 synthetic ~500-node meshes per GPU"),
+    "c5": ("dirichlet", 1, 0.075, "C5: PSI-GNN dirichlet forward Broyden solve (500-step cap) of ONE synthetic 1M-node mesh, node-range partitioned "
+                                   "over the GPUs (NCCL halo exchange + all-reduced inner products)"),
     "c4": ("mixed", 256, 0.037, "C4: PSI-GNN mixed Dirichlet/Neumann training step, batch 256 synthetic ~2k-node meshes per GPU"),
 }
+C5_NODES = 1_000_000
 LR = 1e-6            # end-of-training learning rate (both arms)
 CLIP = 0.1           # launch_local.sh --gradient_clip
 JAC_WEIGHT = 1.0     # launch_local.sh --jac_weight
@@ -111,6 +114,8 @@ def run_native(args):
         dist.init_process_group("nccl", device_id=dev)
     _native.load()                                              # fail loudly if the extension is missing
     family, n_graphs, h, desc = WORKLOADS[args.workload]
+    if args.workload == "c5":
+        return run_native_c5(args, rank, local, world, dev)
     if args.graphs:
         n_graphs = args.graphs
     P, cfg = load_params(family)
@@ -249,6 +254,125 @@ def run_native(args):
         dist.destroy_process_group()
 
 
+def _timed_steps(fn, k, world, dev, flush):
+    import torch.distributed as dist
+    evs = []
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    for _ in range(k):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        evs.append((a, b))
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t = torch.tensor([sum(a.elapsed_time(b) for a, b in evs)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def run_native_c5(args, rank, local, world, dev):
+    """one large mesh: unpartitioned on 1 GPU, node-range partitioned on N GPUs (strong scaling)"""
+    import torch.distributed as dist
+    from psi_gnn_b200 import model as PM, partition, synthetic
+    from psi_gnn_b200.dirichlet.psignn import model as M
+    from psi_gnn_b200.dirichlet.psignn.utilities import solver as S
+    family, _, h, desc = WORKLOADS["c5"]
+    nodes = args.nodes or C5_NODES
+    P, cfg = load_params(family)
+    cfg["solver"] = S.broyden
+    model = M.ModelDEQDSS(cfg)
+    model.load_state_dict(P)
+    model = model.to(dev).eval()
+    mesh = synthetic.make_large_mesh(nodes, seed=0, h=h)
+    if world > 1:
+        part = partition.partition_mesh(mesh, world, rank=rank)[0]
+        host = part.local.pin_memory()
+        n_owned, n_ghost = part.n_owned, part.n_ghost
+    else:
+        host = mesh.pin_memory()
+        n_owned, n_ghost = mesh.num_nodes, 0
+    dev_batch = host.to(dev)
+    flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)
+    stats = {"steps": 0, "evals": 0, "launches": 0}
+
+    def solve(batch, read):
+        with torch.no_grad():
+            u = model.inference(batch)
+        out = model.deqdss.last_forward
+        stats["steps"] += out["steps_run"]; stats["evals"] += out["f_evals"]; stats["launches"] += out["launches"] + 2
+        return u.cpu() if read else None
+
+    def e2e():
+        b = host.to(dev, non_blocking=True)
+        if world > 1:
+            b.partition.comm = dev_batch.partition.comm        # the communicator is built once per process
+        return solve(b, True)
+
+    warm = max(args.warmup, 1)
+    for _ in range(warm):
+        solve(dev_batch, False)
+    g = PM.graph_of(dev_batch, 0)
+    ws = g.solver(cfg["fw_thres"])
+    ws.profile(True)
+    for k in stats:
+        stats[k] = 0
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_total = _timed_steps(lambda: solve(dev_batch, False), args.steps, world, dev, flush)
+    clocks = sampler.stop() if rank == 0 else None
+    prof = ws.profile_read()
+    ws.profile(False)
+    run_stats = dict(stats)
+    e2e()
+    ms_e2e = _timed_steps(e2e, args.steps, world, dev, flush)
+    sec = ms_total / 1e3
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    dom = max(prof, key=lambda k: prof[k]["ms"])
+    d = prof[dom]
+    achieved = d["bytes"] / max(d["ms"], 1e-9) / 1e6
+    kernels = {k: {"launches": v["launches"], "ms_total": round(v["ms"], 3), "avg_us": round(1e3 * v["ms"] / max(v["launches"], 1), 2),
+                   "alg_GBps": round(v["bytes"] / max(v["ms"], 1e-9) / 1e6, 1), "frac_of_peak": round(v["bytes"] / max(v["ms"], 1e-9) / 1e6 / peak, 4)}
+               for k, v in prof.items()}
+    E_glob = int((mesh.edge_index[0] != mesh.edge_index[1]).sum())
+    out = {
+        "metric": "PSI-GNN solve graphs/s (forward Broyden solve of one large mesh)",
+        "value": round(args.steps / sec, 4), "unit": "graphs/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
+        "ms_per_step": round(ms_total / args.steps, 3), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic P1-FEM Poisson mesh (seeded generator); weights = reference shipped checkpoint",
+        "config": {"workload": desc, "nodes": mesh.num_nodes, "nnz": int(mesh.edge_index.shape[1]), "offdiag_edges": E_glob,
+                   "owned_nodes_rank0": n_owned, "ghost_nodes_rank0": n_ghost, "solver": "broyden", "fw_tol": cfg["fw_tol"], "fw_thres": cfg["fw_thres"],
+                   "parallelism": "node-range mesh partition x%d" % world if world > 1 else "single GPU",
+                   "l2": "256 MB buffer written between timed steps; working set (history) exceeds L2"},
+        "iterations_per_s": round(run_stats["steps"] / sec, 1),
+        "edge_msg_updates_per_s": round(run_stats["evals"] * 2 * E_glob / sec, 1),
+        "solver_steps_per_step": {"forward": run_stats["steps"] / args.steps},
+        "gpu_launches": run_stats["launches"],
+        "e2e": {"value": round(args.steps / (ms_e2e / 1e3), 4), "unit": "graphs/s", "ms_per_step": round(ms_e2e / args.steps, 3),
+                "h2d_bytes_per_step": host.nbytes(), "d2h_bytes_per_step": 4 * n_owned},
+        "roofline": {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                     "traffic": None, "peak_source": peak_src, "avg_launch_us": round(1e3 * d["ms"] / max(d["launches"], 1), 2),
+                     "alg_bytes_per_launch": round(d["bytes"] / max(d["launches"], 1), 1)},
+        "kernels": kernels, "clocks": clocks,
+    }
+    if rank == 0:
+        emit(out)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 # =====================================================================================================================
 # CPU arm: the oracle port of the reference's training step (the reference itself is Python that needs PyG/torch_sparse and
 # /root/reference, neither of which exists on the GPU box)
@@ -357,6 +481,7 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--graphs", type=int, default=0, help="override graphs per GPU")
+    ap.add_argument("--nodes", type=int, default=0, help="override the mesh size of workload c5")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -816,7 +816,9 @@ extern "C" int psi_broyden_forced_step(psi_solver_t* s, int n, const float* dev_
     if (s->numel == 0) return 0;
     cudaStream_t st = as_stream(stream);
     if (hist_ensure(s, n - 1)) return -1;
-    s->threshold = s->cap + 1; s->eps = 0.0; s->xtrace = nullptr; s->launches = 0; s->f_evals = 0;
+    s->threshold = s->cap + 1; s->eps = 0.0; s->xtrace = nullptr; s->launches = 0; s->f_evals = 0; s->comm = nullptr;
+    s->act_numel = s->numel; s->act_chunks = (int)((s->numel + QN_CHUNK - 1) / QN_CHUNK); s->act_dchunks = (int)((s->numel + DOTS_CH - 1) / DOTS_CH);
+    s->last_act = -1;   // the next solve re-establishes the zero padding
     k_qn_ctrl_init<<<1, 1, 0, st>>>(s->ctrl);
     for (int k = 0; k < n - 1; ++k) {
         float* du = s->hist.U[k / s->hist.slab_vecs] + (int64_t)(k % s->hist.slab_vecs) * s->stride;

@@ -427,6 +427,6 @@ def test_mesh_partitioned_solve_two_gpus():
         pytest.skip("needs 2 GPUs")
     from conftest import ROOT
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", "29533", os.path.join(ROOT, "tests", "multi_gpu", "partitioned_solve.py"), "20000"]
+           "--master-port", "29533", os.path.join(ROOT, "tests", "multi_gpu", "partitioned_solve.py"), "3000"]
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=550)
     assert p.returncode == 0 and "PARTITIONED_OK" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]
