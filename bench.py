@@ -359,6 +359,7 @@ def run_native_c5(args, rank, local, world, dev):
         "iterations_per_s": round(run_stats["steps"] / sec, 1),
         "edge_msg_updates_per_s": round(run_stats["evals"] * 2 * E_glob / sec, 1),
         "solver_steps_per_step": {"forward": run_stats["steps"] / args.steps},
+        "last_solve": {k: model.deqdss.last_forward[k] for k in ("lowest", "nstep", "steps_run", "stop_reason", "prot_break")},
         "gpu_launches": run_stats["launches"],
         "e2e": {"value": round(args.steps / (ms_e2e / 1e3), 4), "unit": "graphs/s", "ms_per_step": round(ms_e2e / args.steps, 3),
                 "h2d_bytes_per_step": host.nbytes(), "d2h_bytes_per_step": 4 * n_owned},
