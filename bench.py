@@ -54,6 +54,16 @@ def make_batch(family, n_graphs, h, seed0):
     return synthetic.make_batch(n_graphs, seed0=seed0, h=h, mixed=(family == "mixed"), solve=False)
 
 
+def ncu_traffic(kernel, alg_bytes_per_launch):
+    """dram__bytes_read+write per launch for the dominant kernel: the ncu capture (profiles/ncu_traffic.json) gives the ratio of DRAM
+    traffic to algorithmic bytes at one history depth; both scale with the depth, so the ratio carries over to the average launch."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        return round(alg_bytes_per_launch * float(t[kernel]["ratio"]), 1)
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -222,6 +232,7 @@ def run_native(args):
     dom = max(prof, key=lambda k: prof[k]["ms"])
     d = prof[dom]
     achieved = d["bytes"] / max(d["ms"], 1e-9) / 1e6            # GB/s
+    traffic = ncu_traffic(dom, d["bytes"] / max(d["launches"], 1))
     kernels = {k: {"launches": v["launches"], "ms_total": round(v["ms"], 3), "avg_us": round(1e3 * v["ms"] / max(v["launches"], 1), 2),
                    "alg_GBps": round(v["bytes"] / max(v["ms"], 1e-9) / 1e6, 1), "frac_of_peak": round(v["bytes"] / max(v["ms"], 1e-9) / 1e6 / peak, 4)}
                for k, v in prof.items()}
@@ -241,7 +252,7 @@ def run_native(args):
         "e2e": {"value": round(world * n_graphs * args.steps / (ms_e2e / 1e3), 2), "unit": "graphs/s", "ms_per_step": round(ms_e2e / args.steps, 3),
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                     "traffic": None, "peak_source": peak_src, "avg_launch_us": round(1e3 * d["ms"] / max(d["launches"], 1), 2),
+                     "traffic": traffic, "traffic_source": "algorithmic bytes per launch x the DRAM-traffic/algorithmic ratio of the ncu --set full capture in profiles/ncu_traffic.json" if traffic else None, "peak_source": peak_src, "avg_launch_us": round(1e3 * d["ms"] / max(d["launches"], 1), 2),
                      "alg_bytes_per_launch": round(d["bytes"] / max(d["launches"], 1), 1)},
         "kernels": kernels,
         "clocks": clocks,
@@ -343,6 +354,7 @@ def run_native_c5(args, rank, local, world, dev):
     dom = max(prof, key=lambda k: prof[k]["ms"])
     d = prof[dom]
     achieved = d["bytes"] / max(d["ms"], 1e-9) / 1e6
+    traffic = ncu_traffic(dom, d["bytes"] / max(d["launches"], 1))
     kernels = {k: {"launches": v["launches"], "ms_total": round(v["ms"], 3), "avg_us": round(1e3 * v["ms"] / max(v["launches"], 1), 2),
                    "alg_GBps": round(v["bytes"] / max(v["ms"], 1e-9) / 1e6, 1), "frac_of_peak": round(v["bytes"] / max(v["ms"], 1e-9) / 1e6 / peak, 4)}
                for k, v in prof.items()}
@@ -364,7 +376,7 @@ def run_native_c5(args, rank, local, world, dev):
         "e2e": {"value": round(args.steps / (ms_e2e / 1e3), 4), "unit": "graphs/s", "ms_per_step": round(ms_e2e / args.steps, 3),
                 "h2d_bytes_per_step": host.nbytes(), "d2h_bytes_per_step": 4 * n_owned},
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                     "traffic": None, "peak_source": peak_src, "avg_launch_us": round(1e3 * d["ms"] / max(d["launches"], 1), 2),
+                     "traffic": traffic, "traffic_source": "algorithmic bytes per launch x the DRAM-traffic/algorithmic ratio of the ncu --set full capture in profiles/ncu_traffic.json" if traffic else None, "peak_source": peak_src, "avg_launch_us": round(1e3 * d["ms"] / max(d["launches"], 1), 2),
                      "alg_bytes_per_launch": round(d["bytes"] / max(d["launches"], 1), 1)},
         "kernels": kernels, "clocks": clocks,
     }

@@ -23,7 +23,7 @@ struct SellDev {
     const int4*    recs;        // {j, attr0, attr1, attr2} (attrs as float bits) — message lists
     const int2*    recs2;       // {j, a_ij bits}                                 — matrix lists
     const int64_t* slice_off;   // [num_slices+1], in records
-    uint32_t*      xmask;       // per-slot cross ReLU mask for the VJP (message lists only)
+    uint32_t*      xmask;       // per-slot {neighbour, cross ReLU mask} pairs (int2) for the VJP (message lists only)
 };
 
 struct GraphDev {

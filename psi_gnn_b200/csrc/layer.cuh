@@ -60,16 +60,25 @@ __device__ __forceinline__ void edge_aggregate(const SellDev& L, const float* __
     const int width = (int)((L.slice_off[(node >> 5) + 1] - base) >> 5);
     const int4* p = L.recs + base + (node & 31);
     int deg = 0;
-    for (int t = 0; t < width; ++t) {
-        const int4 rec = __ldg(p + (int64_t)t * 32);
-        if (rec.x >= 0) {
-            float hj[PSI_D], z[PSI_D];
-            load_row(h, rec.x, hj);
-            edge_z<WHICH, ATTR>(P, hj, rec, z);
+    // two edges per trip: both records, then both neighbour rows, are requested before the FMAs of either edge start, which
+    // halves the number of dependent memory round trips of the per-destination loop (the kernel is latency-, not FMA-bound)
+    for (int t0 = 0; t0 < width; t0 += 2) {
+        int4 rec[2];
+        rec[0] = __ldg(p + (int64_t)t0 * 32);
+        rec[1] = (t0 + 1 < width) ? __ldg(p + (int64_t)(t0 + 1) * 32) : make_int4(-1, 0, 0, 0);
+        float hj[2][PSI_D];
 #pragma unroll
-            for (int o = 0; o < PSI_D; ++o) S[o] += fmaxf(z[o], 0.f);
-            ++deg;
-        }
+        for (int q = 0; q < 2; ++q)
+            if (rec[q].x >= 0) load_row(h, rec[q].x, hj[q]);
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+            if (rec[q].x >= 0) {
+                float z[PSI_D];
+                edge_z<WHICH, ATTR>(P, hj[q], rec[q], z);
+#pragma unroll
+                for (int o = 0; o < PSI_D; ++o) S[o] += fmaxf(z[o], 0.f);
+                ++deg;
+            }
     }
     const float fdeg = (float)deg;
 #pragma unroll

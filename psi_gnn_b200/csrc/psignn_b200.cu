@@ -250,8 +250,8 @@ static int vjp_alloc(psi_graph* g, cudaStream_t st) {
     const int64_t N = g->N > 0 ? g->N : 1;
     const int64_t floats = N * (10 + 1 + 1 + 10 + 30 + 1 + 20 + 10);
     PSI_CK(psi_malloc_async(&g->p_vjp, floats * sizeof(float), st));
-    PSI_CK(psi_malloc_async(&g->p_xm_T, (g->slots_T > 0 ? g->slots_T : 1) * sizeof(uint32_t), st));
-    PSI_CK(psi_malloc_async(&g->p_xm_F, (g->slots_F > 0 ? g->slots_F : 1) * sizeof(uint32_t), st));
+    PSI_CK(psi_malloc_async(&g->p_xm_T, (g->slots_T > 0 ? g->slots_T : 1) * sizeof(int2), st));
+    PSI_CK(psi_malloc_async(&g->p_xm_F, (g->slots_F > 0 ? g->slots_F : 1) * sizeof(int2), st));
     float* p = (float*)g->p_vjp;
     VjpCacheDev& C = g->vjp;
     C.rhat = p; p += N * 10;
@@ -264,7 +264,7 @@ static int vjp_alloc(psi_graph* g, cudaStream_t st) {
     C.nmask = (uint32_t*)p; p += N;
     g->dev.T.xmask = (uint32_t*)g->p_xm_T;
     g->dev.F.xmask = (uint32_t*)g->p_xm_F;
-    g->bytes += floats * 4 + (g->slots_T + g->slots_F) * 4;
+    g->bytes += floats * 4 + (g->slots_T + g->slots_F) * 8;
     return 0;
 }
 
@@ -276,8 +276,8 @@ extern "C" int psi_vjp_prepare(psi_graph_t* g, int kind, const float* dev_hstar,
     cudaStream_t st = as_stream(stream);
     if (vjp_alloc(g, st)) return -1;
     if (g->N > 0) {
-        PSI_CK(cudaMemsetAsync(g->p_xm_T, 0, (g->slots_T > 0 ? g->slots_T : 1) * sizeof(uint32_t), st));
-        PSI_CK(cudaMemsetAsync(g->p_xm_F, 0, (g->slots_F > 0 ? g->slots_F : 1) * sizeof(uint32_t), st));
+        PSI_CK(cudaMemsetAsync(g->p_xm_T, 0, (g->slots_T > 0 ? g->slots_T : 1) * sizeof(int2), st));
+        PSI_CK(cudaMemsetAsync(g->p_xm_F, 0, (g->slots_F > 0 ? g->slots_F : 1) * sizeof(int2), st));
         if (kind == PSI_KIND_DIRICHLET) k_vjp_prepare<KIND_DIRICHLET><<<node_grid(g->N), PSI_NODE_BLOCK, 0, st>>>(g->dev, g->vjp, dev_hstar);
         else k_vjp_prepare<KIND_MIXED><<<node_grid(g->N), PSI_NODE_BLOCK, 0, st>>>(g->dev, g->vjp, dev_hstar);
         PSI_CK_LAUNCH();
@@ -601,7 +601,7 @@ static int qn_update(psi_solver* s, int n, int norm_blocks, cudaStream_t st) {
         PSI_CK_LAUNCH();
         s->launches += 1;
     }
-    const int fin_blocks = std::max(1, std::min(64, (nhist * 3 + 7) / 8));
+    const int fin_blocks = std::max(1, std::min(2 * s->tma_ctas, (nhist * 3 + 7) / 8));   // one warp per row of the partial matrix
     if (s->comm == nullptr) {
         k_qn_fin1<<<fin_blocks, 256, 0, st>>>(nhist, s->partial, s->act_dchunks, s->coef, s->cap, s->norm_part, norm_blocks, s->ctrl,
                                               s->rel_trace, s->abs_trace, n, s->eps, 1e3 * PSI_D, s->threshold);

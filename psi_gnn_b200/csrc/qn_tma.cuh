@@ -182,7 +182,8 @@ k_qn_axpy_tma(QnHistory H, int nhist, int n, const float* __restrict__ coef, int
             for (int t = 0; t < ntiles; ++t) {
                 const int64_t t0 = q0 + (int64_t)t * tile4;
                 const uint32_t bytes = (uint32_t)(min((int64_t)tile4, q1 - t0) * 16);
-                for (int k = 0; k < nhist; ++k, ++fill) {
+                for (int k = nhist - 1; k >= 0; --k, ++fill) {   // descending: pass 1 just streamed the newest vectors last, the
+                                                                 // tail of the history is what the 126 MB L2 still holds
                     const uint32_t s = fill % AXPY_STAGES, use = fill / AXPY_STAGES;
                     if (use > 0) mbar_wait(&empty[s], (use - 1) & 1);
                     mbar_expect_tx(&full[s], 2 * bytes);
@@ -205,7 +206,7 @@ k_qn_axpy_tma(QnHistory H, int nhist, int n, const float* __restrict__ coef, int
         float4 av[2], aw[2], at[2];
 #pragma unroll
         for (int j = 0; j < 2; ++j) { av[j] = make_float4(0.f, 0.f, 0.f, 0.f); aw[j] = av[j]; at[j] = av[j]; }
-        for (int k = 0; k < nhist; ++k, ++fill) {
+        for (int k = nhist - 1; k >= 0; --k, ++fill) {
             const uint32_t s = fill % AXPY_STAGES, use = fill / AXPY_STAGES;
             mbar_wait(&full[s], use & 1);
             const float4* su = reinterpret_cast<const float4*>(ring + (size_t)s * 2 * AXPY_TILE);

@@ -79,7 +79,7 @@ __device__ __forceinline__ void prepare_list(const GraphDev& G, const SellDev& L
                     xm = relu_bits(z);
                 }
             }
-            L.xmask[slot] = xm;
+            reinterpret_cast<int2*>(L.xmask)[slot] = make_int2(rec.x, (int)xm);
         }
     }
     const float fdeg = (float)deg;
@@ -286,47 +286,55 @@ k_vjp_phase_b(GraphDev G, VjpCacheDev C, const float* __restrict__ y, const floa
         float accT[PSI_D], accF[PSI_D], accN[PSI_D];
 #pragma unroll
         for (int o = 0; o < PSI_D; ++o) { accT[o] = 0.f; accF[o] = 0.f; accN[o] = 0.f; }
+        // Both loops gather S̄ of the destination over the *other* list.  {neighbour, cross mask} pairs are read four slots at a
+        // time and the four S̄ rows are requested together: two dependent round trips per four edges instead of eight.
         {   // row list of this node: edges (node, c) — node is the source of Phi_to messages into c
             const SellDev& L = G.F;
             const int64_t base = L.slice_off[node >> 5];
             const int width = (int)((L.slice_off[(node >> 5) + 1] - base) >> 5);
-            const int64_t col0 = base + (node & 31);
-            for (int t = 0; t < width; ++t) {
-                const int64_t slot = col0 + (int64_t)t * 32;
-                const int j = __ldg(&L.recs[slot].x);
-                if (j >= 0) {
-                    const uint32_t xm = L.xmask[slot];
-                    if (xm) {
-                        float sb[PSI_D];
-                        load_row_rw(C.Sb, (int64_t)j * 2 + 0, sb);
+            const int2* xp = reinterpret_cast<const int2*>(L.xmask) + base + (node & 31);
+            for (int t0 = 0; t0 < width; t0 += 4) {
+                int2 jm[4];
 #pragma unroll
-                        for (int o = 0; o < PSI_D; ++o) accT[o] += ((xm >> o) & 1u) ? sb[o] : 0.f;
+                for (int q = 0; q < 4; ++q) jm[q] = (t0 + q < width) ? xp[(int64_t)(t0 + q) * 32] : make_int2(-1, 0);
+                float sb[4][PSI_D];
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (jm[q].y) load_row_rw(C.Sb, (int64_t)jm[q].x * 2 + 0, sb[q]);
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (jm[q].y) {
+                        const uint32_t xm = (uint32_t)jm[q].y;
+#pragma unroll
+                        for (int o = 0; o < PSI_D; ++o) accT[o] += ((xm >> o) & 1u) ? sb[q][o] : 0.f;
                     }
-                }
             }
         }
         {   // column list: edges (r, node) — node is the source of Phi_from / phi_neumann messages into r
             const SellDev& L = G.T;
             const int64_t base = L.slice_off[node >> 5];
             const int width = (int)((L.slice_off[(node >> 5) + 1] - base) >> 5);
-            const int64_t col0 = base + (node & 31);
-            for (int t = 0; t < width; ++t) {
-                const int64_t slot = col0 + (int64_t)t * 32;
-                const int j = __ldg(&L.recs[slot].x);
-                if (j >= 0) {
-                    const uint32_t xm = L.xmask[slot];
-                    if (xm) {
-                        float sb[PSI_D];
-                        load_row_rw(C.Sb, (int64_t)j * 2 + 1, sb);
+            const int2* xp = reinterpret_cast<const int2*>(L.xmask) + base + (node & 31);
+            for (int t0 = 0; t0 < width; t0 += 4) {
+                int2 jm[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) jm[q] = (t0 + q < width) ? xp[(int64_t)(t0 + q) * 32] : make_int2(-1, 0);
+                float sb[4][PSI_D];
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (jm[q].y) load_row_rw(C.Sb, (int64_t)jm[q].x * 2 + 1, sb[q]);
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (jm[q].y) {
+                        const uint32_t xm = (uint32_t)jm[q].y;
                         if (KIND == KIND_MIXED && (xm & (1u << 10))) {
 #pragma unroll
-                            for (int o = 0; o < PSI_D; ++o) accN[o] += ((xm >> o) & 1u) ? sb[o] : 0.f;
+                            for (int o = 0; o < PSI_D; ++o) accN[o] += ((xm >> o) & 1u) ? sb[q][o] : 0.f;
                         } else {
 #pragma unroll
-                            for (int o = 0; o < PSI_D; ++o) accF[o] += ((xm >> o) & 1u) ? sb[o] : 0.f;
+                            for (int o = 0; o < PSI_D; ++o) accF[o] += ((xm >> o) & 1u) ? sb[q][o] : 0.f;
                         }
                     }
-                }
             }
         }
         load_row_rw(C.Dloc, node, res);

@@ -55,9 +55,16 @@ def full(path, out):
         for k in KEYS:
             if k in hdr:
                 out.write("| %s | %s %s |\n" % (k, r[hdr.index(k)], units[hdr.index(k)]))
-        rd = float(r[hdr.index("dram__bytes_read.sum")]) if "dram__bytes_read.sum" in hdr else 0
-        wr = float(r[hdr.index("dram__bytes_write.sum")]) if "dram__bytes_write.sum" in hdr else 0
-        out.write("| **traffic (read+write)** | %.4g %s |\n\n" % (rd + wr, units[hdr.index("dram__bytes_read.sum")]))
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+
+        def in_bytes(key):
+            if key not in hdr:
+                return 0.0
+            return float(r[hdr.index(key)]) * scale.get(units[hdr.index(key)], 1.0)
+
+        tr = in_bytes("dram__bytes_read.sum") + in_bytes("dram__bytes_write.sum")
+        dur = float(r[hdr.index("gpu__time_duration.sum")]) * {"ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1.0}.get(units[hdr.index("gpu__time_duration.sum")], 1e-9)
+        out.write("| **traffic (read+write)** | %.4f GB (= %.0f GB/s over the kernel's duration) |\n\n" % (tr / 1e9, tr / 1e9 / max(dur, 1e-12)))
 
 
 def main():

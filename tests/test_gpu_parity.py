@@ -430,3 +430,45 @@ def test_mesh_partitioned_solve_two_gpus():
            "--master-port", "29533", os.path.join(ROOT, "tests", "multi_gpu", "partitioned_solve.py"), "3000"]
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=550)
     assert p.returncode == 0 and "PARTITIONED_OK" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]
+
+
+# ---- adjacent API surface --------------------------------------------------------------------------------
+def test_eval_mode_spectral_radius(tmp_path):
+    """DeepEquilibrium.forward under no_grad (validation branch, model.py:228-241): Jacobian estimate + 150 power iterations on the
+    native VJP; the trained checkpoint is a contraction with spectral radius just below 1 (reference logs: ≈ 0.990)."""
+    g = Golden("dirichlet_ckpt")
+    m = g.model(DEV).eval()
+    m.deqdss.path_logs = str(tmp_path)
+    b = g.batch(DEV)
+    with torch.no_grad():
+        h0 = m._encode_native(b.x)
+        new_h, jac = m.deqdss(h0, b)
+    assert new_h.shape == h0.shape and float(jac) > 0
+    rho = float(open(tmp_path / "spectral_radius.csv").read().strip().split()[-1])
+    assert 0.9 < rho < 1.01, rho
+
+
+def test_iterative_inference_trace():
+    g = Golden("dirichlet_seed0")
+    m = g.model(DEV)
+    b = g.batch(DEV)
+    out = m.iterative_inference(b)
+    steps = m.deqdss.last_forward["steps_run"]
+    assert len(out["sol_dic"]) == steps + 2 == len(out["res_dic"])          # batch.x, x0, then every iterate
+    assert out["nstep"] == m.deqdss.last_forward["nstep"]
+    assert out["res_dic"][-1] < out["res_dic"][1]                            # the residual went down along the trace
+    u = m.inference(b)
+    assert rel_err(out["sol_dic"][1 + out["nstep"]].to(DEV), u) < 1e-5       # the best iterate is the one inference returns
+
+
+def test_forward_iteration_generic_callable():
+    from psi_gnn_b200 import solver as S
+    g = Golden("dirichlet_seed0")
+    m = g.model(DEV)
+    b = g.batch(DEV)
+    h0 = g.t("h0", DEV)
+    op = S.LayerOperator(m.deqdss.f, h0, b)
+    a = S.forward_iteration(op, h0, eps=1e-4, threshold=40)
+    c = S.forward_iteration(lambda H: op(H), h0, eps=1e-4, threshold=40)
+    assert a["nstep"] == c["nstep"]
+    assert rel_err(a["result"], c["result"]) < 1e-6
