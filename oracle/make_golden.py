@@ -171,6 +171,9 @@ def make_fixture(family: str, weights: str, n_graphs: int, seed0: int, h: float,
             def recording_solver(fn, x0, threshold, eps):
                 out_ = orig(fn, x0, threshold=threshold, eps=eps)
                 rec.setdefault("calls", []).append(out_)
+                if len(rec["calls"]) == 2:
+                    # the backward solve is y = J^T y + grad from y0 = 0 (model.py:214-218): fn(0) = grad
+                    rec["bw_grad"] = fn(torch.zeros_like(x0)).detach().clone()
                 return out_
 
             model.config_deq["solver"] = recording_solver
@@ -193,6 +196,8 @@ def make_fixture(family: str, weights: str, n_graphs: int, seed0: int, h: float,
             for k, p in model.named_parameters():
                 fx["train_grad." + k] = (p.grad if p.grad is not None else torch.zeros_like(p)).numpy()
             bw = rec["calls"][1]
+            fx["train_bw_grad"] = rec["bw_grad"].numpy()
+            fx["train_hstar"] = rec["calls"][0]["result"].detach().numpy()
             fx.update(train_fw_nstep=np.int64(rec["calls"][0]["nstep"]), train_bw_nstep=np.int64(bw["nstep"]),
                       train_bw_lowest=np.float64(bw["lowest"]), train_bw_result=bw["result"].numpy(),
                       train_bw_rel_trace=np.asarray(bw["rel_trace"], np.float64),
