@@ -268,8 +268,7 @@ def anderson(f: Callable, x0: torch.Tensor, m: int = 2, lam: float = 1e-4, thres
         raise NotImplementedError("psi_gnn_b200.solver.anderson: only stop_mode='rel'")
     _require_cuda(x0)
     if not (isinstance(f, NativeOperator) and f.op == N.OP_LAYER):
-        raise NotImplementedError("psi_gnn_b200.solver.anderson: runs on the fused layer operator only "
-                                  "(pass the LayerOperator DeepEquilibrium builds)")
+        return _anderson_generic(f, x0, m, lam, threshold, eps, beta)
     lib = N.load()
     x0c = N.f32(x0.detach())
     threshold = int(threshold)
@@ -285,6 +284,53 @@ def anderson(f: Callable, x0: torch.Tensor, m: int = 2, lam: float = 1e-4, thres
                 "psi_solver_anderson")
     n = max(threshold - 2, 0)
     return _result_dict(result, stats, list(rel)[:n], list(abs_)[:n], [], eps, threshold)
+
+
+def _anderson_generic(f, x0, m, lam, threshold, eps, beta):
+    """Anderson acceleration for an arbitrary CUDA callable (one Python call of ``f`` per step).  The window algebra is the
+    reference's (solver.py:215-293): a handful of [m, N·d] reductions per step; only the fused layer operator has a native loop."""
+    x0 = x0.detach()
+    shape, nd = x0.shape, x0.numel()
+    X = torch.zeros(1, m, nd, dtype=x0.dtype, device=x0.device)
+    Fm = torch.zeros(1, m, nd, dtype=x0.dtype, device=x0.device)
+    X[:, 0] = x0.reshape(1, -1)
+    Fm[:, 0] = f(x0).reshape(1, -1)
+    X[:, 1] = Fm[:, 0]
+    Fm[:, 1] = f(Fm[:, 0].reshape(shape)).reshape(1, -1)
+    H = torch.zeros(1, m + 1, m + 1, dtype=x0.dtype, device=x0.device)
+    H[:, 0, 1:] = H[:, 1:, 0] = 1
+    y = torch.zeros(1, m + 1, 1, dtype=x0.dtype, device=x0.device)
+    y[:, 0] = 1
+    rel_tr, abs_tr = [], []
+    best = {"rel": 1e8, "abs": 1e8}
+    best_step = {"rel": 0, "abs": 0}
+    best_x = x0
+    trace = [x0]
+    for k in range(2, threshold):
+        n = min(k, m)
+        G = Fm[:, :n] - X[:, :n]
+        H[:, 1:n + 1, 1:n + 1] = torch.bmm(G, G.transpose(1, 2)) + lam * torch.eye(n, dtype=x0.dtype, device=x0.device)[None]
+        alpha = torch.linalg.solve(H[:, :n + 1, :n + 1], y[:, :n + 1])[:, 1:n + 1, 0]
+        X[:, k % m] = beta * (alpha[:, None] @ Fm[:, :n])[:, 0] + (1 - beta) * (alpha[:, None] @ X[:, :n])[:, 0]
+        Fm[:, k % m] = f(X[:, k % m].reshape(shape)).reshape(1, -1)
+        gx = Fm[:, k % m] - X[:, k % m]
+        a = gx.norm().item()
+        r = a / (1e-5 + Fm[:, k % m].norm().item())
+        abs_tr.append(a)
+        rel_tr.append(r)
+        if r < best["rel"]:
+            best_x = X[:, k % m].reshape(shape).clone()
+            best["rel"], best_step["rel"] = r, k
+        if a < best["abs"]:
+            best["abs"], best_step["abs"] = a, k
+        trace.append(best_x)
+        if rel_tr[-1] < eps:
+            pad = threshold - 1 - k
+            rel_tr += [best["rel"]] * pad
+            abs_tr += [best["abs"]] * pad
+            break
+    return {"result": best_x, "lowest": best["rel"], "nstep": best_step["rel"], "prot_break": False, "abs_trace": abs_tr,
+            "rel_trace": rel_tr, "xest_trace": trace, "eps": eps, "threshold": threshold}
 
 
 def newton(f, z0, eps, threshold):

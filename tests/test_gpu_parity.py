@@ -494,3 +494,125 @@ def test_forward_iteration_generic_callable():
     c = S.forward_iteration(lambda H: op(H), h0, eps=1e-4, threshold=40)
     assert a["nstep"] == c["nstep"]
     assert rel_err(a["result"], c["result"]) < 1e-6
+
+
+# ---- randomised ragged graphs against the fp64 oracle (both families, layer and VJP) ----------------------------------------------
+def _random_graph(seed, n, mixed, device):
+    """directed multigraph with isolated nodes, hubs, self loops, asymmetric edges, all three boundary classes"""
+    from psi_gnn_b200.synthetic import GraphData
+    gen = torch.Generator().manual_seed(seed)
+    m = int(n * 5)
+    row = torch.randint(0, n, (m,), generator=gen)
+    col = torch.randint(0, n, (m,), generator=gen)
+    hub = torch.randint(0, n, (1,), generator=gen).item()
+    row[: n // 3] = hub                                       # a hub with degree ~n/3
+    diag = torch.arange(n)
+    ei = torch.stack([torch.cat([row, diag]), torch.cat([col, diag])])
+    nnz = ei.shape[1]
+    cls = torch.randint(0, 3 if mixed else 2, (n,), generator=gen)
+    cls[torch.randint(0, n, (n // 10,), generator=gen)] = 0
+    if mixed:
+        tags = torch.nn.functional.one_hot(cls, 3).float()
+    else:
+        tags = (cls == 1).float().reshape(-1, 1)
+    b = GraphData(x=torch.randn(n, 1, generator=gen), edge_index=ei, edge_attr=torch.randn(nnz, 3, generator=gen),
+                  a_ij=torch.randn(nnz, 1, generator=gen), y=torch.randn(n, 1, generator=gen), sol=torch.zeros(n, 1),
+                  prb_data=torch.randn(n, 3 if mixed else 2, generator=gen), tags=tags)
+    if mixed:
+        b.unit_normal_vector = torch.randn(n, 2, generator=gen)
+    b.num_nodes = n
+    h = torch.randn(n, 10, generator=gen)
+    h0 = torch.randn(n, 10, generator=gen)
+    y = torch.randn(n, 10, generator=gen)
+    return b, h, h0, y
+
+
+@pytest.mark.parametrize("mixed", [False, True])
+@pytest.mark.parametrize("seed,n", [(0, 33), (1, 97), (2, 257), (3, 1000)])
+def test_random_ragged_graphs_layer_and_vjp(mixed, seed, n):
+    from oracle import psignn_oracle as O
+    from psi_gnn_b200.solver import VjpOperator
+    g = Golden("mixed_ckpt" if mixed else "dirichlet_ckpt")
+    m = g.model(DEV)
+    b, h, h0, y = _random_graph(seed, n, mixed, "cpu")
+    P64 = {k: v.double() for k, v in g.params().items()}
+    f = O.f_mixed if mixed else O.f_dirichlet
+    H = h.double().requires_grad_()
+    ref = f(P64, H, h0.double(), b.double())
+    ref_vjp = torch.autograd.grad(ref, H, y.double())[0]
+    bd = b.to(DEV)
+    with torch.no_grad():
+        out = m.deqdss.f(h.to(DEV), h0.to(DEV), bd)
+    assert rel_err(out, ref.detach()) <= TOL
+    op = VjpOperator(m.deqdss.f, h.to(DEV), bd, torch.zeros(n, 10, device=DEV))
+    assert rel_err(op(y.to(DEV)), ref_vjp) <= TOL
+    # residual SpMV on the same ragged matrix
+    u = torch.randn(n, 1, generator=torch.Generator().manual_seed(seed))
+    r = m.residual_loss(u.to(DEV), bd)
+    ref_r = O.residual_loss(u.double(), b.double())
+    assert abs(r.item() - float(ref_r)) <= 1e-5 * float(ref_r)
+
+
+def test_node_permutation_equivariance():
+    """relabelling the nodes permutes the output rows (the re-layout is independent of the input ordering)"""
+    g = Golden("dirichlet_ckpt")
+    m = g.model(DEV)
+    b, h, h0, _ = _random_graph(5, 500, False, "cpu")
+    perm = torch.randperm(500, generator=torch.Generator().manual_seed(1))
+    inv = torch.empty_like(perm)
+    inv[perm] = torch.arange(500)
+    from psi_gnn_b200.synthetic import GraphData
+    bp = GraphData(x=b.x[perm], edge_index=inv[b.edge_index], edge_attr=b.edge_attr, a_ij=b.a_ij, y=b.y[perm], sol=b.sol[perm],
+                   prb_data=b.prb_data[perm], tags=b.tags[perm])
+    bp.num_nodes = 500
+    with torch.no_grad():
+        a = m.deqdss.f(h.to(DEV), h0.to(DEV), b.to(DEV))
+        c = m.deqdss.f(h[perm].to(DEV), h0[perm].to(DEV), bp.to(DEV))
+    assert rel_err(c, a[perm.to(DEV)]) <= 1e-6
+
+
+def test_solve_is_deterministic():
+    """two runs of the whole fused Broyden solve give bit-identical iterates, traces and step counts (no atomics anywhere)"""
+    g = Golden("mixed_ckpt")
+    m = g.model(DEV)
+    b = g.batch(DEV)
+    h0 = g.t("h0", DEV)
+    a = m.deqdss.inference(h0, b)
+    c = m.deqdss.inference(h0, b)
+    assert a["steps_run"] == c["steps_run"] and a["nstep"] == c["nstep"]
+    assert a["rel_trace"] == c["rel_trace"]
+    assert torch.equal(a["result"], c["result"])
+
+
+def test_anderson_generic_callable():
+    from psi_gnn_b200 import solver as S
+    g = Golden("dirichlet_seed0")
+    m = g.model(DEV)
+    b = g.batch(DEV)
+    h0 = g.t("h0", DEV)
+    op = S.LayerOperator(m.deqdss.f, h0, b)
+    out = S.anderson(lambda H: op(H), h0, m=2, threshold=60, eps=1e-4)
+    ref = g["anderson_rel_trace"]
+    assert len(out["rel_trace"]) == ref.shape[0]
+    assert np.allclose(out["rel_trace"][:6], ref[:6], rtol=2e-2)
+    assert rel_err(out["result"], g.t("anderson_result")) <= 1e-2
+
+
+def test_unsupported_configurations_fail_loudly():
+    from psi_gnn_b200.dirichlet.psignn import model as M
+    from psi_gnn_b200.dirichlet.psignn.utilities import solver as S
+    g = Golden("dirichlet_seed0")
+    b = g.batch(DEV)
+    cfg = g.cfg()
+    cfg["solver"] = S.broyden
+    cfg["n_layers"] = 2
+    m2 = M.ModelDEQDSS(cfg).to(DEV)
+    with pytest.raises(NotImplementedError):
+        m2.inference(b)
+    h0 = g.t("h0", DEV)
+    with pytest.raises(NotImplementedError):
+        S.broyden(lambda x: x, h0, threshold=3, eps=1e-3, ls=True)
+    with pytest.raises(NotImplementedError):
+        S.broyden(lambda x: x, h0, threshold=3, eps=1e-3, stop_mode="abs")
+    with pytest.raises(RuntimeError):
+        S.broyden(lambda x: x, h0.double(), threshold=3, eps=1e-3)
