@@ -363,7 +363,7 @@ extern "C" int psi_decode(int64_t num_nodes, const float* dev_h, float* dev_u, v
 // ================================================================================================
 // solver workspace
 // ================================================================================================
-#define PROF_CLASSES 5   // 0 operator (layer / VJP pair), 1 k_qn_dots (c,e or all), 2 k_qn_axpy, 3 k_qn_fin2, 4 k_qn_dots a-half (side stream)
+#define PROF_CLASSES 4   // 0 operator (layer / VJP pair), 1 k_qn_dots, 2 k_qn_axpy, 3 k_qn_fin2
 
 struct psi_solver {
     int64_t numel = 0, stride = 0;        // stride = numel rounded up to whole QN_CHUNKs (tail kept at zero)
@@ -391,10 +391,8 @@ struct psi_solver {
     int profile = 0;
     std::vector<cudaEvent_t> ev;          // [((step * PROF_CLASSES) + cls) * 2 + {begin,end}]
     std::vector<double> ev_bytes;         // algorithmic bytes of the launch(es) bracketed by the pair
-    double prof_ms[PROF_CLASSES] = {0, 0, 0, 0, 0}, prof_bytes[PROF_CLASSES] = {0, 0, 0, 0, 0};
-    int64_t prof_launches[PROF_CLASSES] = {0, 0, 0, 0, 0};
-    // side stream for the half of pass 1 that does not depend on the operator evaluation (a = Uᵀδx)
-    cudaStream_t side = nullptr; cudaEvent_t ev_x = nullptr, ev_a = nullptr; bool forked = false;
+    double prof_ms[PROF_CLASSES] = {0, 0, 0, 0}, prof_bytes[PROF_CLASSES] = {0, 0, 0, 0};
+    int64_t prof_launches[PROF_CLASSES] = {0, 0, 0, 0};
     double op_bytes = 0.0;                // algorithmic bytes of one operator evaluation of the current solve
 };
 
@@ -451,9 +449,7 @@ extern "C" int psi_solver_create(psi_solver_t** out, int64_t numel, int max_thre
         s->tma_ctas = std::min(sms, QN_AXPY_MAX_CTAS);
         static bool attr_done = false;
         if (!attr_done) {
-            cudaFuncSetAttribute(k_qn_dots_tma<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dots_tma_smem());
-            cudaFuncSetAttribute(k_qn_dots_tma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dots_tma_smem());
-            cudaFuncSetAttribute(k_qn_dots_tma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dots_tma_smem());
+            cudaFuncSetAttribute(k_qn_dots_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dots_tma_smem());
             cudaFuncSetAttribute(k_qn_axpy_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)axpy_tma_smem(4096));
             attr_done = true;
         }
@@ -475,9 +471,6 @@ extern "C" int psi_solver_create(psi_solver_t** out, int64_t numel, int max_thre
     rc |= solver_alloc(s, (void**)&s->dbuf, (size_t)(3 * s->cap + 8) * sizeof(double));
     rc |= solver_alloc(s, (void**)&s->rel_trace, (size_t)(s->cap + 2) * sizeof(double));
     rc |= solver_alloc(s, (void**)&s->abs_trace, (size_t)(s->cap + 2) * sizeof(double));
-    if (!rc && (cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking) != cudaSuccess ||
-                cudaEventCreateWithFlags(&s->ev_x, cudaEventDisableTiming) != cudaSuccess ||
-                cudaEventCreateWithFlags(&s->ev_a, cudaEventDisableTiming) != cudaSuccess)) { g_psi_err = "psi_solver_create: stream/event creation failed"; rc = -1; }
     if (!rc && cudaMallocHost((void**)&s->h_ctrl, sizeof(QnCtrl)) != cudaSuccess) { g_psi_err = "psi_solver_create: pinned allocation failed"; rc = -1; }
     if (rc) { psi_solver_destroy(s); return -1; }
     float* vecs[] = {s->x, s->g, s->dg, s->dx, s->best, s->fx};
@@ -505,9 +498,6 @@ extern "C" int psi_solver_destroy(psi_solver_t* s) {
     }
     if (s->h_ctrl) cudaFreeHost(s->h_ctrl);
     for (cudaEvent_t e : s->ev) cudaEventDestroy(e);
-    if (s->ev_x) cudaEventDestroy(s->ev_x);
-    if (s->ev_a) cudaEventDestroy(s->ev_a);
-    if (s->side) cudaStreamDestroy(s->side);
     delete s;
     return 0;
 }
@@ -529,7 +519,7 @@ extern "C" int psi_solver_profile(psi_solver_t* s, int enable) {
     return 0;
 }
 
-extern "C" int psi_solver_profile_read(const psi_solver_t* s, double out[15]) {
+extern "C" int psi_solver_profile_read(const psi_solver_t* s, double out[12]) {
     if (s == nullptr || out == nullptr) PSI_FAIL("psi_solver_profile_read: null argument");
     for (int c = 0; c < PROF_CLASSES; ++c) { out[3 * c] = (double)s->prof_launches[c]; out[3 * c + 1] = s->prof_ms[c]; out[3 * c + 2] = s->prof_bytes[c]; }
     return 0;
@@ -604,20 +594,10 @@ static int qn_update(psi_solver* s, int n, int norm_blocks, cudaStream_t st) {
     if (hist_ensure(s, n - 1)) return -1;
     if (nhist > 0) {
         const double vec = (double)s->act_numel * 4.0;
-        if (s->forked) {
-            // the a-half was launched on the side stream before the operator evaluation (qn_fork); join it, then the c,e-half
-            PSI_CK(cudaStreamWaitEvent(st, s->ev_a, 0));
-            s->forked = false;
-            prof_begin(s, n, 1, (1.0 * nhist + 2.0) * vec, st);
-            k_qn_dots_tma<2><<<s->tma_ctas, TMA_THREADS, dots_tma_smem(), st>>>(s->hist, nhist, s->dx, s->dg, s->g, s->partial, s->act_dchunks,
-                                                                                &s->ctrl->done);
-            prof_end(s, n, 1, st);
-        } else {
-            prof_begin(s, n, 1, (2.0 * nhist + 3.0) * vec, st);
-            k_qn_dots_tma<0><<<s->tma_ctas, TMA_THREADS, dots_tma_smem(), st>>>(s->hist, nhist, s->dx, s->dg, s->g, s->partial, s->act_dchunks,
-                                                                                &s->ctrl->done);
-            prof_end(s, n, 1, st);
-        }
+        prof_begin(s, n, 1, (2.0 * nhist + 3.0) * vec, st);
+        k_qn_dots_tma<<<s->tma_ctas, TMA_THREADS, dots_tma_smem(), st>>>(s->hist, nhist, s->dx, s->dg, s->g, s->partial, s->act_dchunks,
+                                                                         &s->ctrl->done);
+        prof_end(s, n, 1, st);
         PSI_CK_LAUNCH();
         s->launches += 1;
     }
@@ -659,24 +639,6 @@ static int qn_update(psi_solver* s, int n, int norm_blocks, cudaStream_t st) {
     return 0;
 }
 
-// Before the operator evaluation of step n: x_n and δx_n are final, so a = U[:n-1]ᵀδx_n can stream on the side stream while the
-// operator kernel (latency-bound, little bandwidth) runs on the main stream.  Joined in qn_update.
-static int qn_fork(psi_solver* s, int n, cudaStream_t st) {
-    const int nhist = n - 1;
-    if (nhist <= 0 || s->side == nullptr) return 0;
-    PSI_CK(cudaEventRecord(s->ev_x, st));
-    PSI_CK(cudaStreamWaitEvent(s->side, s->ev_x, 0));
-    prof_begin(s, n, 4, (1.0 * nhist + 1.0) * (double)s->act_numel * 4.0, s->side);
-    k_qn_dots_tma<1><<<s->tma_ctas, TMA_THREADS, dots_tma_smem(), s->side>>>(s->hist, nhist, s->dx, s->dg, s->g, s->partial, s->act_dchunks,
-                                                                             &s->ctrl->done);
-    prof_end(s, n, 4, s->side);
-    PSI_CK_LAUNCH();
-    PSI_CK(cudaEventRecord(s->ev_a, s->side));
-    s->forked = true;
-    s->launches += 1;
-    return 0;
-}
-
 static int qn_poll(psi_solver* s, cudaStream_t st) {
     PSI_CK(cudaMemcpyAsync(s->h_ctrl, s->ctrl, sizeof(QnCtrl), cudaMemcpyDeviceToHost, st));
     PSI_CK(cudaStreamSynchronize(st));
@@ -690,7 +652,7 @@ static int qn_finish(psi_solver* s, float* result, psi_solve_stats_t* stats, dou
     // the last executed step stopped before its rank-one update unless it ran out of steps: its axpy/fin2 pairs are no-ops
     if (s->profile) {
         const int stopped = (c.stop_reason != 0) ? ran : ran + 1;
-        for (int cls = 2; cls <= 3; ++cls) {
+        for (int cls = 2; cls < PROF_CLASSES; ++cls) {
             const size_t i = ((size_t)stopped * PROF_CLASSES + cls);
             if (stopped <= s->cap + 1 && i < s->ev_bytes.size()) s->ev_bytes[i] = -1.0;
         }
@@ -777,7 +739,6 @@ extern "C" int psi_solver_broyden(psi_solver_t* s, psi_graph_t* g, int kind, int
         // poll the device-side stop flag every `poll` steps; kernels of steps past the stop are no-ops
         const int poll = s->numel < (1 << 22) ? 16 : 4;
         for (int n = 1; n <= threshold; ++n) {
-            if (qn_fork(s, n, st)) return -1;
             if (op_eval(s, g, kind, op, dev_aux, nullptr, st)) return -1;
             if (qn_update(s, n, norm_blocks, st)) return -1;
             if (n % poll == 0 && n < threshold) {

@@ -57,9 +57,6 @@ struct TmaRing {
 
 // ---- pass 1 ---------------------------------------------------------------------------------------------------------
 // partial[(k*3+q)*num_chunks + chunk], num_chunks = stride / DOTS_CH
-// MODE 0: a, c, e in one sweep.  MODE 1: a = Uᵀδx only — δx is known before the operator evaluation, so this half runs on a side
-// stream underneath the (latency-bound) operator kernel.  MODE 2: c = Vᵀδg, e = Vᵀg only, after the operator.
-template <int MODE>
 __global__ void __launch_bounds__(TMA_THREADS, 1)
 k_qn_dots_tma(QnHistory H, int nhist, const float* __restrict__ dx, const float* __restrict__ dg, const float* __restrict__ g,
               float* __restrict__ partial, int num_chunks, const int* __restrict__ done) {
@@ -88,10 +85,10 @@ k_qn_dots_tma(QnHistory H, int nhist, const float* __restrict__ dx, const float*
                 for (int k = k0; k < k1; ++k, ++fill) {
                     const uint32_t s = fill % DOTS_STAGES, use = fill / DOTS_STAGES;
                     if (use > 0) mbar_wait(&empty[s], (use - 1) & 1);
-                    mbar_expect_tx(&full[s], (MODE == 0 ? 2 : 1) * DOTS_CH * sizeof(float));
+                    mbar_expect_tx(&full[s], 2 * DOTS_CH * sizeof(float));
                     float* dst = ring + (size_t)s * 2 * DOTS_CH;
-                    if (MODE != 2) bulk_g2s(dst, hist_u(H, k) + e0, DOTS_CH * sizeof(float), &full[s]);
-                    if (MODE != 1) bulk_g2s(dst + DOTS_CH, hist_v(H, k) + e0, DOTS_CH * sizeof(float), &full[s]);
+                    bulk_g2s(dst, hist_u(H, k) + e0, DOTS_CH * sizeof(float), &full[s]);
+                    bulk_g2s(dst + DOTS_CH, hist_v(H, k) + e0, DOTS_CH * sizeof(float), &full[s]);
                 }
             }
         }
@@ -107,10 +104,9 @@ k_qn_dots_tma(QnHistory H, int nhist, const float* __restrict__ dx, const float*
         const float4* pdx = reinterpret_cast<const float4*>(dx + e0);
         const float4* pdg = reinterpret_cast<const float4*>(dg + e0);
         const float4* pg = reinterpret_cast<const float4*>(g + e0);
-        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        const float4 dx0 = MODE != 2 ? __ldg(pdx + tid) : zero4, dx1 = MODE != 2 ? __ldg(pdx + tid + TMA_CONSUMERS) : zero4;
-        const float4 dg0 = MODE != 1 ? __ldg(pdg + tid) : zero4, dg1 = MODE != 1 ? __ldg(pdg + tid + TMA_CONSUMERS) : zero4;
-        const float4 g0 = MODE != 1 ? __ldg(pg + tid) : zero4, g1 = MODE != 1 ? __ldg(pg + tid + TMA_CONSUMERS) : zero4;
+        const float4 dx0 = __ldg(pdx + tid), dx1 = __ldg(pdx + tid + TMA_CONSUMERS);
+        const float4 dg0 = __ldg(pdg + tid), dg1 = __ldg(pdg + tid + TMA_CONSUMERS);
+        const float4 g0 = __ldg(pg + tid), g1 = __ldg(pg + tid + TMA_CONSUMERS);
         for (int kb0 = k0; kb0 < k1; kb0 += DOTS_KB) {
             const int nb = min(DOTS_KB, k1 - kb0);
             for (int kk = 0; kk < nb; ++kk, ++fill) {
@@ -118,25 +114,21 @@ k_qn_dots_tma(QnHistory H, int nhist, const float* __restrict__ dx, const float*
                 mbar_wait(&full[s], use & 1);
                 const float4* su = reinterpret_cast<const float4*>(ring + (size_t)s * 2 * DOTS_CH);
                 const float4* sv = su + DOTS_CH / 4;
-                float4 u0 = zero4, u1 = zero4, v0 = zero4, v1 = zero4;
-                if (MODE != 2) { u0 = su[tid]; u1 = su[tid + TMA_CONSUMERS]; }
-                if (MODE != 1) { v0 = sv[tid]; v1 = sv[tid + TMA_CONSUMERS]; }
+                const float4 u0 = su[tid], u1 = su[tid + TMA_CONSUMERS];
+                const float4 v0 = sv[tid], v1 = sv[tid + TMA_CONSUMERS];
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty[s]);
-                float a = 0.f, cc = 0.f, e = 0.f;
-                if (MODE != 2) a = warp_sum(dot4(u1, dx1, dot4(u0, dx0, 0.f)));
-                if (MODE != 1) {
-                    cc = warp_sum(dot4(v1, dg1, dot4(v0, dg0, 0.f)));
-                    e = warp_sum(dot4(v1, g1, dot4(v0, g0, 0.f)));
-                }
+                float a = dot4(u1, dx1, dot4(u0, dx0, 0.f));
+                float cc = dot4(v1, dg1, dot4(v0, dg0, 0.f));
+                float e = dot4(v1, g1, dot4(v0, g0, 0.f));
+                a = warp_sum(a); cc = warp_sum(cc); e = warp_sum(e);
                 if (lane == 0) {
                     float* rp = red + ((buf * DOTS_KB + kk) * 3) * 8 + warp;
-                    if (MODE != 2) rp[0] = a;
-                    if (MODE != 1) { rp[8] = cc; rp[16] = e; }
+                    rp[0] = a; rp[8] = cc; rp[16] = e;
                 }
             }
             consumer_bar();
-            if (tid < nb * 3 && (MODE == 0 || (MODE == 1) == (tid % 3 == 0))) {
+            if (tid < nb * 3) {
                 const int kk = tid / 3, q = tid % 3;
                 const float* rp = red + ((buf * DOTS_KB + kk) * 3 + q) * 8;
                 float sum = 0.f;
