@@ -4,7 +4,7 @@
 // passes are pure streams with no reuse, so the job is to keep enough bytes in flight per SM independent of register
 // pressure: one persistent CTA per SM, a producer warp issuing 1-D bulk copies (cp.async.bulk → UBLKCP) of U_k / V_k tiles
 // into a shared-memory ring, full/empty mbarriers per stage, eight consumer warps doing the FMAs out of shared memory.
-//   pass 1  k_qn_dots_tma : a = Uᵀδx, c = Vᵀδg, e = Vᵀg        work item = (2048-element chunk, range of 32 history vectors)
+//   pass 1  k_qn_dots_tma : a = Uᵀδx, c = Vᵀδg, e = Vᵀg        work item = (4096-element chunk, range of 32 history vectors)
 //   pass 2  k_qn_axpy_tma : v = −δx + V·a, w = U·c, t = U·e      each CTA owns an equal contiguous element range (±16 B)
 // Summation orders are fixed (xor-shuffle tree, then warps in order, then chunks in order): results are deterministic.
 #pragma once
@@ -13,8 +13,8 @@
 
 #define TMA_CONSUMERS 256                    // 8 consumer warps
 #define TMA_THREADS (TMA_CONSUMERS + 32)     // + 1 producer warp
-#define DOTS_CH 2048                         // elements per chunk (8 KB per vector)
-#define DOTS_STAGES 12                       // 12 × (8 KB U + 8 KB V) = 192 KB
+#define DOTS_CH 4096                         // elements per chunk (16 KB per vector), four float4 per consumer thread
+#define DOTS_STAGES 6                        // 6 × (16 KB U + 16 KB V) = 192 KB
 #define DOTS_KR 32                           // history vectors per work item
 #define DOTS_KB 8                            // ks per cross-warp reduction batch
 #define AXPY_TILE 2048                       // max elements per tile (8 KB per vector), two float4 per consumer thread
@@ -104,9 +104,14 @@ k_qn_dots_tma(QnHistory H, int nhist, const float* __restrict__ dx, const float*
         const float4* pdx = reinterpret_cast<const float4*>(dx + e0);
         const float4* pdg = reinterpret_cast<const float4*>(dg + e0);
         const float4* pg = reinterpret_cast<const float4*>(g + e0);
-        const float4 dx0 = __ldg(pdx + tid), dx1 = __ldg(pdx + tid + TMA_CONSUMERS);
-        const float4 dg0 = __ldg(pdg + tid), dg1 = __ldg(pdg + tid + TMA_CONSUMERS);
-        const float4 g0 = __ldg(pg + tid), g1 = __ldg(pg + tid + TMA_CONSUMERS);
+        constexpr int R = DOTS_CH / 4 / TMA_CONSUMERS;          // float4 per thread per vector
+        float4 rdx[R], rdg[R], rg[R];
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+            rdx[j] = __ldg(pdx + tid + j * TMA_CONSUMERS);
+            rdg[j] = __ldg(pdg + tid + j * TMA_CONSUMERS);
+            rg[j] = __ldg(pg + tid + j * TMA_CONSUMERS);
+        }
         for (int kb0 = k0; kb0 < k1; kb0 += DOTS_KB) {
             const int nb = min(DOTS_KB, k1 - kb0);
             for (int kk = 0; kk < nb; ++kk, ++fill) {
@@ -114,13 +119,18 @@ k_qn_dots_tma(QnHistory H, int nhist, const float* __restrict__ dx, const float*
                 mbar_wait(&full[s], use & 1);
                 const float4* su = reinterpret_cast<const float4*>(ring + (size_t)s * 2 * DOTS_CH);
                 const float4* sv = su + DOTS_CH / 4;
-                const float4 u0 = su[tid], u1 = su[tid + TMA_CONSUMERS];
-                const float4 v0 = sv[tid], v1 = sv[tid + TMA_CONSUMERS];
+                float4 u[R], v[R];
+#pragma unroll
+                for (int j = 0; j < R; ++j) { u[j] = su[tid + j * TMA_CONSUMERS]; v[j] = sv[tid + j * TMA_CONSUMERS]; }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty[s]);
-                float a = dot4(u1, dx1, dot4(u0, dx0, 0.f));
-                float cc = dot4(v1, dg1, dot4(v0, dg0, 0.f));
-                float e = dot4(v1, g1, dot4(v0, g0, 0.f));
+                float a = 0.f, cc = 0.f, e = 0.f;
+#pragma unroll
+                for (int j = 0; j < R; ++j) {
+                    a = dot4(u[j], rdx[j], a);
+                    cc = dot4(v[j], rdg[j], cc);
+                    e = dot4(v[j], rg[j], e);
+                }
                 a = warp_sum(a); cc = warp_sum(cc); e = warp_sum(e);
                 if (lane == 0) {
                     float* rp = red + ((buf * DOTS_KB + kk) * 3) * 8 + warp;
