@@ -29,6 +29,8 @@ sys.path.insert(0, ROOT)
 
 WORKLOADS = {
     # name: (family, graphs per GPU, mesh size h, description)
+    "c0": ("dirichlet", 32, 0.075, "C0 (BASELINE configs[0]): PSI-GNN dirichlet forward fixed-point solve (inference: encoder, Broyden, decoder), batch of 32 "
+                                    "synthetic ~500-node 2D triangle Poisson meshes per GPU"),
     "c1": ("dirichlet", 32, 0.075, "C1: PSI-GNN dirichlet training step, batch of 32 synthetic ~500-node 2D triangle Poisson meshes"),
     "c3": ("dirichlet", 256, 0.075, "C3: PSI-GNN dirichlet training step (Broyden forward + implicit-adjoint backward), batch 256 synthetic ~500-node meshes per GPU"),
     "c5": ("dirichlet", 1, 0.075, "C5: PSI-GNN dirichlet forward Broyden solve (500-step cap) of ONE synthetic 1M-node mesh, node-range partitioned "
@@ -124,8 +126,8 @@ def run_native(args):
         dist.init_process_group("nccl", device_id=dev)
     _native.load()                                              # fail loudly if the extension is missing
     family, n_graphs, h, desc = WORKLOADS[args.workload]
-    if args.workload == "c5":
-        return run_native_c5(args, rank, local, world, dev)
+    if args.workload in ("c5", "c0"):
+        return run_native_inference(args, rank, local, world, dev)
     if args.graphs:
         n_graphs = args.graphs
     P, cfg = load_params(family)
@@ -287,21 +289,27 @@ def _timed_steps(fn, k, world, dev, flush):
     return float(t.item())
 
 
-def run_native_c5(args, rank, local, world, dev):
-    """one large mesh: unpartitioned on 1 GPU, node-range partitioned on N GPUs (strong scaling)"""
+def run_native_inference(args, rank, local, world, dev):
+    """forward solves.  c5: one large mesh, unpartitioned on 1 GPU, node-range partitioned on N GPUs (strong scaling);
+    c0: a batch of 32 meshes per GPU (weak scaling, independent solves per rank)."""
     import torch.distributed as dist
     from psi_gnn_b200 import model as PM, partition, synthetic
     from psi_gnn_b200.dirichlet.psignn import model as M
     from psi_gnn_b200.dirichlet.psignn.utilities import solver as S
-    family, _, h, desc = WORKLOADS["c5"]
+    family, n_graphs, h, desc = WORKLOADS[args.workload]
+    one_mesh = args.workload == "c5"
     nodes = args.nodes or C5_NODES
     P, cfg = load_params(family)
     cfg["solver"] = S.broyden
     model = M.ModelDEQDSS(cfg)
     model.load_state_dict(P)
     model = model.to(dev).eval()
-    mesh = synthetic.make_large_mesh(nodes, seed=0, h=h)
-    if world > 1:
+    if one_mesh:
+        mesh = synthetic.make_large_mesh(nodes, seed=0, h=h)
+    else:
+        n_graphs = args.graphs or n_graphs
+        mesh = make_batch(family, n_graphs, h, seed0=rank * n_graphs)
+    if world > 1 and one_mesh:
         part = partition.partition_mesh(mesh, world, rank=rank)[0]
         host = part.local.pin_memory()
         n_owned, n_ghost = part.n_owned, part.n_ghost
@@ -359,21 +367,23 @@ def run_native_c5(args, rank, local, world, dev):
                    "alg_GBps": round(v["bytes"] / max(v["ms"], 1e-9) / 1e6, 1), "frac_of_peak": round(v["bytes"] / max(v["ms"], 1e-9) / 1e6 / peak, 4)}
                for k, v in prof.items()}
     E_glob = int((mesh.edge_index[0] != mesh.edge_index[1]).sum())
+    units = 1 if one_mesh else world * n_graphs            # graphs solved per step over all ranks
+    mult = 1 if one_mesh else world                        # independent solves: iteration / edge rates add up over the ranks
     out = {
-        "metric": "PSI-GNN solve graphs/s (forward Broyden solve of one large mesh)",
-        "value": round(args.steps / sec, 4), "unit": "graphs/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
-        "ms_per_step": round(ms_total / args.steps, 3), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "metric": "PSI-GNN solve graphs/s (forward Broyden solve%s)" % (" of one large mesh" if one_mesh else ", inference"),
+        "value": round(units * args.steps / sec, 4), "unit": "graphs/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
+        "ms_per_step": round(ms_total / args.steps, 3), "higher_is_better": True, "scaling": "strong" if one_mesh else "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic P1-FEM Poisson mesh (seeded generator); weights = reference shipped checkpoint",
         "config": {"workload": desc, "nodes": mesh.num_nodes, "nnz": int(mesh.edge_index.shape[1]), "offdiag_edges": E_glob,
                    "owned_nodes_rank0": n_owned, "ghost_nodes_rank0": n_ghost, "solver": "broyden", "fw_tol": cfg["fw_tol"], "fw_thres": cfg["fw_thres"],
-                   "parallelism": "node-range mesh partition x%d" % world if world > 1 else "single GPU",
+                   "parallelism": ("node-range mesh partition x%d" % world if one_mesh else "independent batches x%d" % world) if world > 1 else "single GPU",
                    "l2": "256 MB buffer written between timed steps; working set (history) exceeds L2"},
-        "iterations_per_s": round(run_stats["steps"] / sec, 1),
-        "edge_msg_updates_per_s": round(run_stats["evals"] * 2 * E_glob / sec, 1),
+        "iterations_per_s": round(mult * run_stats["steps"] / sec, 1),
+        "edge_msg_updates_per_s": round(mult * run_stats["evals"] * 2 * E_glob / sec, 1),
         "solver_steps_per_step": {"forward": run_stats["steps"] / args.steps},
         "last_solve": {k: model.deqdss.last_forward[k] for k in ("lowest", "nstep", "steps_run", "stop_reason", "prot_break")},
         "gpu_launches": run_stats["launches"],
-        "e2e": {"value": round(args.steps / (ms_e2e / 1e3), 4), "unit": "graphs/s", "ms_per_step": round(ms_e2e / args.steps, 3),
+        "e2e": {"value": round(units * args.steps / (ms_e2e / 1e3), 4), "unit": "graphs/s", "ms_per_step": round(ms_e2e / args.steps, 3),
                 "h2d_bytes_per_step": host.nbytes(), "d2h_bytes_per_step": 4 * n_owned},
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                      "traffic": traffic, "traffic_source": "algorithmic bytes per launch x the DRAM-traffic/algorithmic ratio of the ncu --set full capture in profiles/ncu_traffic.json" if traffic else None, "peak_source": peak_src, "avg_launch_us": round(1e3 * d["ms"] / max(d["launches"], 1), 2),
@@ -381,6 +391,8 @@ def run_native_c5(args, rank, local, world, dev):
         "kernels": kernels, "clocks": clocks,
     }
     if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline(args, family, h, budget_s=25.0)
         emit(out)
     if world > 1:
         dist.destroy_process_group()
@@ -415,12 +427,38 @@ def cpu_step_fn(family, h, sample_graphs):
     return step, batch
 
 
+def cpu_infer_fn(family, h, workload, sample):
+    """oracle port of ModelDEQDSS.inference (encoder → Broyden → decoder) on a batch of `sample` meshes (c0) or one mesh of `sample` nodes (c5)"""
+    from oracle import psignn_oracle as O
+    from psi_gnn_b200 import synthetic
+    P, cfg = load_params(family)
+    batch = synthetic.make_large_mesh(sample, seed=0, h=h) if workload == "c5" else make_batch(family, sample, h, seed0=0)
+
+    def step():
+        out = O.inference(P, batch, cfg["fw_thres"], cfg["fw_tol"], mixed=(family == "mixed"))
+        return len(out["xest_trace"]) - 1, 0
+
+    return step, batch
+
+
+def cpu_sample(args):
+    """(step function, batch, graphs per step, description) of the bounded CPU sample of the workload"""
+    family, n_graphs, h, _ = WORKLOADS[args.workload]
+    if args.workload == "c5":
+        step, batch = cpu_infer_fn(family, h, "c5", 20000)
+        return step, batch, 1, "one forward solve of a %d-node mesh (the 1M-node mesh is out of reach of the CPU path in minutes)" % batch.num_nodes
+    if args.workload == "c0":
+        step, batch = cpu_infer_fn(family, h, "c0", n_graphs)
+        return step, batch, n_graphs, "one forward solve of the full batch of %d meshes (N=%d nodes)" % (n_graphs, batch.num_nodes)
+    step, batch = cpu_step_fn(family, h, 8)
+    return step, batch, 8, "one training step on a batch of 8 of the workload's meshes (N=%d nodes)" % batch.num_nodes
+
+
 def cpu_baseline(args, family, h, budget_s):
     torch.set_flush_denormal(True)
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    sample = 8
-    step, batch = cpu_step_fn(family, h, sample)
+    step, batch, sample, what = cpu_sample(args)
     step()                                                      # warm-up (library initialisation)
     t0 = time.perf_counter()
     n, its = 0, 0
@@ -433,8 +471,7 @@ def cpu_baseline(args, family, h, budget_s):
     dt = time.perf_counter() - t0
     return {"value": round(sample * n / dt, 4), "unit": "graphs/s", "cores": torch.get_num_threads(), "kind": "port",
             "iterations_per_s": round(its / dt, 2),
-            "sample": "%d training steps on a batch of %d of the workload's meshes (N=%d nodes), oracle port of the reference "
-                      "training step, torch %s CPU, %d threads" % (n, sample, batch.num_nodes, torch.__version__, torch.get_num_threads())}
+            "sample": "%d x %s; oracle port of the reference, torch %s CPU, %d threads" % (n, what, torch.__version__, torch.get_num_threads())}
 
 
 def run_reference(args):
@@ -445,8 +482,7 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     family, n_graphs, h, desc = WORKLOADS[args.workload]
-    sample = 8
-    step, batch = cpu_step_fn(family, h, sample)
+    step, batch, sample, what = cpu_sample(args)
     for _ in range(max(1, min(args.warmup, 1))):               # one warm-up pass is enough on the CPU (no clocks to ramp)
         step()
     t0 = time.perf_counter()
@@ -456,9 +492,11 @@ def run_reference(args):
         its += fw + bw
     dt = time.perf_counter() - t0
     val = sample * args.steps / dt
-    sample_txt = ("each step = one training step on a batch of %d of the workload's meshes (N=%d nodes); oracle port of the reference "
-                  "(the Python reference needs PyG/torch_sparse and cannot travel to the GPU box)" % (sample, batch.num_nodes))
-    out = {"impl": "reference", "metric": "PSI-GNN solve graphs/s (training step: Broyden forward solve + implicit-adjoint backward solve)",
+    sample_txt = ("each step = %s; oracle port of the reference (the Python reference needs PyG/torch_sparse and cannot travel to the "
+                  "GPU box)" % what)
+    metric = {"c5": "PSI-GNN solve graphs/s (forward Broyden solve of one large mesh)", "c0": "PSI-GNN solve graphs/s (forward Broyden solve, inference)"}.get(
+        args.workload, "PSI-GNN solve graphs/s (training step: Broyden forward solve + implicit-adjoint backward solve)")
+    out = {"impl": "reference", "metric": metric,
            "value": round(val, 4), "unit": "graphs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": 1,
            "ms_per_step": round(1e3 * dt / args.steps, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
            "data": "synthetic P1-FEM Poisson meshes (seeded generator); weights = reference shipped checkpoint",
