@@ -232,11 +232,8 @@ def test_anderson_matches_reference(golden):
     assert rel_err(out["result"], golden.t("anderson_result")) <= 1e-2
 
 
-def test_training_step_matches_reference(golden, monkeypatch):
+def _train_step(m, b, v, monkeypatch):
     from psi_gnn_b200 import model as PM
-    m = golden.model(DEV)
-    b = golden.batch(DEV)
-    v = golden.t("train_v", DEV)
     monkeypatch.setattr(PM.torch, "randn", lambda *a, **k: v.clone())
     m.train()
     m.zero_grad()
@@ -245,24 +242,66 @@ def test_training_step_matches_reference(golden, monkeypatch):
         loss_dic["autoencoder_loss"].mean()
     loss.backward()
     monkeypatch.undo()
-    assert rel_err(u.detach(), golden.t("train_u")) <= BAND_U
+    gs = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1).double().cpu() for _, p in m.named_parameters()])
+    return u, loss_dic, gs
+
+
+def _ref_grads(golden, m):
+    return torch.cat([golden.t("train_grad." + k).reshape(-1).double() for k, _ in m.named_parameters()])
+
+
+def test_training_step_teacher_forced(golden, monkeypatch):
+    """ModelDEQDSS.forward + loss.backward() with the forward fixed point pinned to the reference's H* (so that the chaotic scatter of
+    the forward trajectory is out of the picture): losses, the implicit-adjoint solve and all parameter gradients must match the
+    reference's training step (same Hutchinson probe v)."""
+    from psi_gnn_b200 import solver as S
+    m = golden.model(DEV)
+    b = golden.batch(DEV)
+    hstar = golden.t("train_hstar", DEV)
+    calls = []
+
+    def solver(f, x0, threshold, eps):
+        if not calls:                                  # forward solve → the reference's fixed point
+            calls.append("fw")
+            return {"result": hstar.clone(), "lowest": float(golden["fw_lowest"]), "nstep": int(golden["fw_nstep"]), "steps_run": 0,
+                    "f_evals": 0, "launches": 0}
+        calls.append("bw")
+        return S.broyden(f, x0, threshold=threshold, eps=eps)
+
+    m.deqdss.config_deq["solver"] = solver
+    u, loss_dic, gs = _train_step(m, b, golden.t("train_v", DEV), monkeypatch)
+    assert calls == ["fw", "bw"]
+    assert rel_err(u.detach(), golden.t("train_u")) <= 1e-5
     for k in ("residual_loss", "jacobian_loss", "encoder_loss", "autoencoder_loss", "mse_loss", "mse_dirichlet"):
         ref = float(golden["train_loss." + k])
-        assert abs(loss_dic[k].item() - ref) <= 0.05 * abs(ref) + 1e-7, k
+        assert abs(loss_dic[k].item() - ref) <= 1e-4 * abs(ref) + 1e-9, k
+    bw = m.deqdss.last_backward
+    tol = max(1e-4, 400.0 * max(bw["lowest"], float(golden["train_bw_lowest"])))
+    assert rel_err(bw["result"], golden.t("train_bw_result")) <= tol
+    rs = _ref_grads(golden, m)
+    cos = float((gs @ rs) / (gs.norm() * rs.norm()))
+    assert cos > 0.9999, cos
+    assert abs(float(gs.norm() / rs.norm()) - 1) < 5e-3
+    assert float((gs - rs).norm() / rs.norm()) < 2e-2
+
+
+def test_training_step_free_running(golden, monkeypatch):
+    """The same step with the native forward solve: the fixed point now carries the O(eps/(1−ρ)) scatter every implementation has
+    (SURVEY §7.3-1), so only bands are asserted here; the tight checks are the teacher-forced tests."""
+    m = golden.model(DEV)
+    b = golden.batch(DEV)
+    u, loss_dic, gs = _train_step(m, b, golden.t("train_v", DEV), monkeypatch)
+    assert rel_err(u.detach(), golden.t("train_u")) <= BAND_U
+    for k in ("residual_loss", "jacobian_loss", "encoder_loss", "autoencoder_loss"):
+        ref = float(golden["train_loss." + k])
+        assert abs(loss_dic[k].item() - ref) <= 0.25 * abs(ref) + 1e-7, k
+    assert m.deqdss.last_forward["lowest"] < float(golden["cfg.fw_tol"])
     bw = m.deqdss.last_backward
     assert bw is not None and bw["lowest"] < 50 * float(golden["cfg.bw_tol"]) + float(golden["train_bw_lowest"])
-    # free-running, the adjoint inherits the O(1e-3) scatter of H* amplified by (I − Jᵀ)⁻¹ (ρ ≈ 0.99): a loose band here, the tight
-    # check of the backward solve is test_backward_solve_teacher_forced
-    assert rel_err(bw["result"], golden.t("train_bw_result")) <= 0.25
-    # parameter gradients: cosine similarity + norm (the backward solve amplifies fp32 noise by 1/(1−ρ))
-    gs, rs = [], []
-    for k, p in m.named_parameters():
-        gs.append((p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1).double().cpu())
-        rs.append(golden.t("train_grad." + k).reshape(-1).double())
-    gvec, rvec = torch.cat(gs), torch.cat(rs)
-    cos = float((gvec @ rvec) / (gvec.norm() * rvec.norm()))
-    assert cos > 0.99, cos
-    assert abs(float(gvec.norm() / rvec.norm()) - 1) < 0.15
+    rs = _ref_grads(golden, m)
+    assert torch.isfinite(gs).all()
+    cos = float((gs @ rs) / (gs.norm() * rs.norm()))
+    assert cos > 0.98, cos
 
 
 def test_backward_solve_teacher_forced(golden):
