@@ -31,6 +31,8 @@ WORKLOADS = {
     # name: (family, graphs per GPU, mesh size h, description)
     "c0": ("dirichlet", 32, 0.075, "C0 (BASELINE configs[0]): PSI-GNN dirichlet forward fixed-point solve (inference: encoder, Broyden, decoder), batch of 32 "
                                     "synthetic ~500-node 2D triangle Poisson meshes per GPU"),
+    "c2": ("dss", 32, 0.075, "C2 (BASELINE configs[1]): DSS baseline inference (30 unrolled layers with per-layer weights on the shared fused layer kernel), "
+                              "batch of 32 synthetic ~500-node meshes per GPU, shipped DSS checkpoint"),
     "c1": ("dirichlet", 32, 0.075, "C1: PSI-GNN dirichlet training step, batch of 32 synthetic ~500-node 2D triangle Poisson meshes"),
     "c3": ("dirichlet", 256, 0.075, "C3: PSI-GNN dirichlet training step (Broyden forward + implicit-adjoint backward), batch 256 synthetic ~500-node meshes per GPU"),
     "c5": ("dirichlet", 1, 0.075, "C5: PSI-GNN dirichlet forward Broyden solve (500-step cap) of ONE synthetic 1M-node mesh, node-range partitioned "
@@ -128,6 +130,8 @@ def run_native(args):
     family, n_graphs, h, desc = WORKLOADS[args.workload]
     if args.workload in ("c5", "c0"):
         return run_native_inference(args, rank, local, world, dev)
+    if args.workload == "c2":
+        return run_native_dss(args, rank, local, world, dev)
     if args.graphs:
         n_graphs = args.graphs
     P, cfg = load_params(family)
@@ -398,6 +402,80 @@ def run_native_inference(args, rank, local, world, dev):
         dist.destroy_process_group()
 
 
+def load_dss():
+    z = np.load(os.path.join(ROOT, "tests", "golden", "dss_ckpt.npz"))
+    P = {k[6:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("param.")}
+    return P, dict(latent_dim=10, k=int(z["cfg.k"]), alpha=float(z["cfg.alpha"]), gamma=0.9)
+
+
+def dss_batch(n_graphs, h, seed0):
+    from psi_gnn_b200 import synthetic
+    return synthetic.to_dss(synthetic.make_batch(n_graphs, seed0=seed0, h=h, solve=False))
+
+
+def run_native_dss(args, rank, local, world, dev):
+    """DSS baseline inference: k = 30 launches of the fused layer kernel (kind DSS) with per-layer weight blocks + one decode"""
+    import torch.distributed as dist
+    from psi_gnn_b200.dirichlet.dss import model as M
+    _, n_graphs, h, desc = WORKLOADS["c2"]
+    n_graphs = args.graphs or n_graphs
+    P, cfg = load_dss()
+    model = M.DeepStatisticalSolver(cfg)
+    model.load_state_dict(P)
+    model = model.to(dev).eval()
+    host = dss_batch(n_graphs, h, rank * n_graphs).pin_memory()
+    dev_batch = host.to(dev)
+    flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)
+    N, nnz = host.num_nodes, int(host.edge_index.shape[1])
+    warm = max(args.warmup, 1)
+    for _ in range(warm):
+        model.inference(dev_batch)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    # per-launch time of the layer kernel: CUDA events around the 30 layer launches of each step (the decode is outside the bracket)
+    ms_total = _timed_steps(lambda: model.inference(dev_batch), args.steps, world, dev, flush)
+    clocks = sampler.stop() if rank == 0 else None
+
+    def e2e():
+        return model.inference(host.to(dev, non_blocking=True)).cpu()
+
+    e2e()
+    ms_e2e = _timed_steps(e2e, args.steps, world, dev, flush)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    k = cfg["k"]
+    alg = N * (40.0 + 1.0 + 12.0 + 0.5 + 40.0) + 2 * nnz * 16.0          # h read, tag, b', offsets, h' written; 16-byte records per edge per list
+    per_launch_us = 1e3 * ms_total / args.steps / k                         # upper bound: includes the weight upload and launch gaps
+    achieved = alg / (per_launch_us * 1e-6) / 1e9
+    sec = ms_total / 1e3
+    out = {"metric": "DSS baseline inference graphs/s (30 layers on the shared fused layer kernel)",
+           "value": round(world * n_graphs * args.steps / sec, 2), "unit": "graphs/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
+           "ms_per_step": round(ms_total / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+           "data": "synthetic P1-FEM Poisson meshes in the DSS reader's layout; weights = reference shipped DSS checkpoint",
+           "config": {"workload": desc, "graphs_per_gpu": n_graphs, "nodes_per_gpu": N, "edges_per_gpu": nnz, "layers": k,
+                      "l2": "256 MB buffer written between timed steps"},
+           "edge_msg_updates_per_s": round(world * k * 2 * nnz * args.steps / sec, 1),
+           "gpu_launches": args.steps * (k + 1),
+           "e2e": {"value": round(world * n_graphs * args.steps / (ms_e2e / 1e3), 2), "unit": "graphs/s", "ms_per_step": round(ms_e2e / args.steps, 3),
+                   "h2d_bytes_per_step": host.nbytes(), "d2h_bytes_per_step": 4 * N},
+           "roofline": {"bound": "hbm", "kernel": "k_layer_forward<DSS>", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                        "frac": round(achieved / peak, 4), "traffic": None, "avg_launch_us": round(per_launch_us, 2), "alg_bytes_per_launch": alg,
+                        "note": "latency-bound at this size: 16 k nodes are a fraction of one wave; time per launch includes the 12.7 KB weight-block "
+                                "upload and the launch gap"},
+           "clocks": clocks}
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline(args, "dss", h, budget_s=15.0)
+        emit(out)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 # =====================================================================================================================
 # CPU arm: the oracle port of the reference's training step (the reference itself is Python that needs PyG/torch_sparse and
 # /root/reference, neither of which exists on the GPU box)
@@ -444,6 +522,17 @@ def cpu_infer_fn(family, h, workload, sample):
 def cpu_sample(args):
     """(step function, batch, graphs per step, description) of the bounded CPU sample of the workload"""
     family, n_graphs, h, _ = WORKLOADS[args.workload]
+    if args.workload == "c2":
+        from oracle import psignn_oracle as O
+        P, cfg = load_dss()
+        batch = dss_batch(n_graphs, h, 0)
+
+        def step():
+            with torch.no_grad():
+                O.dss_inference(P, batch, cfg["k"], cfg["alpha"])
+            return cfg["k"], 0
+
+        return step, batch, n_graphs, "one DSS inference (30 layers) of the full batch of %d meshes (N=%d nodes)" % (n_graphs, batch.num_nodes)
     if args.workload == "c5":
         step, batch = cpu_infer_fn(family, h, "c5", 20000)
         return step, batch, 1, "one forward solve of a %d-node mesh (the 1M-node mesh is out of reach of the CPU path in minutes)" % batch.num_nodes
@@ -494,7 +583,8 @@ def run_reference(args):
     val = sample * args.steps / dt
     sample_txt = ("each step = %s; oracle port of the reference (the Python reference needs PyG/torch_sparse and cannot travel to the "
                   "GPU box)" % what)
-    metric = {"c5": "PSI-GNN solve graphs/s (forward Broyden solve of one large mesh)", "c0": "PSI-GNN solve graphs/s (forward Broyden solve, inference)"}.get(
+    metric = {"c2": "DSS baseline inference graphs/s (30 layers on the shared fused layer kernel)",
+              "c5": "PSI-GNN solve graphs/s (forward Broyden solve of one large mesh)", "c0": "PSI-GNN solve graphs/s (forward Broyden solve, inference)"}.get(
         args.workload, "PSI-GNN solve graphs/s (training step: Broyden forward solve + implicit-adjoint backward solve)")
     out = {"impl": "reference", "metric": metric,
            "value": round(val, 4), "unit": "graphs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": 1,
