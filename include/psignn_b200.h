@@ -102,6 +102,11 @@ int psi_halo_exchange(psi_graph_t* g, float* dev_vec, int width, void* stream);
 /* ---- one application of the layer and its transpose-Jacobian --------------------------------- */
 int psi_layer_forward(const psi_graph_t* g, int kind, const float* dev_h, const float* dev_h0,
                       float* dev_out, void* stream);
+/* n_layers unrolled applications in one call (DSS inference dirichlet/dss/model.py:113-123: one packed weight block per layer,
+ * n_blobs = n_layers; DSGPS inference dirichlet/dsgps/model.py:143-160: the same block every step, n_blobs = 1).  dev_blobs holds n_blobs
+ * blocks of psi_weights_floats() floats; the last uploaded block stays resident (its decoder is used by psi_decode). */
+int psi_layers_unrolled(const psi_graph_t* g, int kind, const float* dev_blobs, int n_blobs, int n_layers, const float* dev_h,
+                        const float* dev_h0, float* dev_work, float* dev_out, void* stream);
 /* cache the linearisation point (ReLU masks, gate, LayerNorm statistics) for psi_vjp_apply */
 int psi_vjp_prepare(psi_graph_t* g, int kind, const float* dev_hstar, const float* dev_h0, void* stream);
 /* out = J^T y (+ grad if grad != NULL), J = d f / d h at the prepared point */

@@ -74,8 +74,8 @@ class DeepStatisticalSolver(nn.Module):
         key = (W.version_key(P), str(device))
         if self._blobs[0] != key:
             with torch.no_grad():
-                self._blobs = (key, [W.pack_dss(P, k, self.config["alpha"], device) for k in range(self.config["k"])],
-                               [W.next_serial() for _ in range(self.config["k"])])
+                self._blobs = (key, torch.stack([W.pack_dss(P, k, self.config["alpha"], device) for k in range(self.config["k"])]).contiguous(),
+                               W.next_serial())
         return self._blobs[2], self._blobs[1]
 
     def inference(self, batch):
@@ -85,12 +85,15 @@ class DeepStatisticalSolver(nn.Module):
             raise NotImplementedError("psi_gnn_b200: the fused kernel is built for latent_dim=10")
         g = graph_of(batch, N.KIND_DSS)
         dev = batch.edge_index.device
-        serials, blobs = self._packed(dev)
+        serial, blobs = self._packed(dev)
+        k = self.config["k"]
         H = torch.zeros(g.num_nodes, W.D, dtype=torch.float32, device=dev)
-        for k in range(self.config["k"]):
-            W.upload(blobs[k], serials[k])
-            H = g.layer_forward(N.KIND_DSS, H, None)
-        return _decode(H)                         # Decoder_{k-1} travels in the last layer's block
+        work, out = torch.empty_like(H), torch.empty_like(H)
+        with torch.cuda.device(dev):
+            N.check(N.load().psi_layers_unrolled(g.handle, N.KIND_DSS, N.ptr(blobs), k, k, N.ptr(H), None, N.ptr(work), N.ptr(out),
+                                                 N.stream_ptr()), "psi_layers_unrolled")
+        W.mark_resident(dev, (serial, k - 1))     # the last layer's block (with Decoder_{k-1}) is what the constant bank now holds
+        return _decode(out)
 
     def forward(self, batch):
         raise NotImplementedError("psi_gnn_b200: the unrolled DSS training forward is outside the accelerated path; "
@@ -138,10 +141,14 @@ class ModelDSGPS(nn.Module):
         H0 = torch.empty(x.numel(), W.D, dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
             N.check(N.load().psi_encode(x.numel(), N.ptr(x), N.ptr(H0), N.stream_ptr()), "psi_encode")
-        H = H0
-        for _ in range(self.config["k"] if k is None else k):
-            H = g.layer_forward(N.KIND_DSGPS, H, H0)
-        return _decode(H)
+        steps = self.config["k"] if k is None else k
+        if steps < 1:
+            return _decode(H0)
+        work, out = torch.empty_like(H0), torch.empty_like(H0)
+        with torch.cuda.device(dev):
+            N.check(N.load().psi_layers_unrolled(g.handle, N.KIND_DSGPS, N.ptr(self._blob[1]), 1, steps, N.ptr(H0), N.ptr(H0), N.ptr(work),
+                                                 N.ptr(out), N.stream_ptr()), "psi_layers_unrolled")
+        return _decode(out)
 
     def forward(self, batch):
         raise NotImplementedError("psi_gnn_b200: the unrolled DSGPS training forward is outside the accelerated path; "

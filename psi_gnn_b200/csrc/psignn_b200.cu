@@ -245,6 +245,30 @@ extern "C" int psi_layer_forward(const psi_graph_t* g, int kind, const float* de
     return launch_layer<false>(g, kind, dev_h, dev_h0, dev_out, SolverEpi{nullptr, nullptr, nullptr, nullptr}, as_stream(stream));
 }
 
+// k unrolled applications of the layer (DSS: one weight block per layer; DSGPS: the same block k times) in one call:
+// out = f_{k-1}(… f_1(f_0(h)) …).  dev_work is a scratch [N, d] buffer for the ping-pong.
+extern "C" int psi_layers_unrolled(const psi_graph_t* g, int kind, const float* dev_blobs, int n_blobs, int n_layers, const float* dev_h,
+                                   const float* dev_h0, float* dev_work, float* dev_out, void* stream) {
+    if (check_kind(g, kind)) return -1;
+    if (n_layers < 1 || (n_blobs != 1 && n_blobs != n_layers)) PSI_FAIL("psi_layers_unrolled: n_blobs must be 1 or n_layers");
+    if (dev_blobs == nullptr) PSI_FAIL("psi_layers_unrolled: null weight blocks");
+    if (g->N > 0 && (dev_h == nullptr || dev_out == nullptr || dev_work == nullptr)) PSI_FAIL("psi_layers_unrolled: null pointer");
+    if (g->N > 0 && (dev_h == dev_out || dev_h == dev_work || dev_out == dev_work)) PSI_FAIL("psi_layers_unrolled: buffers must be distinct");
+    cudaStream_t st = as_stream(stream);
+    const SolverEpi noE{nullptr, nullptr, nullptr, nullptr};
+    const size_t wf = sizeof(LayerWeights) / sizeof(float);
+    const float* src = dev_h;
+    for (int k = 0; k < n_layers; ++k) {
+        if (k == 0 || n_blobs > 1)
+            PSI_CK(cudaMemcpyToSymbolAsync(cW, dev_blobs + (size_t)(n_blobs > 1 ? k : 0) * wf, sizeof(LayerWeights), 0, cudaMemcpyDeviceToDevice, st));
+        // ping-pong so that the last layer lands in dev_out
+        float* dst = ((n_layers - 1 - k) % 2 == 0) ? dev_out : dev_work;
+        if (launch_layer<false>(g, kind, src, dev_h0, dst, noE, st)) return -1;
+        src = dst;
+    }
+    return 0;
+}
+
 static int vjp_alloc(psi_graph* g, cudaStream_t st) {
     if (g->p_vjp != nullptr) return 0;
     const int64_t N = g->N > 0 ? g->N : 1;

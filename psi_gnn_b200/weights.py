@@ -168,5 +168,11 @@ def upload(blob: torch.Tensor, key) -> None:
     _UPLOADED[dev] = key
 
 
+def mark_resident(device, key) -> None:
+    """record that a native call left the block identified by ``key`` in the constant bank"""
+    device = torch.device(device)
+    _UPLOADED[device.index if device.index is not None else torch.cuda.current_device()] = key
+
+
 def invalidate() -> None:
     _UPLOADED.clear()
