@@ -180,11 +180,11 @@ k_qn_fin1_global(int nhist, const double* __restrict__ dbuf, float* __restrict__
 }
 
 // Σ of the pass-2 partials → sp[0] = ⟨v_n,δg⟩, sp[1] = ⟨v_n,g_n⟩ (local part, all-reduced before k_qn_fin2)
-__global__ void __launch_bounds__(256) k_qn_red2(const float* __restrict__ partial2, int p2_ctas, double* __restrict__ sp, const QnCtrl* __restrict__ ctrl) {
+__global__ void __launch_bounds__(256) k_qn_red2(const double* __restrict__ partial2, int p2_ctas, double* __restrict__ sp, const QnCtrl* __restrict__ ctrl) {
     __shared__ double sm[16];
     if (ctrl->done) return;
     double a = 0.0, b = 0.0;
-    for (int i = threadIdx.x; i < p2_ctas; i += 256) { a += (double)partial2[i]; b += (double)partial2[p2_ctas + i]; }
+    for (int i = threadIdx.x; i < p2_ctas; i += 256) { a += partial2[i]; b += partial2[p2_ctas + i]; }
     a = warp_sum_d(a); b = warp_sum_d(b);
     if ((threadIdx.x & 31) == 0) { sm[threadIdx.x >> 5] = a; sm[8 + (threadIdx.x >> 5)] = b; }
     __syncthreads();
@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(256) k_qn_red2(const float* __restrict__ parti
 // ---- finalize 2: normalise u_n, form the new update, advance x ---------------------------------------------
 __global__ void __launch_bounds__(QN_THREADS)
 k_qn_fin2(QnHistory H, int n, float* __restrict__ dx_upd /* in: t, out: δx of the next step */, const float* __restrict__ g,
-          float* __restrict__ x, const float* __restrict__ partial2, int p2_ctas, float* __restrict__ xtrace_next,
+          float* __restrict__ x, const double* __restrict__ partial2, int p2_ctas, float* __restrict__ xtrace_next,
           QnCtrl* __restrict__ ctrl, int num_chunks, const double* __restrict__ sp_global) {
     __shared__ double sm[2 * (QN_THREADS / 32)];
     __shared__ float s_sp[2];
@@ -211,7 +211,7 @@ k_qn_fin2(QnHistory H, int n, float* __restrict__ dx_upd /* in: t, out: δx of t
         __syncthreads();
     } else {   // every CTA reduces the pass-2 partials in the same fixed order → identical s, p everywhere
         double a = 0.0, b = 0.0;
-        for (int i = threadIdx.x; i < p2_ctas; i += QN_THREADS) { a += (double)partial2[i]; b += (double)partial2[p2_ctas + i]; }
+        for (int i = threadIdx.x; i < p2_ctas; i += QN_THREADS) { a += partial2[i]; b += partial2[p2_ctas + i]; }
         a = warp_sum_d(a); b = warp_sum_d(b);
         if ((threadIdx.x & 31) == 0) { sm[threadIdx.x >> 5] = a; sm[QN_THREADS / 32 + (threadIdx.x >> 5)] = b; }
         __syncthreads();

@@ -395,7 +395,8 @@ struct psi_solver {
     int num_chunks = 0, axpy_ctas = 0, norm_cap = 0;
     int dots_chunks = 0, tma_ctas = 0;    // 2048-element chunks of pass 1; persistent CTAs (one per SM) of the TMA kernels
     float *x = nullptr, *g = nullptr, *dg = nullptr, *dx = nullptr, *best = nullptr, *fx = nullptr;
-    float *partial = nullptr, *partial2 = nullptr, *coef = nullptr, *norm_part = nullptr;
+    float *partial = nullptr, *coef = nullptr, *norm_part = nullptr;
+    double* partial2 = nullptr;           // fp64 partial sums of ⟨v_n,δg⟩ and ⟨v_n,g_n⟩ per persistent CTA
     QnCtrl* ctrl = nullptr;               // device
     QnCtrl* h_ctrl = nullptr;             // pinned host mirror
     double *rel_trace = nullptr, *abs_trace = nullptr;
@@ -488,7 +489,7 @@ extern "C" int psi_solver_create(psi_solver_t** out, int64_t numel, int max_thre
     rc |= solver_alloc(s, (void**)&s->best, vb);
     rc |= solver_alloc(s, (void**)&s->fx, vb);
     rc |= solver_alloc(s, (void**)&s->partial, (size_t)3 * s->cap * s->dots_chunks * sizeof(float));
-    rc |= solver_alloc(s, (void**)&s->partial2, (size_t)2 * QN_AXPY_MAX_CTAS * sizeof(float));
+    rc |= solver_alloc(s, (void**)&s->partial2, (size_t)2 * QN_AXPY_MAX_CTAS * sizeof(double));
     rc |= solver_alloc(s, (void**)&s->coef, (size_t)3 * s->cap * sizeof(float));
     rc |= solver_alloc(s, (void**)&s->norm_part, (size_t)2 * s->norm_cap * sizeof(float));
     rc |= solver_alloc(s, (void**)&s->ctrl, sizeof(QnCtrl));

@@ -155,14 +155,14 @@ k_qn_dots_tma(QnHistory H, int nhist, const float* __restrict__ dx, const float*
 // Each CTA owns float4 range [q0, q1) of the vectors, split into equal tiles of ≤ AXPY_TILE floats.
 __global__ void __launch_bounds__(TMA_THREADS, 1)
 k_qn_axpy_tma(QnHistory H, int nhist, int n, const float* __restrict__ coef, int cap, float* __restrict__ dx_upd, float* __restrict__ dg_t,
-              const float* __restrict__ g, const float* __restrict__ x, float* __restrict__ best_x, float* __restrict__ partial2,
+              const float* __restrict__ g, const float* __restrict__ x, float* __restrict__ best_x, double* __restrict__ partial2,
               int64_t total4, const QnCtrl* __restrict__ ctrl) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* ring = reinterpret_cast<float*>(smem_raw);                                   // [STAGES][2][AXPY_TILE]
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)AXPY_STAGES * 2 * AXPY_TILE * sizeof(float));
     uint64_t* empty = full + AXPY_STAGES;
-    float* s_red = reinterpret_cast<float*>(empty + AXPY_STAGES);                       // [2][8]
-    float* s_coef = s_red + 16;                                                         // [3][nhist]
+    double* s_red = reinterpret_cast<double*>(empty + AXPY_STAGES);                     // [2][8]
+    float* s_coef = reinterpret_cast<float*>(s_red + 16);                               // [3][nhist]
     const int improved = ctrl->improved, done = ctrl->done;
     if (done && !improved) return;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -207,7 +207,9 @@ k_qn_axpy_tma(QnHistory H, int nhist, int n, const float* __restrict__ coef, int
     }
     float* vn_dst = hist_v(H, n - 1);
     float* un_dst = hist_u(H, n - 1);
-    float acc0 = 0.f, acc1 = 0.f;
+    // The two inner products of the step are accumulated in fp64: their fp32 roundings then do not depend on how the elements are
+    // split over CTAs — or over the ranks of a mesh partition, which is what lets a partitioned solve retrace the single-GPU one.
+    double acc0 = 0.0, acc1 = 0.0;
     uint32_t fill = 0;
     for (int t = 0; t < ntiles; ++t) {
         const int64_t t0 = q0 + (int64_t)t * tile4;
@@ -243,11 +245,11 @@ k_qn_axpy_tma(QnHistory H, int nhist, int n, const float* __restrict__ coef, int
                 const float4 vg = reinterpret_cast<const float4*>(g)[q];
                 // vT = −δx + Σ a_k V_k  (rmatvec, solver.py:104)
                 float4 vn = make_float4(-vdx.x + av[j].x, -vdx.y + av[j].y, -vdx.z + av[j].z, -vdx.w + av[j].w);
-                acc0 = dot4(vn, vdg, acc0);                                   // ⟨vT, δg⟩ uses the un-scrubbed vT (solver.py:187)
+                acc0 += (double)vn.x * vdg.x + (double)vn.y * vdg.y + (double)vn.z * vdg.z + (double)vn.w * vdg.w;   // ⟨vT, δg⟩, un-scrubbed vT (solver.py:187)
                 // vT[vT != vT] = 0  (solver.py:188)
                 vn.x = (vn.x != vn.x) ? 0.f : vn.x; vn.y = (vn.y != vn.y) ? 0.f : vn.y;
                 vn.z = (vn.z != vn.z) ? 0.f : vn.z; vn.w = (vn.w != vn.w) ? 0.f : vn.w;
-                acc1 = dot4(vn, vg, acc1);                                    // V[n-1]ᵀ g_n for the new update
+                acc1 += (double)vn.x * vg.x + (double)vn.y * vg.y + (double)vn.z * vg.z + (double)vn.w * vg.w;        // V[n-1]ᵀ g_n for the new update
                 // numerator of u:  δx − matvec(δg) = δx − (−δg + Σ c_k U_k)   (solver.py:114,187)
                 const float4 un = make_float4(vdx.x - (-vdg.x + aw[j].x), vdx.y - (-vdg.y + aw[j].y), vdx.z - (-vdg.z + aw[j].z),
                                               vdx.w - (-vdg.w + aw[j].w));
@@ -257,12 +259,12 @@ k_qn_axpy_tma(QnHistory H, int nhist, int n, const float* __restrict__ coef, int
             }
         }
     }
-    acc0 = warp_sum(acc0);
-    acc1 = warp_sum(acc1);
+    acc0 = warp_sum_d(acc0);
+    acc1 = warp_sum_d(acc1);
     if (lane == 0) { s_red[warp] = acc0; s_red[8 + warp] = acc1; }
     consumer_bar();
     if (tid == 0) {
-        float a = 0.f, b = 0.f;
+        double a = 0.0, b = 0.0;
 #pragma unroll
         for (int w = 0; w < 8; ++w) { a += s_red[w]; b += s_red[8 + w]; }
         partial2[blockIdx.x] = a;
@@ -271,4 +273,4 @@ k_qn_axpy_tma(QnHistory H, int nhist, int n, const float* __restrict__ coef, int
 }
 
 static inline size_t dots_tma_smem() { return (size_t)DOTS_STAGES * 2 * DOTS_CH * 4 + 2 * DOTS_STAGES * 8 + 2 * DOTS_KB * 3 * 8 * 4; }
-static inline size_t axpy_tma_smem(int nhist) { return (size_t)AXPY_STAGES * 2 * AXPY_TILE * 4 + 2 * AXPY_STAGES * 8 + 16 * 4 + (size_t)3 * (nhist > 0 ? nhist : 1) * 4; }
+static inline size_t axpy_tma_smem(int nhist) { return (size_t)AXPY_STAGES * 2 * AXPY_TILE * 4 + 2 * AXPY_STAGES * 8 + 16 * 8 + (size_t)3 * (nhist > 0 ? nhist : 1) * 4; }

@@ -46,11 +46,21 @@ class MeshPartition:
         self.comm = None                            # Communicator, set by attach()
 
 
+ALIGN_NODES = 2048      # lcm(4096-float reduction chunk, 10 floats per node, 128-node CTA) in nodes
+
+
 def _owner_of(data: GraphData, world: int):
     pos = data.pos.numpy()
     order = np.argsort(pos[:, 0], kind="stable")            # geometric ordering → contiguous ranges
     n = order.shape[0]
-    rank_of_sorted = np.minimum((np.arange(n, dtype=np.int64) * world) // max(n, 1), world - 1)
+    if n >= 2 * ALIGN_NODES * world:
+        # Cut at multiples of 2048 nodes: every rank's rows then start on a boundary of the 4096-float chunks (and 128-node blocks)
+        # the reductions of the solver are organised in, so its fp32 partial sums are the very ones the unpartitioned solve of the
+        # same (reordered) mesh forms — the partitioned solve retraces the single-GPU trajectory instead of a chaotic neighbour.
+        bounds = np.round(np.arange(1, world) * n / world / ALIGN_NODES).astype(np.int64) * ALIGN_NODES
+        rank_of_sorted = np.searchsorted(bounds, np.arange(n, dtype=np.int64), side="right")
+    else:
+        rank_of_sorted = np.minimum((np.arange(n, dtype=np.int64) * world) // max(n, 1), world - 1)
     owner = np.empty(n, np.int64)
     owner[order] = rank_of_sorted
     sorted_pos = np.empty(n, np.int64)
@@ -121,6 +131,11 @@ def partition_mesh(data: GraphData, world: int, rank: Optional[int] = None) -> L
         P.local = loc
         parts.append(P)
     return parts
+
+
+def reorder_mesh(data: GraphData) -> GraphData:
+    """the mesh in the partitioner's geometric node order (a 1-rank 'partition'): the single-GPU counterpart of a partitioned solve"""
+    return partition_mesh(data, 1)[0].local
 
 
 class Communicator:

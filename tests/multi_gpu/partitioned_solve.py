@@ -57,9 +57,14 @@ def main():
         for r in range(world):
             n = int(sizes[r])
             u_glob[idx[r][:n]] = us[r][:n]
-        full = mesh.to(dev)
-        u_ref = model.inference(full).reshape(-1)
+        # single-GPU counterpart on the same node order: with aligned cuts (N ≥ 2·2048·world) the reductions form the same partial sums
+        full = partition.reorder_mesh(mesh).to(dev)
+        order = torch.from_numpy(full.partition.owned_global).to(dev)
+        u_ref = torch.zeros(mesh.num_nodes, device=dev)
+        u_ref[order] = model.inference(full).reshape(-1)
         ref = model.deqdss.last_forward
+        m = min(out["steps_run"], ref["steps_run"])
+        dev_tr = np.abs(np.asarray(out["rel_trace"][:m]) - np.asarray(ref["rel_trace"][:m])) / np.asarray(ref["rel_trace"][:m])
         k = min(8, ref["steps_run"], out["steps_run"])
         tr = np.abs(np.asarray(out["rel_trace"][:k]) - np.asarray(ref["rel_trace"][:k])) / np.asarray(ref["rel_trace"][:k])
         err = float((u_glob - u_ref).norm() / u_ref.norm())
@@ -68,12 +73,16 @@ def main():
                   mesh.num_nodes, world, out["steps_run"], ref["steps_run"], out["lowest"], ref["lowest"],
                   k, float(tr.max()), err, part.n_ghost, out["stop_reason"], ref["stop_reason"], out["prot_break"], ref["prot_break"],
                   out["nstep"], ref["nstep"]))
-        m = min(out["steps_run"], ref["steps_run"])
-        dev_tr = np.abs(np.asarray(out["rel_trace"][:m]) - np.asarray(ref["rel_trace"][:m])) / np.asarray(ref["rel_trace"][:m])
         print("rel-trace deviation by step:", " ".join("%d:%.0e" % (i, dev_tr[i]) for i in range(0, m, max(1, m // 25))))
         print("ref rel trace:", " ".join("%.1e" % v for v in ref["rel_trace"][:m:max(1, m // 25)]))
         eps = float(g["cfg.fw_tol"])
         ok = float(tr.max()) < 1e-3
+        if mesh.num_nodes >= 2 * partition.ALIGN_NODES * world:
+            # aligned partition: the partitioned solve must retrace the single-GPU solve step for step
+            same = out["steps_run"] == ref["steps_run"] and out["nstep"] == ref["nstep"]
+            mdev = float(dev_tr.max()) if m > 0 else 0.0
+            print("aligned partition: identical step counts %s, max rel-trace deviation over all %d steps %.1e, u rel diff %.1e" % (same, m, mdev, err))
+            ok = ok and same and mdev < 1e-6 and err < 1e-5
         if out["lowest"] < eps and ref["lowest"] < eps:      # both converged: same fixed point, similar step counts
             ok = ok and err < 2e-2 and abs(out["nstep"] - ref["nstep"]) <= max(5, 0.5 * ref["nstep"])   # chaotic trajectories
         else:                                                  # step cap hit on a large mesh: comparable best residuals
