@@ -317,6 +317,11 @@ def run_native_inference(args, rank, local, world, dev):
         part = partition.partition_mesh(mesh, world, rank=rank)[0]
         host = part.local.pin_memory()
         n_owned, n_ghost = part.n_owned, part.n_ghost
+    elif one_mesh:
+        # the same geometric node order the partitioner uses: with its 2048-node-aligned cuts the N-GPU solve then retraces this one step
+        # for step (identical reductions), so the step count — and the work — is the same at every GPU count
+        host = partition.reorder_mesh(mesh).pin_memory()
+        n_owned, n_ghost = mesh.num_nodes, 0
     else:
         host = mesh.pin_memory()
         n_owned, n_ghost = mesh.num_nodes, 0
