@@ -131,11 +131,11 @@ int64_t psi_solver_bytes(const psi_solver_t* s);
  * xest_trace buffer passed to the Broyden entry points uses this stride */
 int64_t psi_solver_stride(const psi_solver_t* s);
 /* Optional per-kernel-class timing of the solver loops with CUDA events on the launching stream (used by bench.py for the
- * roofline).  Classes: 0 operator kernel(s) (fused layer, or the VJP pair), 1 k_qn_dots, 2 k_qn_axpy, 3 k_qn_fin2.
+ * roofline).  Classes: 0 operator kernel(s) (fused layer, or the VJP pair), 1 k_qn_dots_tma, 2 k_qn_axpy_tma.
  * psi_solver_profile(s, 1) enables and resets the totals; psi_solver_profile_read fills, per class,
  * {launches, total ms, total algorithmic bytes}. */
 int psi_solver_profile(psi_solver_t* s, int enable);
-int psi_solver_profile_read(const psi_solver_t* s, double out[12]);
+int psi_solver_profile_read(const psi_solver_t* s, double out[9]);
 
 /* operator selector for the fused native loops */
 #define PSI_OP_LAYER 0   /* x -> f(x; h0, graph)                 (forward solve,  model.py:189-193) */

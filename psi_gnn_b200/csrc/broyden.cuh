@@ -6,8 +6,8 @@
 // Per step n (after the operator kernel produced g_n, δg and the norm partials):
 //   pass 1  k_qn_dots_tma : a = U[:n-1]ᵀδx, c = V[:n-1]ᵀδg, e = V[:n-1]ᵀg_n      reads U,V once   (solver.py:103,113)
 //           k_qn_fin1 : reduce partials; ‖g‖, rel; best/trace/stop rules on the device  (solver.py:162-183)
-//   pass 2  k_qn_axpy_tma : v_n = −δx + V·a ; w = U·c ; t = U·e ; ⟨v_n,δg⟩, ⟨v_n,g_n⟩     reads U,V once   (solver.py:186-192)
-//           k_qn_fin2 : u_n = (δx − (−δg + w))/⟨v_n,δg⟩ ; update = −(−g_n + t + u_n⟨v_n,g_n⟩) ; x ← x + update
+//   pass 2  k_qn_axpy_tma : v_n = −δx + V·a ; w = U·c ; t = U·e ; u_n = (δx − (−δg + w))/s ; update = −(−g_n + t + u_n·p) ; x ← x + update
+//           with s = ⟨v_n,δg⟩ = −⟨δx,δg⟩ + Σ a_k c_k and p = ⟨v_n,g_n⟩ = −⟨δx,g_n⟩ + Σ a_k e_k from pass 1 by linearity (fp64)   reads U,V once
 // = 4(n−1) history vectors of traffic per step (the reference's op order costs 6n−4) while still forming
 // the reference's u_n, v_n, update_n from fresh dot products (no cached Vᵀg — that drifts).
 // No host synchronisation inside the loop: the stop decision lives in a device control block and every
@@ -116,18 +116,22 @@ __device__ __forceinline__ void qn_decide(int lane, double n1, double n2, QnCtrl
 // evaluates the reference's stopping logic (solver.py:160-183) in double precision.
 __global__ void __launch_bounds__(256)
 k_qn_fin1(int nhist, const float* __restrict__ partial, int num_chunks, float* __restrict__ coef /* [3][cap] */, int cap,
-          const float* __restrict__ norm_part, int norm_blocks, QnCtrl* __restrict__ ctrl, double* __restrict__ rel_trace,
-          double* __restrict__ abs_trace, int step, double eps, double protect, int threshold) {
+          double* __restrict__ dbuf /* [3·nhist + 2] fp64 row sums for pass 2 */, const float* __restrict__ norm_part, int norm_blocks,
+          QnCtrl* __restrict__ ctrl, double* __restrict__ rel_trace, double* __restrict__ abs_trace, int step, double eps, double protect,
+          int threshold) {
     if (ctrl->done) return;
     const int lane = threadIdx.x & 31;
     const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
-    for (int row = gwarp; row < nhist * 3; row += nwarps) {
+    for (int row = gwarp; row < nhist * 3 + 2; row += nwarps) {       // the last two rows are ⟨δx,δg⟩ and ⟨δx,g⟩
         const float* p = partial + (int64_t)row * num_chunks;
         double s = 0.0;
         for (int i = lane; i < num_chunks; i += 32) s += (double)p[i];
         s = warp_sum_d(s);
-        if (lane == 0) coef[(row % 3) * cap + row / 3] = (float)s;
+        if (lane == 0) {
+            dbuf[row] = s;
+            if (row < nhist * 3) coef[(row % 3) * cap + row / 3] = (float)s;
+        }
     }
     if (blockIdx.x == 0 && threadIdx.x < 32) {
         double n1 = 0.0, n2 = 0.0;
@@ -142,7 +146,7 @@ k_qn_fin1(int nhist, const float* __restrict__ partial, int num_chunks, float* _
 }
 
 // ---- mesh-partitioned variant: local sums → (NCCL all-reduce of the fp64 buffer) → coefficients + stop rules -------------
-// dbuf[row] = Σ_chunks partial[row], row = k*3+q ; dbuf[3·nhist] = Σ‖g‖² partials ; dbuf[3·nhist+1] = Σ‖f‖² partials
+// dbuf[row] = Σ_chunks partial[row], row = k*3+q, then ⟨δx,δg⟩, ⟨δx,g⟩ ; dbuf[3·nhist+2] = Σ‖g‖² partials ; dbuf[3·nhist+3] = Σ‖f‖² partials
 __global__ void __launch_bounds__(256)
 k_qn_fin1_local(int nhist, const float* __restrict__ partial, int num_chunks, double* __restrict__ dbuf, const float* __restrict__ norm_part,
                 int norm_blocks, const QnCtrl* __restrict__ ctrl) {
@@ -150,7 +154,7 @@ k_qn_fin1_local(int nhist, const float* __restrict__ partial, int num_chunks, do
     const int lane = threadIdx.x & 31;
     const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
-    for (int row = gwarp; row < nhist * 3; row += nwarps) {
+    for (int row = gwarp; row < nhist * 3 + 2; row += nwarps) {
         const float* p = partial + (int64_t)row * num_chunks;
         double s = 0.0;
         for (int i = lane; i < num_chunks; i += 32) s += (double)p[i];
@@ -165,7 +169,7 @@ k_qn_fin1_local(int nhist, const float* __restrict__ partial, int num_chunks, do
         }
         n1 = warp_sum_d(n1);
         n2 = warp_sum_d(n2);
-        if (lane == 0) { dbuf[3 * nhist] = n1; dbuf[3 * nhist + 1] = n2; }
+        if (lane == 0) { dbuf[3 * nhist + 2] = n1; dbuf[3 * nhist + 3] = n2; }
     }
 }
 
@@ -173,79 +177,8 @@ __global__ void __launch_bounds__(256)
 k_qn_fin1_global(int nhist, const double* __restrict__ dbuf, float* __restrict__ coef, int cap, QnCtrl* __restrict__ ctrl,
                  double* __restrict__ rel_trace, double* __restrict__ abs_trace, int step, double eps, double protect, int threshold) {
     if (ctrl->done) return;
-    __shared__ int was_done;
     for (int row = threadIdx.x; row < nhist * 3; row += blockDim.x) coef[(row % 3) * cap + row / 3] = (float)dbuf[row];
-    if (threadIdx.x < 32) qn_decide(threadIdx.x, dbuf[3 * nhist], dbuf[3 * nhist + 1], ctrl, rel_trace, abs_trace, step, eps, protect, threshold);
-    (void)was_done;
-}
-
-// Σ of the pass-2 partials → sp[0] = ⟨v_n,δg⟩, sp[1] = ⟨v_n,g_n⟩ (local part, all-reduced before k_qn_fin2)
-__global__ void __launch_bounds__(256) k_qn_red2(const double* __restrict__ partial2, int p2_ctas, double* __restrict__ sp, const QnCtrl* __restrict__ ctrl) {
-    __shared__ double sm[16];
-    if (ctrl->done) return;
-    double a = 0.0, b = 0.0;
-    for (int i = threadIdx.x; i < p2_ctas; i += 256) { a += partial2[i]; b += partial2[p2_ctas + i]; }
-    a = warp_sum_d(a); b = warp_sum_d(b);
-    if ((threadIdx.x & 31) == 0) { sm[threadIdx.x >> 5] = a; sm[8 + (threadIdx.x >> 5)] = b; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double sa = 0.0, sb = 0.0;
-        for (int w = 0; w < 8; ++w) { sa += sm[w]; sb += sm[8 + w]; }
-        sp[0] = sa; sp[1] = sb;
-    }
-}
-
-// ---- finalize 2: normalise u_n, form the new update, advance x ---------------------------------------------
-__global__ void __launch_bounds__(QN_THREADS)
-k_qn_fin2(QnHistory H, int n, float* __restrict__ dx_upd /* in: t, out: δx of the next step */, const float* __restrict__ g,
-          float* __restrict__ x, const double* __restrict__ partial2, int p2_ctas, float* __restrict__ xtrace_next,
-          QnCtrl* __restrict__ ctrl, int num_chunks, const double* __restrict__ sp_global) {
-    __shared__ double sm[2 * (QN_THREADS / 32)];
-    __shared__ float s_sp[2];
-    if (ctrl->done) return;
-    if (sp_global != nullptr) {   // mesh-partitioned solve: the sums were all-reduced over the ranks
-        if (threadIdx.x == 0) {
-            s_sp[0] = (float)sp_global[0]; s_sp[1] = (float)sp_global[1];
-            if (blockIdx.x == 0) { ctrl->s = sp_global[0]; ctrl->p = sp_global[1]; }
-        }
-        __syncthreads();
-    } else {   // every CTA reduces the pass-2 partials in the same fixed order → identical s, p everywhere
-        double a = 0.0, b = 0.0;
-        for (int i = threadIdx.x; i < p2_ctas; i += QN_THREADS) { a += partial2[i]; b += partial2[p2_ctas + i]; }
-        a = warp_sum_d(a); b = warp_sum_d(b);
-        if ((threadIdx.x & 31) == 0) { sm[threadIdx.x >> 5] = a; sm[QN_THREADS / 32 + (threadIdx.x >> 5)] = b; }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            double sa = 0.0, sb = 0.0;
-            for (int w = 0; w < QN_THREADS / 32; ++w) { sa += sm[w]; sb += sm[QN_THREADS / 32 + w]; }
-            s_sp[0] = (float)sa; s_sp[1] = (float)sb;
-            if (blockIdx.x == 0) { ctrl->s = sa; ctrl->p = sb; }
-        }
-        __syncthreads();
-    }
-    const float s = s_sp[0], p = s_sp[1];
-    float* un_dst = hist_u(H, n - 1);
-    for (int chunk = blockIdx.x; chunk < num_chunks; chunk += gridDim.x) {
-        const int64_t e0 = (int64_t)chunk * QN_CHUNK + threadIdx.x * 4;
-        float4 u = *reinterpret_cast<const float4*>(un_dst + e0);
-        const float4 t = *reinterpret_cast<const float4*>(dx_upd + e0);
-        const float4 vg = *reinterpret_cast<const float4*>(g + e0);
-        float4 xv = *reinterpret_cast<const float4*>(x + e0);
-        // u = numerator / ⟨vT,δg⟩ ; u[u != u] = 0   (solver.py:187,189)
-        u.x = __fdiv_rn(u.x, s); u.y = __fdiv_rn(u.y, s); u.z = __fdiv_rn(u.z, s); u.w = __fdiv_rn(u.w, s);
-        u.x = (u.x != u.x) ? 0.f : u.x; u.y = (u.y != u.y) ? 0.f : u.y; u.z = (u.z != u.z) ? 0.f : u.z; u.w = (u.w != u.w) ? 0.f : u.w;
-        // update = −matvec(U[:n], V[:n], g) = −(−g + Σ_{k<n} U_k (V_kᵀ g))   (solver.py:192)
-        float4 upd;
-        upd.x = -(-vg.x + fmaf(u.x, p, t.x)); upd.y = -(-vg.y + fmaf(u.y, p, t.y));
-        upd.z = -(-vg.z + fmaf(u.z, p, t.z)); upd.w = -(-vg.w + fmaf(u.w, p, t.w));
-        // line_search with s = 1: x_est = x0 + update ; delta_x = x_est − x0   (solver.py:89,94)
-        float4 xn = make_float4(xv.x + upd.x, xv.y + upd.y, xv.z + upd.z, xv.w + upd.w);
-        float4 dxn = make_float4(xn.x - xv.x, xn.y - xv.y, xn.z - xv.z, xn.w - xv.w);
-        *reinterpret_cast<float4*>(un_dst + e0) = u;
-        *reinterpret_cast<float4*>(dx_upd + e0) = dxn;
-        *reinterpret_cast<float4*>(x + e0) = xn;
-        if (xtrace_next != nullptr) *reinterpret_cast<float4*>(xtrace_next + e0) = xn;
-    }
+    if (threadIdx.x < 32) qn_decide(threadIdx.x, dbuf[3 * nhist + 2], dbuf[3 * nhist + 3], ctrl, rel_trace, abs_trace, step, eps, protect, threshold);
 }
 
 // ---- start of a solve: update_0 = g_0 ; x_1 = x_0 + update_0 ------------------------------------------------

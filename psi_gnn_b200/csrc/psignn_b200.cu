@@ -387,7 +387,7 @@ extern "C" int psi_decode(int64_t num_nodes, const float* dev_h, float* dev_u, v
 // ================================================================================================
 // solver workspace
 // ================================================================================================
-#define PROF_CLASSES 4   // 0 operator (layer / VJP pair), 1 k_qn_dots, 2 k_qn_axpy, 3 k_qn_fin2
+#define PROF_CLASSES 3   // 0 operator (layer / VJP pair), 1 k_qn_dots_tma, 2 k_qn_axpy_tma
 
 struct psi_solver {
     int64_t numel = 0, stride = 0;        // stride = numel rounded up to whole QN_CHUNKs (tail kept at zero)
@@ -396,7 +396,6 @@ struct psi_solver {
     int dots_chunks = 0, tma_ctas = 0;    // 2048-element chunks of pass 1; persistent CTAs (one per SM) of the TMA kernels
     float *x = nullptr, *g = nullptr, *dg = nullptr, *dx = nullptr, *best = nullptr, *fx = nullptr;
     float *partial = nullptr, *coef = nullptr, *norm_part = nullptr;
-    double* partial2 = nullptr;           // fp64 partial sums of ⟨v_n,δg⟩ and ⟨v_n,g_n⟩ per persistent CTA
     QnCtrl* ctrl = nullptr;               // device
     QnCtrl* h_ctrl = nullptr;             // pinned host mirror
     double *rel_trace = nullptr, *abs_trace = nullptr;
@@ -416,8 +415,8 @@ struct psi_solver {
     int profile = 0;
     std::vector<cudaEvent_t> ev;          // [((step * PROF_CLASSES) + cls) * 2 + {begin,end}]
     std::vector<double> ev_bytes;         // algorithmic bytes of the launch(es) bracketed by the pair
-    double prof_ms[PROF_CLASSES] = {0, 0, 0, 0}, prof_bytes[PROF_CLASSES] = {0, 0, 0, 0};
-    int64_t prof_launches[PROF_CLASSES] = {0, 0, 0, 0};
+    double prof_ms[PROF_CLASSES] = {0, 0, 0}, prof_bytes[PROF_CLASSES] = {0, 0, 0};
+    int64_t prof_launches[PROF_CLASSES] = {0, 0, 0};
     double op_bytes = 0.0;                // algorithmic bytes of one operator evaluation of the current solve
 };
 
@@ -488,8 +487,7 @@ extern "C" int psi_solver_create(psi_solver_t** out, int64_t numel, int max_thre
     rc |= solver_alloc(s, (void**)&s->dx, vb);
     rc |= solver_alloc(s, (void**)&s->best, vb);
     rc |= solver_alloc(s, (void**)&s->fx, vb);
-    rc |= solver_alloc(s, (void**)&s->partial, (size_t)3 * s->cap * s->dots_chunks * sizeof(float));
-    rc |= solver_alloc(s, (void**)&s->partial2, (size_t)2 * QN_AXPY_MAX_CTAS * sizeof(double));
+    rc |= solver_alloc(s, (void**)&s->partial, (size_t)(3 * s->cap + 2) * s->dots_chunks * sizeof(float));
     rc |= solver_alloc(s, (void**)&s->coef, (size_t)3 * s->cap * sizeof(float));
     rc |= solver_alloc(s, (void**)&s->norm_part, (size_t)2 * s->norm_cap * sizeof(float));
     rc |= solver_alloc(s, (void**)&s->ctrl, sizeof(QnCtrl));
@@ -513,7 +511,7 @@ extern "C" int psi_solver_create(psi_solver_t** out, int64_t numel, int max_thre
 
 extern "C" int psi_solver_destroy(psi_solver_t* s) {
     if (s == nullptr) return 0;
-    void* ps[] = {s->x, s->g, s->dg, s->dx, s->best, s->fx, s->partial, s->partial2, s->coef, s->norm_part, s->ctrl,
+    void* ps[] = {s->x, s->g, s->dg, s->dx, s->best, s->fx, s->partial, s->coef, s->norm_part, s->ctrl,
                   s->rel_trace, s->abs_trace, s->and_X, s->and_F, s->and_small, s->dbuf};
     for (void* p : ps)
         if (p) cudaFree(p);
@@ -544,7 +542,7 @@ extern "C" int psi_solver_profile(psi_solver_t* s, int enable) {
     return 0;
 }
 
-extern "C" int psi_solver_profile_read(const psi_solver_t* s, double out[12]) {
+extern "C" int psi_solver_profile_read(const psi_solver_t* s, double out[9]) {
     if (s == nullptr || out == nullptr) PSI_FAIL("psi_solver_profile_read: null argument");
     for (int c = 0; c < PROF_CLASSES; ++c) { out[3 * c] = (double)s->prof_launches[c]; out[3 * c + 1] = s->prof_ms[c]; out[3 * c + 2] = s->prof_bytes[c]; }
     return 0;
@@ -617,48 +615,35 @@ static int qn_first(psi_solver* s, cudaStream_t st) {
 static int qn_update(psi_solver* s, int n, int norm_blocks, cudaStream_t st) {
     const int nhist = n - 1;
     if (hist_ensure(s, n - 1)) return -1;
-    if (nhist > 0) {
-        const double vec = (double)s->act_numel * 4.0;
-        prof_begin(s, n, 1, (2.0 * nhist + 3.0) * vec, st);
-        k_qn_dots_tma<<<s->tma_ctas, TMA_THREADS, dots_tma_smem(), st>>>(s->hist, nhist, s->dx, s->dg, s->g, s->partial, s->act_dchunks,
-                                                                         &s->ctrl->done);
-        prof_end(s, n, 1, st);
-        PSI_CK_LAUNCH();
-        s->launches += 1;
-    }
-    const int fin_blocks = std::max(1, std::min(2 * s->tma_ctas, (nhist * 3 + 7) / 8));   // one warp per row of the partial matrix
+    const double vec = (double)s->act_numel * 4.0;
+    // pass 1 (also at nhist = 0: it carries ⟨δx,δg⟩ and ⟨δx,g⟩, from which s and p of this step follow)
+    prof_begin(s, n, 1, (2.0 * nhist + 3.0) * vec, st);
+    k_qn_dots_tma<<<s->tma_ctas, TMA_THREADS, dots_tma_smem(), st>>>(s->hist, nhist, s->dx, s->dg, s->g, s->partial, s->act_dchunks,
+                                                                     &s->ctrl->done);
+    prof_end(s, n, 1, st);
+    PSI_CK_LAUNCH();
+    const int fin_blocks = std::max(1, std::min(2 * s->tma_ctas, (nhist * 3 + 2 + 7) / 8));   // one warp per row of the partial matrix
     if (s->comm == nullptr) {
-        k_qn_fin1<<<fin_blocks, 256, 0, st>>>(nhist, s->partial, s->act_dchunks, s->coef, s->cap, s->norm_part, norm_blocks, s->ctrl,
+        k_qn_fin1<<<fin_blocks, 256, 0, st>>>(nhist, s->partial, s->act_dchunks, s->coef, s->cap, s->dbuf, s->norm_part, norm_blocks, s->ctrl,
                                               s->rel_trace, s->abs_trace, n, s->eps, 1e3 * PSI_D, s->threshold);
         PSI_CK_LAUNCH();
     } else {
-        // mesh-partitioned: local fp64 sums → one all-reduce of 3(n−1)+2 doubles → coefficients and stop rules (identical on every rank)
+        // mesh-partitioned: local fp64 sums → ONE all-reduce of 3(n−1)+4 doubles per step → coefficients and stop rules (identical on every rank)
         k_qn_fin1_local<<<fin_blocks, 256, 0, st>>>(nhist, s->partial, s->act_dchunks, s->dbuf, s->norm_part, norm_blocks, s->ctrl);
         PSI_CK_LAUNCH();
-        if (allreduce_f64(s->comm, s->dbuf, (size_t)3 * nhist + 2, st)) return -1;
+        if (allreduce_f64(s->comm, s->dbuf, (size_t)3 * nhist + 4, st)) return -1;
         k_qn_fin1_global<<<1, 256, 0, st>>>(nhist, s->dbuf, s->coef, s->cap, s->ctrl, s->rel_trace, s->abs_trace, n, s->eps, 1e3 * PSI_D,
                                             s->threshold);
         PSI_CK_LAUNCH();
         s->launches += 1;
     }
-    prof_begin(s, n, 2, (2.0 * nhist + 6.0) * (double)s->act_numel * 4.0, st);
-    k_qn_axpy_tma<<<s->tma_ctas, TMA_THREADS, axpy_tma_smem(nhist), st>>>(s->hist, nhist, n, s->coef, s->cap, s->dx, s->dg, s->g, s->x, s->best,
-                                                                         s->partial2, (s->act_numel + 3) / 4, s->ctrl);
-    prof_end(s, n, 2, st);
-    PSI_CK_LAUNCH();
     float* xt = s->xtrace ? s->xtrace + (int64_t)(n + 1) * s->stride : nullptr;
     if (n >= s->threshold) xt = nullptr;
-    double* sp = nullptr;
-    if (s->comm != nullptr) {
-        sp = s->dbuf + 3 * s->cap + 4;
-        k_qn_red2<<<1, 256, 0, st>>>(s->partial2, s->tma_ctas, sp, s->ctrl);
-        PSI_CK_LAUNCH();
-        if (allreduce_f64(s->comm, sp, 2, st)) return -1;
-        s->launches += 1;
-    }
-    prof_begin(s, n, 3, 7.0 * (double)s->act_numel * 4.0, st);
-    k_qn_fin2<<<s->axpy_ctas, QN_THREADS, 0, st>>>(s->hist, n, s->dx, s->g, s->x, s->partial2, s->tma_ctas, xt, s->ctrl, s->act_chunks, sp);
-    prof_end(s, n, 3, st);
+    // pass 2: rank-one update, new update direction and the step itself (history read once, 4 vectors read + 4 written besides)
+    prof_begin(s, n, 2, (2.0 * nhist + 8.0) * vec, st);
+    k_qn_axpy_tma<<<s->tma_ctas, TMA_THREADS, axpy_tma_smem(nhist), st>>>(s->hist, nhist, n, s->coef, s->cap, s->dbuf, s->dx, s->dg, s->g, s->x,
+                                                                         s->best, xt, (s->act_numel + 3) / 4, s->ctrl);
+    prof_end(s, n, 2, st);
     PSI_CK_LAUNCH();
     s->launches += 3;
     return 0;

@@ -5,7 +5,8 @@
 // pressure: one persistent CTA per SM, a producer warp issuing 1-D bulk copies (cp.async.bulk → UBLKCP) of U_k / V_k tiles
 // into a shared-memory ring, full/empty mbarriers per stage, eight consumer warps doing the FMAs out of shared memory.
 //   pass 1  k_qn_dots_tma : a = Uᵀδx, c = Vᵀδg, e = Vᵀg        work item = (4096-element chunk, range of 32 history vectors)
-//   pass 2  k_qn_axpy_tma : v = −δx + V·a, w = U·c, t = U·e      each CTA owns an equal contiguous element range (±16 B)
+//   pass 2  k_qn_axpy_tma : v = −δx + V·a, w = U·c, t = U·e, then u_n, the new update and x ← x + update in the same sweep;
+//                           each CTA owns an equal contiguous element range (±16 B)
 // Summation orders are fixed (xor-shuffle tree, then warps in order, then chunks in order): results are deterministic.
 #pragma once
 #include "common.cuh"
@@ -65,6 +66,7 @@ k_qn_dots_tma(QnHistory H, int nhist, const float* __restrict__ dx, const float*
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)DOTS_STAGES * 2 * DOTS_CH * sizeof(float));
     uint64_t* empty = full + DOTS_STAGES;
     float* red = reinterpret_cast<float*>(empty + DOTS_STAGES);                         // [2][DOTS_KB][3][8]
+    float* red_x = red + 2 * DOTS_KB * 3 * 8;                                           // [2][2][8]: ⟨δx,δg⟩, ⟨δx,g⟩ of a chunk
     if (*done) return;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
@@ -72,7 +74,7 @@ k_qn_dots_tma(QnHistory H, int nhist, const float* __restrict__ dx, const float*
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    const int kranges = (nhist + DOTS_KR - 1) / DOTS_KR;
+    const int kranges = max(1, (nhist + DOTS_KR - 1) / DOTS_KR);       // at least one item per chunk: it also carries ⟨δx,δg⟩, ⟨δx,g⟩
     const int items = num_chunks * kranges;
     if (warp == TMA_CONSUMERS / 32) {
         // ---- producer ----
@@ -96,7 +98,7 @@ k_qn_dots_tma(QnHistory H, int nhist, const float* __restrict__ dx, const float*
     }
     // ---- consumers ----
     uint32_t fill = 0;
-    int buf = 0;
+    int buf = 0, xbuf = 0;
     for (int item = blockIdx.x; item < items; item += gridDim.x) {
         const int c = item % num_chunks, r = item / num_chunks;
         const int k0 = r * DOTS_KR, k1 = min(nhist, k0 + DOTS_KR);
@@ -111,6 +113,24 @@ k_qn_dots_tma(QnHistory H, int nhist, const float* __restrict__ dx, const float*
             rdx[j] = __ldg(pdx + tid + j * TMA_CONSUMERS);
             rdg[j] = __ldg(pdg + tid + j * TMA_CONSUMERS);
             rg[j] = __ldg(pg + tid + j * TMA_CONSUMERS);
+        }
+        if (r == 0) {
+            // rows 3·nhist and 3·nhist+1: ⟨δx,δg⟩ and ⟨δx,g_n⟩.  With them s = ⟨v_n,δg⟩ and p = ⟨v_n,g_n⟩ follow from this pass by
+            // linearity (v_n = −δx + Σ a_k V_k ⇒ s = −⟨δx,δg⟩ + Σ a_k c_k, p = −⟨δx,g⟩ + Σ a_k e_k): pass 2 needs no reduction of its own.
+            float d1 = 0.f, d2 = 0.f;
+#pragma unroll
+            for (int j = 0; j < R; ++j) { d1 = dot4(rdx[j], rdg[j], d1); d2 = dot4(rdx[j], rg[j], d2); }
+            d1 = warp_sum(d1); d2 = warp_sum(d2);
+            if (lane == 0) { red_x[(xbuf * 2 + 0) * 8 + warp] = d1; red_x[(xbuf * 2 + 1) * 8 + warp] = d2; }
+            consumer_bar();
+            if (tid < 2) {
+                const float* rp = red_x + (xbuf * 2 + tid) * 8;
+                float sum = 0.f;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) sum += rp[w];
+                partial[((int64_t)3 * nhist + tid) * num_chunks + c] = sum;
+            }
+            xbuf ^= 1;
         }
         for (int kb0 = k0; kb0 < k1; kb0 += DOTS_KB) {
             const int nb = min(DOTS_KB, k1 - kb0);
@@ -152,17 +172,19 @@ k_qn_dots_tma(QnHistory H, int nhist, const float* __restrict__ dx, const float*
 }
 
 // ---- pass 2 ---------------------------------------------------------------------------------------------------------
-// Each CTA owns float4 range [q0, q1) of the vectors, split into equal tiles of ≤ AXPY_TILE floats.
+// v_n = −δx + V·a ; w = −δg + U·c ; t = U·e ; u_n = (δx − w)/s ; update = g_n − t − u_n·p ; x ← x + update ; δx ← x_new − x.
+// s = ⟨v_n,δg⟩ and p = ⟨v_n,g_n⟩ come from the fp64 row sums of pass 1 (dbuf), so the whole rank-one update and the step are one
+// sweep with no trailing reduction.  Each CTA owns float4 range [q0, q1) of the vectors, split into equal tiles of ≤ AXPY_TILE floats.
 __global__ void __launch_bounds__(TMA_THREADS, 1)
-k_qn_axpy_tma(QnHistory H, int nhist, int n, const float* __restrict__ coef, int cap, float* __restrict__ dx_upd, float* __restrict__ dg_t,
-              const float* __restrict__ g, const float* __restrict__ x, float* __restrict__ best_x, double* __restrict__ partial2,
-              int64_t total4, const QnCtrl* __restrict__ ctrl) {
+k_qn_axpy_tma(QnHistory H, int nhist, int n, const float* __restrict__ coef, int cap, const double* __restrict__ dbuf, float* __restrict__ dx_io,
+              const float* __restrict__ dg, const float* __restrict__ g, float* __restrict__ x, float* __restrict__ best_x,
+              float* __restrict__ xtrace_next, int64_t total4, QnCtrl* __restrict__ ctrl) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* ring = reinterpret_cast<float*>(smem_raw);                                   // [STAGES][2][AXPY_TILE]
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)AXPY_STAGES * 2 * AXPY_TILE * sizeof(float));
     uint64_t* empty = full + AXPY_STAGES;
-    double* s_red = reinterpret_cast<double*>(empty + AXPY_STAGES);                     // [2][8]
-    float* s_coef = reinterpret_cast<float*>(s_red + 16);                               // [3][nhist]
+    double* s_red = reinterpret_cast<double*>(empty + AXPY_STAGES);                     // [2][9]
+    float* s_coef = reinterpret_cast<float*>(s_red + 18);                               // [3][nhist]
     const int improved = ctrl->improved, done = ctrl->done;
     if (done && !improved) return;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -182,7 +204,23 @@ k_qn_axpy_tma(QnHistory H, int nhist, int n, const float* __restrict__ coef, int
         s_coef[nhist + i] = coef[cap + i];
         s_coef[2 * nhist + i] = coef[2 * cap + i];
     }
+    {   // s = −⟨δx,δg⟩ + Σ_k a_k c_k ,  p = −⟨δx,g⟩ + Σ_k a_k e_k  in fp64, identical order in every CTA (and on every rank)
+        double ps = 0.0, pp = 0.0;
+        for (int k = tid; k < nhist; k += TMA_THREADS) {
+            const double ak = dbuf[3 * k];
+            ps = fma(ak, dbuf[3 * k + 1], ps);
+            pp = fma(ak, dbuf[3 * k + 2], pp);
+        }
+        ps = warp_sum_d(ps);
+        pp = warp_sum_d(pp);
+        if (lane == 0) { s_red[warp] = ps; s_red[9 + warp] = pp; }
+    }
     __syncthreads();
+    double sd = -dbuf[3 * nhist], pd = -dbuf[3 * nhist + 1];
+#pragma unroll
+    for (int w = 0; w < TMA_THREADS / 32; ++w) { sd += s_red[w]; pd += s_red[9 + w]; }
+    const float s = (float)sd, p = (float)pd;            // torch.einsum(...) / matvec produce fp32 scalars (solver.py:187,192)
+    if (blockIdx.x == 0 && tid == 0) { ctrl->s = sd; ctrl->p = pd; }
     const int64_t len4 = q1 - q0;
     const int ntiles = (int)((len4 * 4 + AXPY_TILE - 1) / AXPY_TILE);
     const int tile4 = ntiles > 0 ? (int)((len4 + ntiles - 1) / ntiles) : 0;            // ≤ AXPY_TILE/4 float4 per tile
@@ -194,12 +232,12 @@ k_qn_axpy_tma(QnHistory H, int nhist, int n, const float* __restrict__ coef, int
                 const uint32_t bytes = (uint32_t)(min((int64_t)tile4, q1 - t0) * 16);
                 for (int k = nhist - 1; k >= 0; --k, ++fill) {   // descending: pass 1 just streamed the newest vectors last, the
                                                                  // tail of the history is what the 126 MB L2 still holds
-                    const uint32_t s = fill % AXPY_STAGES, use = fill / AXPY_STAGES;
-                    if (use > 0) mbar_wait(&empty[s], (use - 1) & 1);
-                    mbar_expect_tx(&full[s], 2 * bytes);
-                    float* dst = ring + (size_t)s * 2 * AXPY_TILE;
-                    bulk_g2s(dst, hist_u(H, k) + t0 * 4, bytes, &full[s]);
-                    bulk_g2s(dst + AXPY_TILE, hist_v(H, k) + t0 * 4, bytes, &full[s]);
+                    const uint32_t st = fill % AXPY_STAGES, use = fill / AXPY_STAGES;
+                    if (use > 0) mbar_wait(&empty[st], (use - 1) & 1);
+                    mbar_expect_tx(&full[st], 2 * bytes);
+                    float* dst = ring + (size_t)st * 2 * AXPY_TILE;
+                    bulk_g2s(dst, hist_u(H, k) + t0 * 4, bytes, &full[st]);
+                    bulk_g2s(dst + AXPY_TILE, hist_v(H, k) + t0 * 4, bytes, &full[st]);
                 }
             }
         }
@@ -207,9 +245,6 @@ k_qn_axpy_tma(QnHistory H, int nhist, int n, const float* __restrict__ coef, int
     }
     float* vn_dst = hist_v(H, n - 1);
     float* un_dst = hist_u(H, n - 1);
-    // The two inner products of the step are accumulated in fp64: their fp32 roundings then do not depend on how the elements are
-    // split over CTAs — or over the ranks of a mesh partition, which is what lets a partitioned solve retrace the single-GPU one.
-    double acc0 = 0.0, acc1 = 0.0;
     uint32_t fill = 0;
     for (int t = 0; t < ntiles; ++t) {
         const int64_t t0 = q0 + (int64_t)t * tile4;
@@ -219,16 +254,16 @@ k_qn_axpy_tma(QnHistory H, int nhist, int n, const float* __restrict__ coef, int
 #pragma unroll
         for (int j = 0; j < 2; ++j) { av[j] = make_float4(0.f, 0.f, 0.f, 0.f); aw[j] = av[j]; at[j] = av[j]; }
         for (int k = nhist - 1; k >= 0; --k, ++fill) {
-            const uint32_t s = fill % AXPY_STAGES, use = fill / AXPY_STAGES;
-            mbar_wait(&full[s], use & 1);
-            const float4* su = reinterpret_cast<const float4*>(ring + (size_t)s * 2 * AXPY_TILE);
+            const uint32_t st = fill % AXPY_STAGES, use = fill / AXPY_STAGES;
+            mbar_wait(&full[st], use & 1);
+            const float4* su = reinterpret_cast<const float4*>(ring + (size_t)st * 2 * AXPY_TILE);
             const float a = s_coef[k], c = s_coef[nhist + k], e = s_coef[2 * nhist + k];
             float4 u[2], v[2];
             // rows beyond cnt4 hold stale ring data: they are read (harmless) but never stored
             u[0] = su[tid]; u[1] = su[tid + TMA_CONSUMERS];
             v[0] = su[AXPY_TILE / 4 + tid]; v[1] = su[AXPY_TILE / 4 + tid + TMA_CONSUMERS];
             __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[s]);
+            if (lane == 0) mbar_arrive(&empty[st]);
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
                 av[j].x = fmaf(a, v[j].x, av[j].x); av[j].y = fmaf(a, v[j].y, av[j].y); av[j].z = fmaf(a, v[j].z, av[j].z); av[j].w = fmaf(a, v[j].w, av[j].w);
@@ -240,37 +275,35 @@ k_qn_axpy_tma(QnHistory H, int nhist, int n, const float* __restrict__ coef, int
         for (int j = 0; j < 2; ++j) {
             if (j == 0 ? act0 : act1) {
                 const int64_t q = t0 + tid + j * TMA_CONSUMERS;
-                const float4 vdx = reinterpret_cast<const float4*>(dx_upd)[q];
-                const float4 vdg = reinterpret_cast<const float4*>(dg_t)[q];
+                const float4 vdx = reinterpret_cast<const float4*>(dx_io)[q];
+                const float4 vdg = reinterpret_cast<const float4*>(dg)[q];
                 const float4 vg = reinterpret_cast<const float4*>(g)[q];
-                // vT = −δx + Σ a_k V_k  (rmatvec, solver.py:104)
+                const float4 xv = reinterpret_cast<const float4*>(x)[q];
+                // vT = −δx + Σ a_k V_k  (rmatvec, solver.py:104) ; vT[vT != vT] = 0  (solver.py:188)
                 float4 vn = make_float4(-vdx.x + av[j].x, -vdx.y + av[j].y, -vdx.z + av[j].z, -vdx.w + av[j].w);
-                acc0 += (double)vn.x * vdg.x + (double)vn.y * vdg.y + (double)vn.z * vdg.z + (double)vn.w * vdg.w;   // ⟨vT, δg⟩, un-scrubbed vT (solver.py:187)
-                // vT[vT != vT] = 0  (solver.py:188)
                 vn.x = (vn.x != vn.x) ? 0.f : vn.x; vn.y = (vn.y != vn.y) ? 0.f : vn.y;
                 vn.z = (vn.z != vn.z) ? 0.f : vn.z; vn.w = (vn.w != vn.w) ? 0.f : vn.w;
-                acc1 += (double)vn.x * vg.x + (double)vn.y * vg.y + (double)vn.z * vg.z + (double)vn.w * vg.w;        // V[n-1]ᵀ g_n for the new update
-                // numerator of u:  δx − matvec(δg) = δx − (−δg + Σ c_k U_k)   (solver.py:114,187)
-                const float4 un = make_float4(vdx.x - (-vdg.x + aw[j].x), vdx.y - (-vdg.y + aw[j].y), vdx.z - (-vdg.z + aw[j].z),
-                                              vdx.w - (-vdg.w + aw[j].w));
+                // u = (δx − matvec(δg)) / ⟨vT,δg⟩ = (δx − (−δg + Σ c_k U_k)) / s ; u[u != u] = 0   (solver.py:114,187,189)
+                float4 un = make_float4(vdx.x - (-vdg.x + aw[j].x), vdx.y - (-vdg.y + aw[j].y), vdx.z - (-vdg.z + aw[j].z),
+                                        vdx.w - (-vdg.w + aw[j].w));
+                un.x = __fdiv_rn(un.x, s); un.y = __fdiv_rn(un.y, s); un.z = __fdiv_rn(un.z, s); un.w = __fdiv_rn(un.w, s);
+                un.x = (un.x != un.x) ? 0.f : un.x; un.y = (un.y != un.y) ? 0.f : un.y;
+                un.z = (un.z != un.z) ? 0.f : un.z; un.w = (un.w != un.w) ? 0.f : un.w;
+                // update = −matvec(U[:n], V[:n], g) = −(−g + Σ_{k<n-1} U_k e_k + u_n·p)   (solver.py:192)
+                float4 upd;
+                upd.x = -(-vg.x + fmaf(un.x, p, at[j].x)); upd.y = -(-vg.y + fmaf(un.y, p, at[j].y));
+                upd.z = -(-vg.z + fmaf(un.z, p, at[j].z)); upd.w = -(-vg.w + fmaf(un.w, p, at[j].w));
+                // line_search with s = 1: x_est = x0 + update ; delta_x = x_est − x0   (solver.py:89,94)
+                const float4 xn = make_float4(xv.x + upd.x, xv.y + upd.y, xv.z + upd.z, xv.w + upd.w);
                 reinterpret_cast<float4*>(vn_dst)[q] = vn;
                 reinterpret_cast<float4*>(un_dst)[q] = un;
-                reinterpret_cast<float4*>(dx_upd)[q] = at[j];                 // t = Σ e_k U_k, finished in k_qn_fin2
+                reinterpret_cast<float4*>(x)[q] = xn;
+                reinterpret_cast<float4*>(dx_io)[q] = make_float4(xn.x - xv.x, xn.y - xv.y, xn.z - xv.z, xn.w - xv.w);
+                if (xtrace_next != nullptr) reinterpret_cast<float4*>(xtrace_next)[q] = xn;
             }
         }
     }
-    acc0 = warp_sum_d(acc0);
-    acc1 = warp_sum_d(acc1);
-    if (lane == 0) { s_red[warp] = acc0; s_red[8 + warp] = acc1; }
-    consumer_bar();
-    if (tid == 0) {
-        double a = 0.0, b = 0.0;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) { a += s_red[w]; b += s_red[8 + w]; }
-        partial2[blockIdx.x] = a;
-        partial2[gridDim.x + blockIdx.x] = b;
-    }
 }
 
-static inline size_t dots_tma_smem() { return (size_t)DOTS_STAGES * 2 * DOTS_CH * 4 + 2 * DOTS_STAGES * 8 + 2 * DOTS_KB * 3 * 8 * 4; }
-static inline size_t axpy_tma_smem(int nhist) { return (size_t)AXPY_STAGES * 2 * AXPY_TILE * 4 + 2 * AXPY_STAGES * 8 + 16 * 8 + (size_t)3 * (nhist > 0 ? nhist : 1) * 4; }
+static inline size_t dots_tma_smem() { return (size_t)DOTS_STAGES * 2 * DOTS_CH * 4 + 2 * DOTS_STAGES * 8 + 2 * DOTS_KB * 3 * 8 * 4 + 2 * 2 * 8 * 4; }
+static inline size_t axpy_tma_smem(int nhist) { return (size_t)AXPY_STAGES * 2 * AXPY_TILE * 4 + 2 * AXPY_STAGES * 8 + 18 * 8 + (size_t)3 * (nhist > 0 ? nhist : 1) * 4; }

@@ -48,14 +48,14 @@ class SolverWorkspace:
         except Exception:
             pass
 
-    PROFILE_CLASSES = ("operator", "k_qn_dots", "k_qn_axpy", "k_qn_fin2")
+    PROFILE_CLASSES = ("operator", "k_qn_dots", "k_qn_axpy")
 
     def profile(self, enable: bool = True):
         """per-kernel-class CUDA-event timing of the solver loops (resets the totals when enabled)"""
         N.check(N.load().psi_solver_profile(self.handle, 1 if enable else 0), "psi_solver_profile")
 
     def profile_read(self) -> dict:
-        buf = (c_double * 12)()
+        buf = (c_double * 9)()
         N.check(N.load().psi_solver_profile_read(self.handle, buf), "psi_solver_profile_read")
         return {name: {"launches": int(buf[3 * i]), "ms": float(buf[3 * i + 1]), "bytes": float(buf[3 * i + 2])}
                 for i, name in enumerate(self.PROFILE_CLASSES)}
