@@ -116,3 +116,50 @@ def test_synthetic_generator_contract():
     m = synthetic.make_batch(1, seed0=3, h=0.15, mixed=True)
     assert m.tags.shape[1] == 3 and m.prb_data.shape[1] == 3 and m.unit_normal_vector.shape == (m.num_nodes, 2)
     assert float(m.tags.sum(1).min()) == 1.0 and float(m.tags.sum(1).max()) == 1.0
+
+
+def test_weight_block_layout_baselines():
+    from psi_gnn_b200 import weights as W
+    o = W.OFFSETS
+    gd = Golden("dss_ckpt")
+    P = gd.params()
+    k = 7
+    blob = W.pack_dss(P, k, 1e-3, "cpu")
+    W1 = P["phi_to_list.%d.mlp.mlp.0.weight" % k]                      # [10, 21]: h_i, h_j, a_ij
+    assert torch.equal(blob[o["to.W1a"]:o["to.W1a"] + 30].view(10, 3)[:, 0], W1[:, 20])
+    assert float(blob[o["to.W1a"]:o["to.W1a"] + 30].view(10, 3)[:, 1:].abs().max()) == 0.0
+    assert torch.equal(blob[o["up_W1"]:o["up_W1"] + 330].view(10, 33), P["psi_list.%d.mlp.mlp.0.weight" % k])
+    assert torch.equal(blob[o["dec_W1"]:o["dec_W1"] + 100].view(10, 10), P["decoder_list.%d.mlp.mlp.0.weight" % k])
+    assert abs(float(blob[o["dss_alpha"]]) - 1e-3) < 1e-9               # fp32(1e-3), what `alpha * tensor` uses in the reference too
+    gg = Golden("dsgps_ckpt")
+    Pg = gg.params()
+    bg = W.pack_dsgps(Pg, "cpu")
+    assert torch.equal(bg[o["gz_W"]:o["gz_W"] + 320].view(10, 32), Pg["z_k.mlp.0.weight"])
+    assert torch.equal(bg[o["gc_b"]:o["gc_b"] + 10], Pg["correction.mlp.0.bias"])
+    assert torch.equal(bg[o["enc_W1"]:o["enc_W1"] + 10], Pg["autoencoder.encoder.mlp.mlp.0.weight"].reshape(-1))
+
+
+def test_baseline_state_dict_keys():
+    from psi_gnn_b200.dirichlet.dss import model as DSS
+    from psi_gnn_b200.dirichlet.dsgps import model as DSGPS
+    gd, gg = Golden("dss_ckpt"), Golden("dsgps_ckpt")
+    m = DSS.DeepStatisticalSolver(dict(latent_dim=10, k=int(gd["cfg.k"]), alpha=float(gd["cfg.alpha"]), gamma=0.9))
+    assert set(m.state_dict().keys()) == set(gd.params().keys())          # 480 tensors of the shipped DSS checkpoint
+    m2 = DSGPS.ModelDSGPS(dict(latent_dim=10, k=30, alpha=1e-3, gamma=0.9))
+    assert set(m2.state_dict().keys()) == set(gg.params().keys())
+    with pytest.raises(NotImplementedError):
+        m.forward(None)
+
+
+def test_shard_batch_balanced_and_complete():
+    from psi_gnn_b200 import parallel, synthetic
+    b = synthetic.make_batch(7, seed0=50, h=0.2)
+    for world in (1, 2, 3, 7):
+        shards = [parallel.shard_batch(b, r, world) for r in range(world)]
+        assert sum(s.num_graphs for s in shards) == 7 and sum(s.num_nodes for s in shards) == b.num_nodes
+        x = torch.cat([s.x for s in shards])
+        assert torch.equal(x, b.x)
+        for s in shards:
+            assert s.num_graphs >= 1 and int(s.edge_index.max()) < s.num_nodes
+    with pytest.raises(ValueError):
+        parallel.shard_batch(b, 0, 8)
