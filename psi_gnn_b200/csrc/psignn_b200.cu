@@ -296,6 +296,7 @@ extern "C" int psi_vjp_prepare(psi_graph_t* g, int kind, const float* dev_hstar,
     (void)dev_h0;   // the Dirichlet rows of f do not depend on h: h0 never enters the Jacobian
     if (check_kind(g, kind)) return -1;
     if (kind != PSI_KIND_DIRICHLET && kind != PSI_KIND_MIXED) PSI_FAIL("psi_vjp_prepare: VJP exists for the PSI-GNN layers only");
+    if (g->part != nullptr) PSI_FAIL("psi_vjp_prepare: the backward solve of a mesh-partitioned graph is not implemented");
     if (g->N > 0 && dev_hstar == nullptr) PSI_FAIL("psi_vjp_prepare: null pointer");
     cudaStream_t st = as_stream(stream);
     if (vjp_alloc(g, st)) return -1;
@@ -861,6 +862,7 @@ extern "C" int psi_solver_picard(psi_solver_t* s, psi_graph_t* g, int kind, cons
     if (s == nullptr) PSI_FAIL("psi_solver_picard: null solver");
     if (check_kind(g, kind)) return -1;
     if (g->N * PSI_D != s->numel) PSI_FAIL("psi_solver_picard: solver workspace size does not match the graph");
+    if (g->part != nullptr) PSI_FAIL("psi_solver_picard: mesh-partitioned graphs are solved with psi_solver_broyden");
     if (threshold < 0 || threshold > s->cap) PSI_FAIL("psi_solver_picard: threshold exceeds the solver workspace");
     cudaStream_t st = as_stream(stream);
     if (qn_begin(s, dev_x0, threshold, eps, nullptr, st)) return -1;
@@ -918,6 +920,7 @@ extern "C" int psi_solver_anderson(psi_solver_t* s, psi_graph_t* g, int kind, co
     if (s == nullptr) PSI_FAIL("psi_solver_anderson: null solver");
     if (check_kind(g, kind)) return -1;
     if (g->N * PSI_D != s->numel) PSI_FAIL("psi_solver_anderson: solver workspace size does not match the graph");
+    if (g->part != nullptr) PSI_FAIL("psi_solver_anderson: mesh-partitioned graphs are solved with psi_solver_broyden");
     if (m < 2 || m > AND_MAX_M) PSI_FAIL("psi_solver_anderson: m must be in [2, 8]");
     if (threshold < 0 || threshold > s->cap) PSI_FAIL("psi_solver_anderson: threshold exceeds the solver workspace");
     cudaStream_t st = as_stream(stream);

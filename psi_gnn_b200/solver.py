@@ -82,7 +82,7 @@ def workspace_for(numel: int, threshold: int, device) -> SolverWorkspace:
     if key in _POOL_ORDER:
         _POOL_ORDER.remove(key)
     _POOL_ORDER.append(key)
-    while len(_POOL_ORDER) > 1 and sum(w.nbytes for w in _POOL.values()) > POOL_MAX_BYTES:
+    while len(_POOL_ORDER) > 1 and len(_POOL) > 1 and sum(w.nbytes for w in _POOL.values()) > POOL_MAX_BYTES:
         old = _POOL_ORDER.pop(0)
         _POOL.pop(old).close()
     return ws
