@@ -168,6 +168,27 @@ struct SellBuild {
     void* recs = nullptr; void* off = nullptr; int64_t slots = 0; int64_t kept = 0;
 };
 
+// stream-ordered temporaries that are released on every exit path of build_sell
+struct TmpAllocs {
+    cudaStream_t st;
+    void* p[16];
+    int n = 0;
+    explicit TmpAllocs(cudaStream_t s) : st(s) {}
+    cudaError_t get(void** out, size_t bytes) {
+        cudaError_t e = psi_malloc_async(out, bytes, st);
+        if (e == cudaSuccess && n < 16) p[n++] = *out;
+        return e;
+    }
+    void keep(void* q) {          // hand ownership to the caller
+        for (int i = 0; i < n; ++i)
+            if (p[i] == q) p[i] = nullptr;
+    }
+    ~TmpAllocs() {
+        for (int i = 0; i < n; ++i)
+            if (p[i]) psi_free_async(p[i], st);
+    }
+};
+
 // Builds one list.  msg=true: int4 records with attrs (self loops dropped); msg=false: int2 {j, a_ij}.
 static int build_sell(int64_t N, int64_t nnz, const int64_t* ei, const float* attr, int attr_dim, const float* aij,
                       bool msg, bool by_col, cudaStream_t st, SellBuild* out) {
@@ -175,21 +196,23 @@ static int build_sell(int64_t N, int64_t nnz, const int64_t* ei, const float* at
     int *keys = nullptr, *vals = nullptr, *skeys = nullptr, *svals = nullptr, *ptr = nullptr;
     int64_t *slice_recs = nullptr, *slice_off = nullptr;
     void* tmp = nullptr;
+    void* recs = nullptr;
     size_t tmp_bytes = 0, tmp2 = 0;
     const int64_t nn = nnz > 0 ? nnz : 1;
-    PSI_CK(psi_malloc_async((void**)&keys, nn * sizeof(int), st));
-    PSI_CK(psi_malloc_async((void**)&vals, nn * sizeof(int), st));
-    PSI_CK(psi_malloc_async((void**)&skeys, nn * sizeof(int), st));
-    PSI_CK(psi_malloc_async((void**)&svals, nn * sizeof(int), st));
-    PSI_CK(psi_malloc_async((void**)&ptr, (N + 2) * sizeof(int), st));
-    PSI_CK(psi_malloc_async((void**)&slice_recs, (num_slices + 1) * sizeof(int64_t), st));
-    PSI_CK(psi_malloc_async((void**)&slice_off, (num_slices + 1) * sizeof(int64_t), st));
+    TmpAllocs T(st);
+    PSI_CK(T.get((void**)&keys, nn * sizeof(int)));
+    PSI_CK(T.get((void**)&vals, nn * sizeof(int)));
+    PSI_CK(T.get((void**)&skeys, nn * sizeof(int)));
+    PSI_CK(T.get((void**)&svals, nn * sizeof(int)));
+    PSI_CK(T.get((void**)&ptr, (N + 2) * sizeof(int)));
+    PSI_CK(T.get((void**)&slice_recs, (num_slices + 1) * sizeof(int64_t)));
+    PSI_CK(T.get((void**)&slice_off, (num_slices + 1) * sizeof(int64_t)));
     int end_bit = 1;
     while ((1ll << end_bit) <= N) ++end_bit;   // keys in [0, N]
     PSI_CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, skeys, vals, svals, (int)nnz, 0, end_bit, st));
     PSI_CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp2, slice_recs, slice_off, num_slices + 1, st));
     if (tmp2 > tmp_bytes) tmp_bytes = tmp2;
-    PSI_CK(psi_malloc_async(&tmp, tmp_bytes, st));
+    PSI_CK(T.get(&tmp, tmp_bytes));
     if (nnz > 0) {
         k_graph_keys<<<(unsigned)((nnz + 255) / 256), 256, 0, st>>>(nnz, (int)N, ei, by_col ? 1 : 0, msg ? 1 : 0, keys, vals);
         PSI_CK_LAUNCH();
@@ -209,8 +232,7 @@ static int build_sell(int64_t N, int64_t nnz, const int64_t* ei, const float* at
     PSI_CK(cudaMemcpyAsync(&kept, ptr + N, sizeof(int), cudaMemcpyDeviceToHost, st));
     PSI_CK(cudaStreamSynchronize(st));
     const size_t rec_bytes = msg ? sizeof(int4) : sizeof(int2);
-    void* recs = nullptr;
-    PSI_CK(psi_malloc_async(&recs, (total > 0 ? total : 1) * rec_bytes, st));
+    PSI_CK(T.get(&recs, (total > 0 ? total : 1) * rec_bytes));
     PSI_CK(cudaMemsetAsync(recs, 0xFF, (total > 0 ? total : 1) * rec_bytes, st));   // j = -1 everywhere
     if (N > 0 && nnz > 0) {
         if (msg)
@@ -221,8 +243,8 @@ static int build_sell(int64_t N, int64_t nnz, const int64_t* ei, const float* at
                                                                          slice_off, (int2*)recs);
         PSI_CK_LAUNCH();
     }
-    psi_free_async(keys, st); psi_free_async(vals, st); psi_free_async(skeys, st); psi_free_async(svals, st); psi_free_async(ptr, st);
-    psi_free_async(slice_recs, st); psi_free_async(tmp, st);
+    T.keep(recs);
+    T.keep(slice_off);
     out->recs = recs; out->off = slice_off; out->slots = total; out->kept = kept;
     return 0;
 }
