@@ -681,3 +681,37 @@ def test_solver_recovers_after_nonfinite_solve():
     again = S.broyden(op, h0, threshold=200, eps=1e-5)
     assert again["steps_run"] == ref["steps_run"] and again["rel_trace"] == ref["rel_trace"]
     assert torch.equal(again["result"], ref["result"])
+
+
+# ---- quasi-Newton kernels across sizes: a linear contraction is not chaotic, so the fp32 kernels must track the fp64 oracle ---------
+@pytest.mark.parametrize("rows", [1, 7, 409, 410, 411, 1000, 4099, 20481])
+def test_broyden_linear_operator_tracks_fp64_oracle(rows):
+    """f(x) = d ⊙ x + 0.05·W(Wᵀx) + b with |d| < 0.8: Broyden converges in a few dozen steps; sizes straddle the 4096-float chunk,
+    the 2048-float tile and the float4 granularities of the TMA kernels (rows × 10 floats), depths straddle the 32-vector work items."""
+    from oracle import psignn_oracle as O
+    from psi_gnn_b200 import solver as S
+    gen = torch.Generator().manual_seed(rows)
+    d = (torch.rand(rows, 10, generator=gen) * 1.6 - 0.8).double()
+    Wm = (torch.randn(rows * 10, 3, generator=gen) / (rows * 10) ** 0.5).double()
+    bvec = torch.randn(rows, 10, generator=gen).double()
+
+    def f64(x):
+        return d * x + 0.05 * (Wm @ (Wm.t() @ x.reshape(-1))).reshape(rows, 10) + bvec
+
+    d32, W32, b32 = d.float().to(DEV), Wm.float().to(DEV), bvec.float().to(DEV)
+
+    def f32(x):
+        return d32 * x + 0.05 * (W32 @ (W32.t() @ x.reshape(-1))).reshape(rows, 10) + b32
+
+    x0 = torch.zeros(rows, 10)
+    thr = 80
+    ref = O.broyden(f64, x0.double(), threshold=thr, eps=1e-6, keep_trace=False)
+    out = S.broyden(f32, x0.to(DEV), threshold=thr, eps=1e-6)
+    assert out["lowest"] < 1e-6 and ref["lowest"] < 1e-6
+    assert abs(out["nstep"] - ref["nstep"]) <= 2
+    k = min(out["steps_run"], len([r for r in ref["rel_trace"] if r > 1e-4]))
+    got, want = np.asarray(out["rel_trace"][:k]), np.asarray(ref["rel_trace"][:k])
+    assert np.all(np.abs(got - want) <= 2e-2 * want + 1e-7), (got, want)
+    xs = torch.linalg.solve(torch.eye(rows * 10, dtype=torch.float64) - torch.diag(d.reshape(-1)) - 0.05 * Wm @ Wm.t(), bvec.reshape(-1)) \\
+        if rows <= 1000 else ref["result"].reshape(-1)
+    assert float((out["result"].double().cpu().reshape(-1) - xs).norm() / xs.norm()) < 2e-5
