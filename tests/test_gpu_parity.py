@@ -712,6 +712,8 @@ def test_broyden_linear_operator_tracks_fp64_oracle(rows):
     k = min(out["steps_run"], len([r for r in ref["rel_trace"] if r > 1e-4]))
     got, want = np.asarray(out["rel_trace"][:k]), np.asarray(ref["rel_trace"][:k])
     assert np.all(np.abs(got - want) <= 2e-2 * want + 1e-7), (got, want)
-    xs = torch.linalg.solve(torch.eye(rows * 10, dtype=torch.float64) - torch.diag(d.reshape(-1)) - 0.05 * Wm @ Wm.t(), bvec.reshape(-1)) \\
-        if rows <= 1000 else ref["result"].reshape(-1)
+    if rows <= 1000:
+        xs = torch.linalg.solve(torch.eye(rows * 10, dtype=torch.float64) - torch.diag(d.reshape(-1)) - 0.05 * Wm @ Wm.t(), bvec.reshape(-1))
+    else:
+        xs = ref["result"].reshape(-1)
     assert float((out["result"].double().cpu().reshape(-1) - xs).norm() / xs.norm()) < 2e-5
