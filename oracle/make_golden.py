@@ -142,6 +142,20 @@ def make_fixture(family: str, weights: str, n_graphs: int, seed0: int, h: float,
                   fw_x1=fw["xest_trace"][1].numpy(), fw_x2=fw["xest_trace"][2].numpy(), fw_x3=fw["xest_trace"][3].numpy(),
                   fw_steps_run=np.int64(len(fw["xest_trace"]) - 1),
                   u=u.numpy(), residual=np.float64(res.item()), residual_x=np.float64(res_x.item()))
+        # the reference against ITSELF under a mere permutation of the edge list (same graph, same weights): how far two arithmetically
+        # equivalent runs of the reference drift apart — the band any other implementation can be held to for free-running solves
+        gen_p = torch.Generator().manual_seed(77)
+        perm = torch.randperm(batch.edge_index.shape[1], generator=gen_p)
+        bp = synthetic.GraphData()
+        bp.__dict__.update(batch.__dict__)
+        bp.edge_index, bp.edge_attr, bp.a_ij = batch.edge_index[:, perm], batch.edge_attr[perm], batch.a_ij[perm]
+        with torch.no_grad():
+            fwp = solver_mod.broyden(lambda Hh: f(Hh, h0, bp), h0, threshold=cfg["fw_thres"], eps=cfg["fw_tol"])
+            up = model.autoencoder.decoder(fwp["result"])
+        fx.update(perm_fw_nstep=np.int64(fwp["nstep"]), perm_fw_lowest=np.float64(fwp["lowest"]), perm_u=up.numpy(),
+                  perm_fw_steps_run=np.int64(len(fwp["xest_trace"]) - 1))
+        self_dev = float((up - u).norm() / u.norm())
+        print("    reference vs itself under an edge permutation: nstep %d vs %d, u rel diff %.2e" % (fw["nstep"], fwp["nstep"], self_dev))
         # the oracle must reproduce the reference bit for bit on this fixture (checked again in tests)
         of = O.f_mixed if mixed else O.f_dirichlet
         with torch.no_grad():

@@ -15,7 +15,20 @@ from conftest import Golden, rel_err
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 TOL = 1e-5
-BAND_U = 1.5e-2      # free-running solves only: see test_forward_solve_free_running
+
+
+def band_u(golden):
+    """Allowed deviation of a free-running solution: 5 × the distance between two runs of the REFERENCE ITSELF that differ only by a
+    permutation of the edge list (stored in the fixture as perm_u), floor 1e-5.  For short solves (random-init fixtures: 17–19 steps)
+    the reference is permutation-stable to 2e-7 and the band is the 1e-5 parity bar; for the trained checkpoints (67–191 steps,
+    spectral radius 0.99) the reference's own scatter is 4e-4 (dirichlet) to 5e-3 (mixed)."""
+    self_dev = rel_err(golden.t("perm_u"), golden.t("u"))
+    return max(TOL, 5.0 * self_dev)
+
+
+def nstep_stable(golden):
+    return int(golden["perm_fw_nstep"]) == int(golden["fw_nstep"])
+
 
 
 def _kind(g):
@@ -171,7 +184,12 @@ def test_forward_solve_free_running(golden):
     # the fixed point itself: both are eps-accurate solutions of the same contraction
     # two eps-accurate fixed points of a map with spectral radius ρ ≈ 0.99 differ by up to ~2·eps/(1−ρ) ≈ 3e-3 in h (more in u): band
     u = m._decode_native(out["result"])
-    assert rel_err(u, golden.t("u")) <= BAND_U
+    dev = rel_err(u, golden.t("u"))
+    print("free-running %s: nstep %d (reference %d, permuted reference %d), u rel diff %.2e (reference vs itself %.2e)" % (
+        golden.name, out["nstep"], int(golden["fw_nstep"]), int(golden["perm_fw_nstep"]), dev, rel_err(golden.t("perm_u"), golden.t("u"))))
+    assert dev <= band_u(golden)
+    if nstep_stable(golden):            # where the reference's own step count is permutation-invariant, ours must equal it
+        assert out["nstep"] == int(golden["fw_nstep"])
     r = m.residual_loss(u, b).item()
     assert abs(r - float(golden["residual"])) <= 0.05 * float(golden["residual"]) + 1e-7
     # and it is a fixed point of the CUDA layer to the requested tolerance
@@ -185,7 +203,7 @@ def test_model_inference_matches_reference(golden):
     b = golden.batch(DEV)
     u = m.inference(b)
     assert u.shape == (b.num_nodes, 1)
-    assert rel_err(u, golden.t("u")) <= BAND_U
+    assert rel_err(u, golden.t("u")) <= band_u(golden)
 
 
 def test_broyden_generic_callable_matches_fused(golden):
@@ -291,7 +309,7 @@ def test_training_step_free_running(golden, monkeypatch):
     m = golden.model(DEV)
     b = golden.batch(DEV)
     u, loss_dic, gs = _train_step(m, b, golden.t("train_v", DEV), monkeypatch)
-    assert rel_err(u.detach(), golden.t("train_u")) <= BAND_U
+    assert rel_err(u.detach(), golden.t("train_u")) <= band_u(golden)
     for k in ("residual_loss", "jacobian_loss", "encoder_loss", "autoencoder_loss"):
         ref = float(golden["train_loss." + k])
         assert abs(loss_dic[k].item() - ref) <= 0.25 * abs(ref) + 1e-7, k
