@@ -119,8 +119,6 @@ k_qn_fin1(int nhist, const float* __restrict__ partial, int num_chunks, float* _
           double* __restrict__ dbuf /* [3·nhist + 2] fp64 row sums for pass 2 */, const float* __restrict__ norm_part, int norm_blocks,
           QnCtrl* __restrict__ ctrl, double* __restrict__ rel_trace, double* __restrict__ abs_trace, int step, double eps, double protect,
           int threshold) {
-    pdl_trigger();
-    pdl_wait();
     if (ctrl->done) return;
     const int lane = threadIdx.x & 31;
     const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;

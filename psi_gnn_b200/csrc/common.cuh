@@ -49,29 +49,6 @@ static inline void psi_free_async(void* p, cudaStream_t st) {
     if (p) cudaFreeAsync(p, st);
 }
 
-// Programmatic dependent launch: the kernels of the solver loop are launched with programmatic stream serialisation, call
-// pdl_trigger() first thing (the next kernel of the stream may then be scheduled as soon as every CTA of this one is running) and
-// pdl_wait() before their first global-memory access (returns once the preceding grid has completed and its writes are visible).
-// Launch latency and prologues (mbarrier set-up of the TMA kernels) overlap with the tail of the previous kernel; ordering of all
-// global-memory traffic is exactly that of plain stream order.  Without the launch attribute both instructions are no-ops.
-__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-
-template <typename... KArgs, typename... Args>
-static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = grid;
-    cfg.blockDim = block;
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
-}
-
 static inline int64_t round_up64(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
 
 // ---- row access: a latent row is 10 contiguous floats (40 B, 8-byte aligned) -----------------

@@ -298,8 +298,6 @@ template <int KIND, bool EPI>
 __global__ void __launch_bounds__(PSI_NODE_BLOCK)
 k_layer_forward(GraphDev G, const float* __restrict__ h, const float* __restrict__ h0, float* __restrict__ out, SolverEpi E) {
     __shared__ float smem[2 * PSI_NODE_BLOCK / 32];
-    pdl_trigger();
-    pdl_wait();
     if (EPI && *E.done) return;
     const int node = blockIdx.x * PSI_NODE_BLOCK + threadIdx.x;
     const bool valid = node < G.n_compute;

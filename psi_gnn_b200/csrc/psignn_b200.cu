@@ -228,10 +228,10 @@ static int launch_layer(const psi_graph* g, int kind, const float* h, const floa
     if (g->dev.n_compute == 0) return 0;
     const unsigned grid = node_grid(g->dev.n_compute);
     switch (kind) {
-        case PSI_KIND_DIRICHLET: PSI_CK(launch_pdl(k_layer_forward<KIND_DIRICHLET, EPI>, grid, PSI_NODE_BLOCK, 0, st, g->dev, h, h0, out, E)); break;
-        case PSI_KIND_MIXED:     PSI_CK(launch_pdl(k_layer_forward<KIND_MIXED, EPI>, grid, PSI_NODE_BLOCK, 0, st, g->dev, h, h0, out, E)); break;
-        case PSI_KIND_DSS:       PSI_CK(launch_pdl(k_layer_forward<KIND_DSS, EPI>, grid, PSI_NODE_BLOCK, 0, st, g->dev, h, h0, out, E)); break;
-        default:                 PSI_CK(launch_pdl(k_layer_forward<KIND_DSGPS, EPI>, grid, PSI_NODE_BLOCK, 0, st, g->dev, h, h0, out, E)); break;
+        case PSI_KIND_DIRICHLET: k_layer_forward<KIND_DIRICHLET, EPI><<<grid, PSI_NODE_BLOCK, 0, st>>>(g->dev, h, h0, out, E); break;
+        case PSI_KIND_MIXED:     k_layer_forward<KIND_MIXED, EPI><<<grid, PSI_NODE_BLOCK, 0, st>>>(g->dev, h, h0, out, E); break;
+        case PSI_KIND_DSS:       k_layer_forward<KIND_DSS, EPI><<<grid, PSI_NODE_BLOCK, 0, st>>>(g->dev, h, h0, out, E); break;
+        default:                 k_layer_forward<KIND_DSGPS, EPI><<<grid, PSI_NODE_BLOCK, 0, st>>>(g->dev, h, h0, out, E); break;
     }
     PSI_CK_LAUNCH();
     return 0;
@@ -317,11 +317,11 @@ static int launch_vjp(psi_graph* g, int kind, const float* y, const float* grad,
     if (g->N == 0) return 0;
     const unsigned grid = node_grid(g->N);
     if (kind == PSI_KIND_DIRICHLET) {
-        PSI_CK(launch_pdl(k_vjp_phase_a<KIND_DIRICHLET>, grid, PSI_NODE_BLOCK, 0, st, g->dev, g->vjp, y, E.done));
-        PSI_CK(launch_pdl(k_vjp_phase_b<KIND_DIRICHLET, EPI>, grid, PSI_NODE_BLOCK, 0, st, g->dev, g->vjp, y, grad, out, E));
+        k_vjp_phase_a<KIND_DIRICHLET><<<grid, PSI_NODE_BLOCK, 0, st>>>(g->dev, g->vjp, y, E.done);
+        k_vjp_phase_b<KIND_DIRICHLET, EPI><<<grid, PSI_NODE_BLOCK, 0, st>>>(g->dev, g->vjp, y, grad, out, E);
     } else {
-        PSI_CK(launch_pdl(k_vjp_phase_a<KIND_MIXED>, grid, PSI_NODE_BLOCK, 0, st, g->dev, g->vjp, y, E.done));
-        PSI_CK(launch_pdl(k_vjp_phase_b<KIND_MIXED, EPI>, grid, PSI_NODE_BLOCK, 0, st, g->dev, g->vjp, y, grad, out, E));
+        k_vjp_phase_a<KIND_MIXED><<<grid, PSI_NODE_BLOCK, 0, st>>>(g->dev, g->vjp, y, E.done);
+        k_vjp_phase_b<KIND_MIXED, EPI><<<grid, PSI_NODE_BLOCK, 0, st>>>(g->dev, g->vjp, y, grad, out, E);
     }
     PSI_CK_LAUNCH();
     return 0;
@@ -619,14 +619,14 @@ static int qn_update(psi_solver* s, int n, int norm_blocks, cudaStream_t st) {
     const double vec = (double)s->act_numel * 4.0;
     // pass 1 (also at nhist = 0: it carries ⟨δx,δg⟩ and ⟨δx,g⟩, from which s and p of this step follow)
     prof_begin(s, n, 1, (2.0 * nhist + 3.0) * vec, st);
-    PSI_CK(launch_pdl(k_qn_dots_tma, s->tma_ctas, TMA_THREADS, dots_tma_smem(), st, s->hist, nhist, s->dx, s->dg, s->g, s->partial, s->act_dchunks,
-                      &s->ctrl->done));
+    k_qn_dots_tma<<<s->tma_ctas, TMA_THREADS, dots_tma_smem(), st>>>(s->hist, nhist, s->dx, s->dg, s->g, s->partial, s->act_dchunks,
+                                                                     &s->ctrl->done);
     prof_end(s, n, 1, st);
     PSI_CK_LAUNCH();
     const int fin_blocks = std::max(1, std::min(2 * s->tma_ctas, (nhist * 3 + 2 + 7) / 8));   // one warp per row of the partial matrix
     if (s->comm == nullptr) {
-        PSI_CK(launch_pdl(k_qn_fin1, fin_blocks, 256, 0, st, nhist, s->partial, s->act_dchunks, s->coef, s->cap, s->dbuf, s->norm_part, norm_blocks,
-                          s->ctrl, s->rel_trace, s->abs_trace, n, s->eps, 1e3 * PSI_D, s->threshold));
+        k_qn_fin1<<<fin_blocks, 256, 0, st>>>(nhist, s->partial, s->act_dchunks, s->coef, s->cap, s->dbuf, s->norm_part, norm_blocks, s->ctrl,
+                                              s->rel_trace, s->abs_trace, n, s->eps, 1e3 * PSI_D, s->threshold);
         PSI_CK_LAUNCH();
     } else {
         // mesh-partitioned: local fp64 sums → ONE all-reduce of 3(n−1)+4 doubles per step → coefficients and stop rules (identical on every rank)
@@ -642,8 +642,8 @@ static int qn_update(psi_solver* s, int n, int norm_blocks, cudaStream_t st) {
     if (n >= s->threshold) xt = nullptr;
     // pass 2: rank-one update, new update direction and the step itself (history read once, 4 vectors read + 4 written besides)
     prof_begin(s, n, 2, (2.0 * nhist + 8.0) * vec, st);
-    PSI_CK(launch_pdl(k_qn_axpy_tma, s->tma_ctas, TMA_THREADS, axpy_tma_smem(nhist), st, s->hist, nhist, n, s->coef, s->cap, s->dbuf, s->dx, s->dg,
-                      s->g, s->x, s->best, xt, (s->act_numel + 3) / 4, s->ctrl));
+    k_qn_axpy_tma<<<s->tma_ctas, TMA_THREADS, axpy_tma_smem(nhist), st>>>(s->hist, nhist, n, s->coef, s->cap, s->dbuf, s->dx, s->dg, s->g, s->x,
+                                                                         s->best, xt, (s->act_numel + 3) / 4, s->ctrl);
     prof_end(s, n, 2, st);
     PSI_CK_LAUNCH();
     s->launches += 3;

@@ -67,14 +67,12 @@ k_qn_dots_tma(QnHistory H, int nhist, const float* __restrict__ dx, const float*
     uint64_t* empty = full + DOTS_STAGES;
     float* red = reinterpret_cast<float*>(empty + DOTS_STAGES);                         // [2][DOTS_KB][3][8]
     float* red_x = red + 2 * DOTS_KB * 3 * 8;                                           // [2][2][8]: ⟨δx,δg⟩, ⟨δx,g⟩ of a chunk
+    if (*done) return;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    pdl_trigger();
-    if (tid == 0) {                        // barrier set-up overlaps the tail of the previous kernel (programmatic dependent launch)
+    if (tid == 0) {
         for (int s = 0; s < DOTS_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], TMA_CONSUMERS / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    pdl_wait();
-    if (*done) return;
     __syncthreads();
     const int kranges = max(1, (nhist + DOTS_KR - 1) / DOTS_KR);       // at least one item per chunk: it also carries ⟨δx,δg⟩, ⟨δx,g⟩
     const int items = num_chunks * kranges;
@@ -187,15 +185,9 @@ k_qn_axpy_tma(QnHistory H, int nhist, int n, const float* __restrict__ coef, int
     uint64_t* empty = full + AXPY_STAGES;
     double* s_red = reinterpret_cast<double*>(empty + AXPY_STAGES);                     // [2][9]
     float* s_coef = reinterpret_cast<float*>(s_red + 18);                               // [3][nhist]
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    pdl_trigger();
-    if (tid == 0) {                        // barrier set-up overlaps the tail of the previous kernel (programmatic dependent launch)
-        for (int s = 0; s < AXPY_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], TMA_CONSUMERS / 32); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    pdl_wait();
     const int improved = ctrl->improved, done = ctrl->done;
     if (done && !improved) return;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t per = (total4 + gridDim.x - 1) / gridDim.x;
     const int64_t q0 = min(total4, (int64_t)blockIdx.x * per), q1 = min(total4, q0 + per);
     if (improved) {                        // lowest_xest = x_est.clone()  (solver.py:172)
@@ -203,6 +195,10 @@ k_qn_axpy_tma(QnHistory H, int nhist, int n, const float* __restrict__ coef, int
             reinterpret_cast<float4*>(best_x)[q] = reinterpret_cast<const float4*>(x)[q];
     }
     if (done) return;
+    if (tid == 0) {
+        for (int s = 0; s < AXPY_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], TMA_CONSUMERS / 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     for (int i = tid; i < nhist; i += TMA_THREADS) {
         s_coef[i] = coef[i];
         s_coef[nhist + i] = coef[cap + i];

@@ -160,8 +160,6 @@ k_vjp_prepare(GraphDev G, VjpCacheDev C, const float* __restrict__ h) {
 template <int KIND>
 __global__ void __launch_bounds__(PSI_NODE_BLOCK)
 k_vjp_phase_a(GraphDev G, VjpCacheDev C, const float* __restrict__ y, const int* __restrict__ done) {
-    pdl_trigger();
-    pdl_wait();
     if (done != nullptr && *done) return;
     const int node = blockIdx.x * PSI_NODE_BLOCK + threadIdx.x;
     if (node >= G.N) return;
@@ -280,8 +278,6 @@ __global__ void __launch_bounds__(PSI_NODE_BLOCK)
 k_vjp_phase_b(GraphDev G, VjpCacheDev C, const float* __restrict__ y, const float* __restrict__ grad,
               float* __restrict__ out, SolverEpi E) {
     __shared__ float smem[2 * PSI_NODE_BLOCK / 32];
-    pdl_trigger();
-    pdl_wait();
     if (EPI && *E.done) return;
     const int node = blockIdx.x * PSI_NODE_BLOCK + threadIdx.x;
     const bool valid = node < G.N;
