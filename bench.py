@@ -207,17 +207,20 @@ def run_native(args):
     for _ in range(warm):
         train_step(dev_batch, False)
     ws = PM.graph_of(dev_batch, model.deqdss.f.kind).solver(max(cfg["fw_thres"], cfg["bw_thres"]))
-    ws.profile(True)
     for k in stats:
         stats[k] = 0
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms_total = timed(lambda: train_step(dev_batch, False), args.steps)
+    ms_total = timed(lambda: train_step(dev_batch, False), args.steps)           # headline pass: no instrumentation inside the loop
     clocks = sampler.stop() if rank == 0 else None
+    run_stats = dict(stats)
+    # second pass of the same K steps with one CUDA-event pair around every solver-loop launch (psi_solver_profile) for the roofline:
+    # the ~3 µs per event pair cost 2–3 % of a C3 step and 30 % of a C0 step, so they are kept out of the headline pass
+    ws.profile(True)
+    ms_profiled = timed(lambda: train_step(dev_batch, False), args.steps)
     prof = ws.profile_read()
     ws.profile(False)
-    run_stats = dict(stats)
     # ---- end-to-end arm (host buffers, H2D + re-layout + D2H inside the timed region) --------------------------
     for _ in range(2):
         e2e_step()
@@ -260,7 +263,7 @@ def run_native(args):
         "e2e": {"value": round(world * n_graphs * args.steps / (ms_e2e / 1e3), 2), "unit": "graphs/s", "ms_per_step": round(ms_e2e / args.steps, 3),
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                     "traffic": traffic, "traffic_source": "algorithmic bytes per launch x the DRAM-traffic/algorithmic ratio of the ncu --set full capture in profiles/ncu_traffic.json" if traffic else None, "peak_source": peak_src, "avg_launch_us": round(1e3 * d["ms"] / max(d["launches"], 1), 2),
+                     "measured_in": "second pass of the same K steps with one CUDA-event pair per solver-loop launch (%.3f ms/step instrumented vs %.3f ms/step in the headline pass)" % (ms_profiled / args.steps, ms_total / args.steps), "traffic": traffic, "traffic_source": "algorithmic bytes per launch x the DRAM-traffic/algorithmic ratio of the ncu --set full capture in profiles/ncu_traffic.json" if traffic else None, "peak_source": peak_src, "avg_launch_us": round(1e3 * d["ms"] / max(d["launches"], 1), 2),
                      "alg_bytes_per_launch": round(d["bytes"] / max(d["launches"], 1), 1)},
         "kernels": kernels,
         "clocks": clocks,
@@ -349,17 +352,18 @@ def run_native_inference(args, rank, local, world, dev):
         solve(dev_batch, False)
     g = PM.graph_of(dev_batch, 0)
     ws = g.solver(cfg["fw_thres"])
-    ws.profile(True)
     for k in stats:
         stats[k] = 0
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms_total = _timed_steps(lambda: solve(dev_batch, False), args.steps, world, dev, flush)
+    ms_total = _timed_steps(lambda: solve(dev_batch, False), args.steps, world, dev, flush)     # headline pass: no instrumentation
     clocks = sampler.stop() if rank == 0 else None
+    run_stats = dict(stats)
+    ws.profile(True)                                                                            # second pass with per-launch CUDA events
+    ms_profiled = _timed_steps(lambda: solve(dev_batch, False), args.steps, world, dev, flush)
     prof = ws.profile_read()
     ws.profile(False)
-    run_stats = dict(stats)
     e2e()
     ms_e2e = _timed_steps(e2e, args.steps, world, dev, flush)
     sec = ms_total / 1e3
@@ -397,7 +401,7 @@ def run_native_inference(args, rank, local, world, dev):
         "e2e": {"value": round(units * args.steps / (ms_e2e / 1e3), 4), "unit": "graphs/s", "ms_per_step": round(ms_e2e / args.steps, 3),
                 "h2d_bytes_per_step": host.nbytes(), "d2h_bytes_per_step": 4 * n_owned},
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                     "traffic": traffic, "traffic_source": "algorithmic bytes per launch x the DRAM-traffic/algorithmic ratio of the ncu --set full capture in profiles/ncu_traffic.json" if traffic else None, "peak_source": peak_src, "avg_launch_us": round(1e3 * d["ms"] / max(d["launches"], 1), 2),
+                     "measured_in": "second pass of the same K steps with one CUDA-event pair per solver-loop launch (%.3f ms/step instrumented vs %.3f ms/step in the headline pass)" % (ms_profiled / args.steps, ms_total / args.steps), "traffic": traffic, "traffic_source": "algorithmic bytes per launch x the DRAM-traffic/algorithmic ratio of the ncu --set full capture in profiles/ncu_traffic.json" if traffic else None, "peak_source": peak_src, "avg_launch_us": round(1e3 * d["ms"] / max(d["launches"], 1), 2),
                      "alg_bytes_per_launch": round(d["bytes"] / max(d["launches"], 1), 1)},
         "kernels": kernels, "clocks": clocks,
     }
