@@ -113,3 +113,33 @@ def test_mesh_partition_reproduces_global_layer():
                 roff += rc
     single = partition.partition_mesh(mesh, world, rank=1)[0]
     assert np.array_equal(single.owned_global, parts[1].owned_global) and np.array_equal(single.send_index, parts[1].send_index)
+
+
+def test_mesh_partition_aligned_cuts():
+    """large enough meshes are cut at multiples of 2048 nodes (what makes the partitioned solve retrace the single-GPU trajectory),
+    and the 1-rank 'partition' is a pure reordering of the mesh"""
+    import numpy as np
+    from conftest import Golden
+    from oracle import psignn_oracle as O
+    from psi_gnn_b200 import partition, synthetic
+    mesh = synthetic.make_large_mesh(9500, seed=1)
+    assert mesh.num_nodes >= 2 * partition.ALIGN_NODES * 2
+    parts = partition.partition_mesh(mesh, 2)
+    assert parts[0].n_owned % partition.ALIGN_NODES == 0 and parts[0].n_owned + parts[1].n_owned == mesh.num_nodes
+    assert abs(parts[0].n_owned - mesh.num_nodes / 2) <= partition.ALIGN_NODES
+    # geometric order: every owned x of rank 0 is left of every owned x of rank 1
+    x0 = mesh.pos[torch.from_numpy(parts[0].owned_global), 0]
+    x1 = mesh.pos[torch.from_numpy(parts[1].owned_global), 0]
+    assert float(x0.max()) <= float(x1.min())
+    one = partition.reorder_mesh(mesh)
+    P = Golden("dirichlet_ckpt").params()
+    gen = torch.Generator().manual_seed(2)
+    h = torch.randn(mesh.num_nodes, 10, generator=gen)
+    h0 = torch.randn(mesh.num_nodes, 10, generator=gen)
+    order = torch.from_numpy(one.partition.owned_global)
+    with torch.no_grad():
+        a = O.f_dirichlet(P, h, h0, mesh)
+        b = O.f_dirichlet(P, h[order], h0[order], one)
+    assert one.partition.n_ghost == 0 and float((b - a[order]).abs().max()) <= 1e-5
+    # ranks of the aligned partition own contiguous slices of that order
+    assert np.array_equal(np.concatenate([p.owned_global for p in parts]), one.partition.owned_global)
