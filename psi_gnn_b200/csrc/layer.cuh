@@ -189,11 +189,9 @@ __device__ __forceinline__ void load_prb(const GraphDev& G, int node, float (&pr
 }
 
 // One application of the layer for one node.  `hi` is the node's own row of h.
-// `pre` (PAIR only): the node's second aggregate — ΣΦ← (or ΣΦ_neumann on a Neumann row) — computed by the partner warp of
-// k_layer_forward_pair and handed over through shared memory; otherwise this thread walks both lists itself.
-template <int KIND, bool PAIR>
+template <int KIND>
 __device__ __forceinline__ void node_forward(const GraphDev& G, const float* __restrict__ h, const float* __restrict__ h0,
-                                             int node, const float (&hi)[PSI_D], const float* pre, float (&out)[PSI_D]) {
+                                             int node, const float (&hi)[PSI_D], float (&out)[PSI_D]) {
     const uint8_t tg = G.tag[node];
     if (KIND != KIND_DSS && (tg & 1)) {           // Dirichlet clamp: h[dir] = h_initial[dir] (model.py:298)
         load_row(h0, node, out);
@@ -206,12 +204,7 @@ __device__ __forceinline__ void node_forward(const GraphDev& G, const float* __r
         float r[PSI_D];
         if (KIND == KIND_MIXED && (tg & 2)) {     // Neumann rows are overwritten before LayerNorm (mixed model.py:235-237)
             float mN[PSI_D], m[PSI_D];
-            if (PAIR) {
-#pragma unroll
-                for (int o = 0; o < PSI_D; ++o) mN[o] = pre[o];
-            } else {
-                edge_aggregate<2, 3>(G.F, h, node, hi, mN);
-            }
+            edge_aggregate<2, 3>(G.F, h, node, hi, mN);
             const float nv[2] = {__ldg(G.nrm + 2 * (int64_t)node), __ldg(G.nrm + 2 * (int64_t)node + 1)};
             uint32_t hm;
             neumann_mlp(hi, mN, prb, nv, m, hm);
@@ -220,12 +213,7 @@ __device__ __forceinline__ void node_forward(const GraphDev& G, const float* __r
         } else {
             float mT[PSI_D], mF[PSI_D], m[PSI_D];
             edge_aggregate<0, 3>(G.T, h, node, hi, mT);
-            if (PAIR) {
-#pragma unroll
-                for (int o = 0; o < PSI_D; ++o) mF[o] = pre[o];
-            } else {
-                edge_aggregate<1, 3>(G.F, h, node, hi, mF);
-            }
+            edge_aggregate<1, 3>(G.F, h, node, hi, mF);
             const float alpha = gate<PRB>(hi, mT, mF, prb);
             uint32_t hm;
             update_mlp<PRB>(hi, mT, mF, prb, m, hm);
@@ -238,12 +226,7 @@ __device__ __forceinline__ void node_forward(const GraphDev& G, const float* __r
         float prb[3], mT[PSI_D], mF[PSI_D], m[PSI_D];
         load_prb<3>(G, node, prb);
         edge_aggregate<0, 1>(G.T, h, node, hi, mT);
-        if (PAIR) {
-#pragma unroll
-            for (int o = 0; o < PSI_D; ++o) mF[o] = pre[o];
-        } else {
-            edge_aggregate<1, 1>(G.F, h, node, hi, mF);
-        }
+        edge_aggregate<1, 1>(G.F, h, node, hi, mF);
         uint32_t hm;
         update_mlp<3>(hi, mT, mF, prb, m, hm);
 #pragma unroll
@@ -252,12 +235,7 @@ __device__ __forceinline__ void node_forward(const GraphDev& G, const float* __r
         float prb[3], mT[PSI_D], mF[PSI_D];
         load_prb<2>(G, node, prb);
         edge_aggregate<0, 3>(G.T, h, node, hi, mT);
-        if (PAIR) {
-#pragma unroll
-            for (int o = 0; o < PSI_D; ++o) mF[o] = pre[o];
-        } else {
-            edge_aggregate<1, 3>(G.F, h, node, hi, mF);
-        }
+        edge_aggregate<1, 3>(G.F, h, node, hi, mF);
         float c[32];
 #pragma unroll
         for (int i = 0; i < PSI_D; ++i) { c[i] = hi[i]; c[PSI_D + i] = mT[i]; c[2 * PSI_D + i] = mF[i]; }
@@ -292,7 +270,6 @@ struct SolverEpi {
     const int* done;     // device flag: skip all work once the solve has finished
 };
 
-template <int NWARPS = PSI_NODE_BLOCK / 32>
 __device__ __forceinline__ void solver_epilogue(const SolverEpi& E, int node, bool valid, const float (&xi)[PSI_D],
                                                 const float (&fx)[PSI_D], float* smem) {
     float acc[2] = {0.f, 0.f};
@@ -310,7 +287,7 @@ __device__ __forceinline__ void solver_epilogue(const SolverEpi& E, int node, bo
         store_row(E.g, node, gn);
         store_row(E.dg, node, dgv);
     }
-    block_sum<2, NWARPS>(acc, smem);
+    block_sum<2, PSI_NODE_BLOCK / 32>(acc, smem);
     if (threadIdx.x == 0) {
         E.norm_part[blockIdx.x] = acc[0];
         E.norm_part[gridDim.x + blockIdx.x] = acc[1];
@@ -327,57 +304,10 @@ k_layer_forward(GraphDev G, const float* __restrict__ h, const float* __restrict
     float hi[PSI_D], fx[PSI_D];
     if (valid) {
         load_row(h, node, hi);
-        node_forward<KIND, false>(G, h, h0, node, hi, nullptr, fx);
+        node_forward<KIND>(G, h, h0, node, hi, fx);
         if (!EPI || out != nullptr) store_row(out, node, fx);   // Picard keeps f(x) itself
     }
     if (EPI) solver_epilogue(E, node, valid, hi, fx, smem);
-}
-
-// ---- the same layer with two warps per 32-node slice --------------------------------------------------------------------------
-// For batches that fit in about one wave (≤ 64 k nodes) the kernel's duration is the latency of one thread walking both adjacency
-// lists of its node.  Here warp 2s walks list T and does the node update, warp 2s+1 walks list F (Φ← or Φ_neumann) of the same 32
-// nodes and hands its aggregate over through shared memory: the dependent gather chain is halved.  Every floating-point operation
-// and its order are those of k_layer_forward (the helper warps contribute exact zeros to the norm partials), so the two kernels are
-// bit-identical; larger problems keep the one-thread-per-node kernel, which holds twice as many nodes in flight per SM.
-#define PSI_PAIR_BLOCK 256
-
-template <int KIND>
-__device__ __forceinline__ void second_aggregate(const GraphDev& G, const float* __restrict__ h, int node, const float (&hi)[PSI_D],
-                                                 float (&m)[PSI_D]) {
-    const uint8_t tg = G.tag[node];
-#pragma unroll
-    for (int o = 0; o < PSI_D; ++o) m[o] = 0.f;
-    if (KIND != KIND_DSS && (tg & 1)) return;                 // Dirichlet rows are clamped, nothing to aggregate
-    if (KIND == KIND_MIXED && (tg & 2)) edge_aggregate<2, 3>(G.F, h, node, hi, m);
-    else if (KIND == KIND_DSS) edge_aggregate<1, 1>(G.F, h, node, hi, m);
-    else edge_aggregate<1, 3>(G.F, h, node, hi, m);
-}
-
-template <int KIND, bool EPI>
-__global__ void __launch_bounds__(PSI_PAIR_BLOCK)
-k_layer_forward_pair(GraphDev G, const float* __restrict__ h, const float* __restrict__ h0, float* __restrict__ out, SolverEpi E) {
-    __shared__ float smem[2 * PSI_PAIR_BLOCK / 32];
-    __shared__ float s_m[PSI_NODE_BLOCK / 32][32][PSI_D + 1];          // odd row pitch: conflict-free
-    if (EPI && *E.done) return;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int slice_local = warp >> 1, role = warp & 1;
-    const int node = blockIdx.x * PSI_NODE_BLOCK + slice_local * 32 + lane;
-    const bool valid = node < G.n_compute;
-    float hi[PSI_D], fx[PSI_D];
-    if (valid) load_row(h, node, hi);
-    if (role == 1 && valid) {
-        float m[PSI_D];
-        second_aggregate<KIND>(G, h, node, hi, m);
-#pragma unroll
-        for (int o = 0; o < PSI_D; ++o) s_m[slice_local][lane][o] = m[o];
-    }
-    __syncthreads();
-    const bool worker = valid && role == 0;
-    if (worker) {
-        node_forward<KIND, true>(G, h, h0, node, hi, &s_m[slice_local][lane][0], fx);
-        if (!EPI || out != nullptr) store_row(out, node, fx);
-    }
-    if (EPI) solver_epilogue<PSI_PAIR_BLOCK / 32>(E, node, worker, hi, fx, smem);
 }
 
 // ---- encoder / decoder (model.py:370-389) --------------------------------------------------------

@@ -15,7 +15,6 @@
 #include "comm.cuh"
 
 #include <algorithm>
-#include <cstdlib>
 #include <cstring>
 #include <cmath>
 #include <limits>
@@ -224,27 +223,10 @@ static int check_kind(const psi_graph* g, int kind) {
 // ================================================================================================
 // layer / VJP / residual / encoder / decoder
 // ================================================================================================
-// nodes up to which the two-warps-per-slice variant is used (about one wave of the one-thread-per-node kernel); PSI_LAYER_PAIR_MAX
-// overrides it (0 disables) — used by the parity test that checks the two kernels against each other bit for bit
-static int64_t layer_pair_max() {
-    const char* e = getenv("PSI_LAYER_PAIR_MAX");
-    return e != nullptr ? atoll(e) : 65536;
-}
-
 template <bool EPI>
 static int launch_layer(const psi_graph* g, int kind, const float* h, const float* h0, float* out, SolverEpi E, cudaStream_t st) {
     if (g->dev.n_compute == 0) return 0;
     const unsigned grid = node_grid(g->dev.n_compute);
-    if (g->dev.n_compute <= layer_pair_max()) {
-        switch (kind) {
-            case PSI_KIND_DIRICHLET: k_layer_forward_pair<KIND_DIRICHLET, EPI><<<grid, PSI_PAIR_BLOCK, 0, st>>>(g->dev, h, h0, out, E); break;
-            case PSI_KIND_MIXED:     k_layer_forward_pair<KIND_MIXED, EPI><<<grid, PSI_PAIR_BLOCK, 0, st>>>(g->dev, h, h0, out, E); break;
-            case PSI_KIND_DSS:       k_layer_forward_pair<KIND_DSS, EPI><<<grid, PSI_PAIR_BLOCK, 0, st>>>(g->dev, h, h0, out, E); break;
-            default:                 k_layer_forward_pair<KIND_DSGPS, EPI><<<grid, PSI_PAIR_BLOCK, 0, st>>>(g->dev, h, h0, out, E); break;
-        }
-        PSI_CK_LAUNCH();
-        return 0;
-    }
     switch (kind) {
         case PSI_KIND_DIRICHLET: k_layer_forward<KIND_DIRICHLET, EPI><<<grid, PSI_NODE_BLOCK, 0, st>>>(g->dev, h, h0, out, E); break;
         case PSI_KIND_MIXED:     k_layer_forward<KIND_MIXED, EPI><<<grid, PSI_NODE_BLOCK, 0, st>>>(g->dev, h, h0, out, E); break;

@@ -735,32 +735,3 @@ def test_broyden_linear_operator_tracks_fp64_oracle(rows):
     else:
         xs = ref["result"].reshape(-1)
     assert float((out["result"].double().cpu().reshape(-1) - xs).norm() / xs.norm()) < 2e-5
-
-
-def test_pair_layer_kernel_is_bit_identical(monkeypatch):
-    """k_layer_forward_pair (two warps per 32-node slice, used up to 64 k nodes) against k_layer_forward (one thread per node):
-    same operations in the same order ⇒ bit-identical layer outputs, norm partials and therefore whole solves; all four kinds."""
-    import os
-    from psi_gnn_b200 import solver as S
-    for name in ("dirichlet_ckpt", "mixed_ckpt"):
-        g = Golden(name)
-        m = g.model(DEV)
-        b = g.batch(DEV)
-        h0 = g.t("h0", DEV)
-        res = {}
-        for mode, val in (("pair", "1000000000"), ("single", "0")):
-            monkeypatch.setenv("PSI_LAYER_PAIR_MAX", val)
-            with torch.no_grad():
-                f1 = m.deqdss.f(h0, h0, b)
-            out = S.broyden(S.LayerOperator(m.deqdss.f, h0, b), h0, threshold=60, eps=1e-30)
-            res[mode] = (f1, out)
-        assert torch.equal(res["pair"][0], res["single"][0])
-        assert res["pair"][1]["rel_trace"] == res["single"][1]["rel_trace"]
-        assert torch.equal(res["pair"][1]["result"], res["single"][1]["result"])
-    for name in ("dss_ckpt", "dsgps_ckpt"):
-        g, m, b = _baseline(name)
-        us = []
-        for val in ("1000000000", "0"):
-            monkeypatch.setenv("PSI_LAYER_PAIR_MAX", val)
-            us.append(m.inference(b))
-        assert torch.equal(us[0], us[1])
