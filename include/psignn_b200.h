@@ -8,6 +8,7 @@
  *   mixed/psignn/model.py:216-245       Function.forward (mixed)  -> psi_layer_forward (kind 1)
  *   dirichlet/dss/model.py:113-121      DSS layer                 -> psi_layer_forward (kind 2)
  *   dirichlet/dsgps/model.py:143-163    DSGPS recurrent step      -> psi_layer_forward (kind 3)
+ *   mixed/dsgps/model.py:76-97          DSGPS step, mixed BCs     -> psi_layer_forward (kind 4)
  *   dirichlet/psignn/model.py:214       autograd.grad(f(H*),H*,y) -> psi_vjp_prepare / psi_vjp_apply
  *   dirichlet/psignn/model.py:157-167   residual_loss             -> psi_residual
  *   dirichlet/psignn/model.py:370-389   Encoder / Decoder         -> psi_encode / psi_decode
@@ -44,6 +45,7 @@ extern "C" {
 #define PSI_KIND_MIXED     1   /* mixed/psignn:     + Neumann branch, prb 3, unit normals 2                 */
 #define PSI_KIND_DSS       2   /* dirichlet/dss:    edge attr 1, b' 3, H += alpha*Psi, no LN, no clamp      */
 #define PSI_KIND_DSGPS     3   /* dirichlet/dsgps:  GRU-style gate, Dirichlet clamp                         */
+#define PSI_KIND_DSGPS_MIXED 4 /* mixed/dsgps:      + Neumann overwrite (phi_neumann, update_neumann), prb 3, unit normals 2 */
 
 typedef struct psi_graph  psi_graph_t;    /* re-laid-out batch of meshes (destination-sorted, warp-sliced CSR) */
 typedef struct psi_solver psi_solver_t;   /* fixed-point solver workspace (iterate, residual, U/V history)      */
@@ -166,14 +168,30 @@ int psi_broyden_forced_step(psi_solver_t* s, int n, const float* dev_x, const fl
                             const float* dev_U /* [n-1, numel] */, const float* dev_V /* [n-1, numel] */,
                             float* dev_u, float* dev_v, float* dev_update, void* stream);
 
-/* Anderson(m) (solver.py:215-293) and Picard iteration (solver.py:301-341) on the layer operator */
+/* Anderson(m) (solver.py:215-293) and Picard iteration (solver.py:301-341) on the layer operator.
+ * dev_xtrace: optional [(threshold+2), stride] device buffer receiving the reference's xest_trace (Anderson: x0, then the best
+ * iterate so far after every step; Picard: every iterate) or NULL. */
 int psi_solver_anderson(psi_solver_t* s, psi_graph_t* g, int kind, const float* dev_x0, const float* dev_h0,
                         int m, double lam, int threshold, double eps, double beta,
                         float* dev_result, psi_solve_stats_t* stats, double* rel_trace, double* abs_trace,
-                        void* stream);
+                        float* dev_xtrace, void* stream);
 int psi_solver_picard(psi_solver_t* s, psi_graph_t* g, int kind, const float* dev_x0, const float* dev_h0,
                       int threshold, double eps, float* dev_result, psi_solve_stats_t* stats,
-                      double* rel_trace, double* abs_trace, void* stream);
+                      double* rel_trace, double* abs_trace, float* dev_xtrace, void* stream);
+/* Step APIs of the same kernels for an arbitrary (e.g. Python) operator — the callable form of
+ * anderson(f, x0, ...) / forward_iteration(f, z0, ...):
+ *   begin(x0) ; loop { fx = f(psi_*_x()) ; psi_*_feed(fx, &done) } until done ; finish */
+int psi_anderson_begin(psi_solver_t* s, const float* dev_x0, int m, double lam, int threshold, double eps, double beta,
+                       float* dev_xtrace, void* stream);
+const float* psi_anderson_x(const psi_solver_t* s);               /* device pointer of the point to evaluate next */
+int psi_anderson_feed(psi_solver_t* s, const float* dev_fx, int* done, void* stream);
+int psi_anderson_finish(psi_solver_t* s, float* dev_result, psi_solve_stats_t* stats, double* rel_trace, double* abs_trace,
+                        void* stream);
+int psi_picard_begin(psi_solver_t* s, const float* dev_z0, int threshold, double eps, float* dev_xtrace, void* stream);
+const float* psi_picard_x(const psi_solver_t* s);
+int psi_picard_feed(psi_solver_t* s, const float* dev_fx, int* done, void* stream);
+int psi_picard_finish(psi_solver_t* s, float* dev_result, psi_solve_stats_t* stats, double* rel_trace, double* abs_trace,
+                      void* stream);
 
 #ifdef __cplusplus
 }

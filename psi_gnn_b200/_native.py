@@ -21,7 +21,7 @@ class SolveStats(ctypes.Structure):
                 ("stop_reason", c_int32), ("f_evals", c_int32), ("launches", c_int32)]
 
 
-KIND_DIRICHLET, KIND_MIXED, KIND_DSS, KIND_DSGPS = 0, 1, 2, 3
+KIND_DIRICHLET, KIND_MIXED, KIND_DSS, KIND_DSGPS, KIND_DSGPS_MIXED = 0, 1, 2, 3, 4
 OP_LAYER, OP_VJP = 0, 1
 
 # name -> (restype, argtypes); every symbol include/psignn_b200.h declares
@@ -63,9 +63,17 @@ SIGNATURES = {
     "psi_broyden_forced_step": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                         c_void_p, c_void_p, c_void_p, c_void_p]),
     "psi_solver_anderson": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_double, c_int, c_double, c_double,
-                                    c_void_p, POINTER(SolveStats), POINTER(c_double), POINTER(c_double), c_void_p]),
+                                    c_void_p, POINTER(SolveStats), POINTER(c_double), POINTER(c_double), c_void_p, c_void_p]),
     "psi_solver_picard": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_double, c_void_p,
-                                  POINTER(SolveStats), POINTER(c_double), POINTER(c_double), c_void_p]),
+                                  POINTER(SolveStats), POINTER(c_double), POINTER(c_double), c_void_p, c_void_p]),
+    "psi_anderson_begin": (c_int, [c_void_p, c_void_p, c_int, c_double, c_int, c_double, c_double, c_void_p, c_void_p]),
+    "psi_anderson_x": (c_void_p, [c_void_p]),
+    "psi_anderson_feed": (c_int, [c_void_p, c_void_p, POINTER(c_int), c_void_p]),
+    "psi_anderson_finish": (c_int, [c_void_p, c_void_p, POINTER(SolveStats), POINTER(c_double), POINTER(c_double), c_void_p]),
+    "psi_picard_begin": (c_int, [c_void_p, c_void_p, c_int, c_double, c_void_p, c_void_p]),
+    "psi_picard_x": (c_void_p, [c_void_p]),
+    "psi_picard_feed": (c_int, [c_void_p, c_void_p, POINTER(c_int), c_void_p]),
+    "psi_picard_finish": (c_int, [c_void_p, c_void_p, POINTER(SolveStats), POINTER(c_double), POINTER(c_double), c_void_p]),
 }
 
 

@@ -8,6 +8,9 @@
 #define PSI_D 10                       // latent width (every shipped reference config)
 #define PSI_NODE_BLOCK 128             // threads per CTA of the node-parallel kernels (4 warp-slices)
 #define PSI_NUM_SMS_B200 148
+#ifndef PSI_OP_MIN_CTAS
+#define PSI_OP_MIN_CTAS 5                // resident CTAs per SM the operator kernels are compiled for (register cap 65536 / (128·5) = 102 → 96)
+#endif
 
 extern thread_local std::string g_psi_err;
 

@@ -64,6 +64,7 @@ struct psi_graph {
     void* p_xm_T = nullptr; void* p_xm_F = nullptr;
     void* p_tag = nullptr; void* p_prb = nullptr; void* p_nrm = nullptr;
     void* p_vjp = nullptr;
+    float* p_q = nullptr;         // [3][N][10] pre-pass scratch of the layer kernel (W1j·h per edge MLP), allocated on first use
     float* p_scratch = nullptr;   // small per-graph scratch for residual partial sums
     struct Partition* part = nullptr;   // set by psi_graph_set_partition (mesh-partitioned solve)
     int64_t scratch_floats = 0;
@@ -74,11 +75,21 @@ struct psi_graph {
 // ------------------------------------------------------------------------------------------------
 
 // key = grouping node (or N for dropped self loops), value = edge id
+// An entry whose row or column lies outside [0, N) is dropped like a self loop (key N) and counted in *bad: the host
+// fails the build with "edge index out of range" (PyG / torch_sparse raise an index error there; gathering h[nb] would
+// otherwise read out of bounds).
 __global__ void k_graph_keys(int64_t nnz, int N, const int64_t* __restrict__ ei, int by_col, int drop_diag,
-                             int* __restrict__ keys, int* __restrict__ vals) {
+                             int* __restrict__ keys, int* __restrict__ vals, int* __restrict__ bad) {
     int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (e >= nnz) return;
-    int r = (int)ei[e], c = (int)ei[nnz + e];
+    const int64_t r64 = ei[e], c64 = ei[nnz + e];
+    if (r64 < 0 || r64 >= N || c64 < 0 || c64 >= N) {
+        atomicAdd(bad, 1);
+        keys[e] = N;
+        vals[e] = (int)e;
+        return;
+    }
+    int r = (int)r64, c = (int)c64;
     int k = by_col ? c : r;
     if (drop_diag && r == c) k = N;
     keys[e] = k;
@@ -195,6 +206,7 @@ static int build_sell(int64_t N, int64_t nnz, const int64_t* ei, const float* at
     const int num_slices = (int)((N + 31) / 32);
     int *keys = nullptr, *vals = nullptr, *skeys = nullptr, *svals = nullptr, *ptr = nullptr;
     int64_t *slice_recs = nullptr, *slice_off = nullptr;
+    int* bad = nullptr;
     void* tmp = nullptr;
     void* recs = nullptr;
     size_t tmp_bytes = 0, tmp2 = 0;
@@ -207,6 +219,8 @@ static int build_sell(int64_t N, int64_t nnz, const int64_t* ei, const float* at
     PSI_CK(T.get((void**)&ptr, (N + 2) * sizeof(int)));
     PSI_CK(T.get((void**)&slice_recs, (num_slices + 1) * sizeof(int64_t)));
     PSI_CK(T.get((void**)&slice_off, (num_slices + 1) * sizeof(int64_t)));
+    PSI_CK(T.get((void**)&bad, sizeof(int)));
+    PSI_CK(cudaMemsetAsync(bad, 0, sizeof(int), st));
     int end_bit = 1;
     while ((1ll << end_bit) <= N) ++end_bit;   // keys in [0, N]
     PSI_CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, skeys, vals, svals, (int)nnz, 0, end_bit, st));
@@ -214,7 +228,7 @@ static int build_sell(int64_t N, int64_t nnz, const int64_t* ei, const float* at
     if (tmp2 > tmp_bytes) tmp_bytes = tmp2;
     PSI_CK(T.get(&tmp, tmp_bytes));
     if (nnz > 0) {
-        k_graph_keys<<<(unsigned)((nnz + 255) / 256), 256, 0, st>>>(nnz, (int)N, ei, by_col ? 1 : 0, msg ? 1 : 0, keys, vals);
+        k_graph_keys<<<(unsigned)((nnz + 255) / 256), 256, 0, st>>>(nnz, (int)N, ei, by_col ? 1 : 0, msg ? 1 : 0, keys, vals, bad);
         PSI_CK_LAUNCH();
         PSI_CK(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, skeys, vals, svals, (int)nnz, 0, end_bit, st));
     }
@@ -227,10 +241,12 @@ static int build_sell(int64_t N, int64_t nnz, const int64_t* ei, const float* at
     }
     PSI_CK(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, slice_recs, slice_off, num_slices + 1, st));
     int64_t total = 0;
-    int kept = 0;
+    int kept = 0, n_bad = 0;
     PSI_CK(cudaMemcpyAsync(&total, slice_off + num_slices, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     PSI_CK(cudaMemcpyAsync(&kept, ptr + N, sizeof(int), cudaMemcpyDeviceToHost, st));
+    PSI_CK(cudaMemcpyAsync(&n_bad, bad, sizeof(int), cudaMemcpyDeviceToHost, st));
     PSI_CK(cudaStreamSynchronize(st));
+    if (n_bad > 0) PSI_FAIL("psi_graph_create: edge index out of range (" + std::to_string(n_bad) + " entries outside [0, num_nodes))");
     const size_t rec_bytes = msg ? sizeof(int4) : sizeof(int2);
     PSI_CK(T.get(&recs, (total > 0 ? total : 1) * rec_bytes));
     PSI_CK(cudaMemsetAsync(recs, 0xFF, (total > 0 ? total : 1) * rec_bytes, st));   // j = -1 everywhere

@@ -41,7 +41,7 @@ extern "C" int psi_weights_upload(const float* dev_blob, int n_floats, void* str
 // ================================================================================================
 static void graph_free(psi_graph* g) {
     void* ps[] = {g->p_recs_T, g->p_recs_F, g->p_recs_Ar, g->p_recs_Ac, g->p_off_T, g->p_off_F, g->p_off_Ar, g->p_off_Ac,
-                  g->p_xm_T, g->p_xm_F, g->p_tag, g->p_prb, g->p_nrm, g->p_vjp, g->p_scratch};
+                  g->p_xm_T, g->p_xm_F, g->p_tag, g->p_prb, g->p_nrm, g->p_vjp, g->p_scratch, g->p_q};
     if (g->part != nullptr) {
         psi_free_async(g->part->send_index, nullptr);
         psi_free_async(g->part->send_buf, nullptr);
@@ -58,7 +58,7 @@ extern "C" int psi_graph_create(psi_graph_t** out, int64_t num_nodes, int64_t nn
     if (out == nullptr) PSI_FAIL("psi_graph_create: null out");
     *out = nullptr;
     if (num_nodes < 0 || nnz < 0) PSI_FAIL("psi_graph_create: negative size");
-    if (num_nodes >= (1ll << 31) - 64 || nnz >= (1ll << 31) - 64) PSI_FAIL("psi_graph_create: graph exceeds int32 indexing");
+    if (3 * num_nodes >= (1ll << 31) - 64 || nnz >= (1ll << 31) - 64) PSI_FAIL("psi_graph_create: graph exceeds int32 indexing");
     if (attr_dim < 1 || attr_dim > 3) PSI_FAIL("psi_graph_create: attr_dim must be 1..3");
     if (prb_dim < 0 || prb_dim > 3) PSI_FAIL("psi_graph_create: prb_dim must be 0..3");
     if (dev_tags != nullptr && tag_dim != 1 && tag_dim != 3) PSI_FAIL("psi_graph_create: tag_dim must be 1 or 3");
@@ -211,10 +211,12 @@ extern "C" int psi_halo_exchange(psi_graph_t* g, float* dev_vec, int width, void
 
 static int check_kind(const psi_graph* g, int kind) {
     if (g == nullptr) PSI_FAIL("null graph handle");
-    if (kind < 0 || kind > 3) PSI_FAIL("unknown layer kind");
-    const int want_prb = (kind == PSI_KIND_MIXED || kind == PSI_KIND_DSS) ? 3 : 2;
+    if (kind < 0 || kind > 4) PSI_FAIL("unknown layer kind");
+    const bool mixed = (kind == PSI_KIND_MIXED || kind == PSI_KIND_DSGPS_MIXED);
+    const int want_prb = (mixed || kind == PSI_KIND_DSS) ? 3 : 2;
     if (g->prb_dim != want_prb) PSI_FAIL("graph second-member width does not match the layer kind");
-    if (kind == PSI_KIND_MIXED && g->p_nrm == nullptr) PSI_FAIL("mixed layer needs unit normals");
+    if (mixed && g->p_nrm == nullptr) PSI_FAIL("mixed layer needs unit normals");
+    if (mixed && g->tag_dim != 3) PSI_FAIL("mixed layer needs 3-column one-hot tags");
     if (kind == PSI_KIND_DSS && g->attr_dim != 1) PSI_FAIL("DSS layer needs 1 edge attribute");
     if (kind != PSI_KIND_DSS && g->attr_dim != 3) PSI_FAIL("layer needs 3 edge attributes");
     return 0;
@@ -223,15 +225,35 @@ static int check_kind(const psi_graph* g, int kind) {
 // ================================================================================================
 // layer / VJP / residual / encoder / decoder
 // ================================================================================================
+// scratch of the layer pre-pass: Q[w][node] = W1j_w·h[node], w < 3 (allocated on first use, lives with the handle)
+static int graph_q(const psi_graph* cg, cudaStream_t st, float** q) {
+    psi_graph* g = const_cast<psi_graph*>(cg);
+    if (g->p_q == nullptr) {
+        const int64_t N1 = g->N > 0 ? g->N : 1;
+        PSI_CK(psi_malloc_async((void**)&g->p_q, (size_t)3 * N1 * PSI_D * sizeof(float), st));
+        g->bytes += 3 * N1 * PSI_D * 4;
+    }
+    *q = g->p_q;
+    return 0;
+}
+
+// one application of the layer = pre-pass (per-source half of the first edge layer) + fused gather/update kernel: 2 launches
 template <bool EPI>
 static int launch_layer(const psi_graph* g, int kind, const float* h, const float* h0, float* out, SolverEpi E, cudaStream_t st) {
     if (g->dev.n_compute == 0) return 0;
+    float* Q = nullptr;
+    if (graph_q(g, st, &Q)) return -1;
     const unsigned grid = node_grid(g->dev.n_compute);
+    const unsigned pre_grid = node_grid(g->N);           // every row that can be a message source (owned + ghost rows)
+    const bool mixed = (kind == PSI_KIND_MIXED || kind == PSI_KIND_DSGPS_MIXED);
+    if (mixed) k_layer_pre<3><<<pre_grid, PSI_NODE_BLOCK, 0, st>>>((int)g->N, h, Q, E.done);
+    else k_layer_pre<2><<<pre_grid, PSI_NODE_BLOCK, 0, st>>>((int)g->N, h, Q, E.done);
     switch (kind) {
-        case PSI_KIND_DIRICHLET: k_layer_forward<KIND_DIRICHLET, EPI><<<grid, PSI_NODE_BLOCK, 0, st>>>(g->dev, h, h0, out, E); break;
-        case PSI_KIND_MIXED:     k_layer_forward<KIND_MIXED, EPI><<<grid, PSI_NODE_BLOCK, 0, st>>>(g->dev, h, h0, out, E); break;
-        case PSI_KIND_DSS:       k_layer_forward<KIND_DSS, EPI><<<grid, PSI_NODE_BLOCK, 0, st>>>(g->dev, h, h0, out, E); break;
-        default:                 k_layer_forward<KIND_DSGPS, EPI><<<grid, PSI_NODE_BLOCK, 0, st>>>(g->dev, h, h0, out, E); break;
+        case PSI_KIND_DIRICHLET:   k_layer_forward<KIND_DIRICHLET, EPI><<<grid, PSI_NODE_BLOCK, 0, st>>>(g->dev, h, h0, Q, out, E); break;
+        case PSI_KIND_MIXED:       k_layer_forward<KIND_MIXED, EPI><<<grid, PSI_NODE_BLOCK, 0, st>>>(g->dev, h, h0, Q, out, E); break;
+        case PSI_KIND_DSS:         k_layer_forward<KIND_DSS, EPI><<<grid, PSI_NODE_BLOCK, 0, st>>>(g->dev, h, h0, Q, out, E); break;
+        case PSI_KIND_DSGPS:       k_layer_forward<KIND_DSGPS, EPI><<<grid, PSI_NODE_BLOCK, 0, st>>>(g->dev, h, h0, Q, out, E); break;
+        default:                   k_layer_forward<KIND_DSGPS_MIXED, EPI><<<grid, PSI_NODE_BLOCK, 0, st>>>(g->dev, h, h0, Q, out, E); break;
     }
     PSI_CK_LAUNCH();
     return 0;
@@ -405,6 +427,7 @@ struct psi_solver {
     int64_t bytes = 0;
     // Anderson window (allocated on first use)
     float* and_X = nullptr; float* and_F = nullptr; float* and_small = nullptr; int and_m = 0;
+    int and_cur_m = 2, and_e = 0; double and_lam = 1e-4, and_beta = 1.0;   // state of the Anderson / Picard step machines
     // state of the step API
     int threshold = 0; double eps = 0.0; int n = 0; int launches = 0; int f_evals = 0; bool active = false;
     float* xtrace = nullptr; int norm_blocks = 0;
@@ -709,7 +732,7 @@ static int op_eval(psi_solver* s, psi_graph* g, int kind, int op, const float* a
     if (g->part != nullptr && halo_exchange(g->part, s->x, PSI_D, &s->ctrl->done, st)) return -1;
     prof_begin(s, step, 0, s->op_bytes, st);
     if (op == PSI_OP_LAYER) {
-        s->launches += 1;
+        s->launches += 2;
         rc = launch_layer<true>(g, kind, s->x, aux, out, E, st);
     } else {
         s->launches += 2;
@@ -858,14 +881,14 @@ extern "C" int psi_broyden_forced_step(psi_solver_t* s, int n, const float* dev_
 // ================================================================================================
 extern "C" int psi_solver_picard(psi_solver_t* s, psi_graph_t* g, int kind, const float* dev_x0, const float* dev_h0, int threshold,
                                  double eps, float* dev_result, psi_solve_stats_t* stats, double* rel_trace, double* abs_trace,
-                                 void* stream) {
+                                 float* dev_xtrace, void* stream) {
     if (s == nullptr) PSI_FAIL("psi_solver_picard: null solver");
     if (check_kind(g, kind)) return -1;
     if (g->N * PSI_D != s->numel) PSI_FAIL("psi_solver_picard: solver workspace size does not match the graph");
     if (g->part != nullptr) PSI_FAIL("psi_solver_picard: mesh-partitioned graphs are solved with psi_solver_broyden");
     if (threshold < 0 || threshold > s->cap) PSI_FAIL("psi_solver_picard: threshold exceeds the solver workspace");
     cudaStream_t st = as_stream(stream);
-    if (qn_begin(s, dev_x0, threshold, eps, nullptr, st)) return -1;
+    if (qn_begin(s, dev_x0, threshold, eps, dev_xtrace, st)) return -1;       // xest_trace[0] = z0 (solver.py:303-304)
     const int norm_blocks = (int)node_grid(g->N);
     int it = 0, evals = 0;
     double last_rel = 0.0;
@@ -880,7 +903,9 @@ extern "C" int psi_solver_picard(psi_solver_t* s, psi_graph_t* g, int kind, cons
             PSI_CK_LAUNCH();
             std::swap(s->x, s->fx);
             ++evals;
-            s->launches += 2;
+            s->launches += 3;
+            if (dev_xtrace != nullptr && evals <= threshold + 1)                  // z_est.append(z) (rows past the stop are never read)
+                PSI_CK(cudaMemcpyAsync(dev_xtrace + (size_t)evals * s->stride, s->x, s->stride * sizeof(float), cudaMemcpyDeviceToDevice, st));
             if (evals % poll == 0 || evals > threshold) {
                 if (qn_poll(s, st)) return -1;
                 done = s->h_ctrl->done != 0;
@@ -912,63 +937,77 @@ extern "C" int psi_solver_picard(psi_solver_t* s, psi_graph_t* g, int kind, cons
 }
 
 // ================================================================================================
-// Anderson acceleration (solver.py:215-293) on the layer operator
+// Anderson acceleration (solver.py:215-293): one state machine serves the fused loop on the layer operator and the step API
+// for an arbitrary operator.  Evaluation e (0-based) reads X[e % m] and writes F[e % m]:
+//   e = 0: X[0] = x0 ; e = 1: X[1] = F[0] ; e = k ≥ 2: X[k % m] = β·Σ α_i F_i + (1−β)·Σ α_i X_i with α from the bordered system.
 // ================================================================================================
-extern "C" int psi_solver_anderson(psi_solver_t* s, psi_graph_t* g, int kind, const float* dev_x0, const float* dev_h0, int m, double lam,
-                                   int threshold, double eps, double beta, float* dev_result, psi_solve_stats_t* stats,
-                                   double* rel_trace, double* abs_trace, void* stream) {
-    if (s == nullptr) PSI_FAIL("psi_solver_anderson: null solver");
-    if (check_kind(g, kind)) return -1;
-    if (g->N * PSI_D != s->numel) PSI_FAIL("psi_solver_anderson: solver workspace size does not match the graph");
-    if (g->part != nullptr) PSI_FAIL("psi_solver_anderson: mesh-partitioned graphs are solved with psi_solver_broyden");
-    if (m < 2 || m > AND_MAX_M) PSI_FAIL("psi_solver_anderson: m must be in [2, 8]");
-    if (threshold < 0 || threshold > s->cap) PSI_FAIL("psi_solver_anderson: threshold exceeds the solver workspace");
-    cudaStream_t st = as_stream(stream);
-    if (s->and_m < m) {
-        if (s->and_X) { cudaFree(s->and_X); cudaFree(s->and_F); cudaFree(s->and_small); s->and_X = s->and_F = s->and_small = nullptr; }
-        if (solver_alloc(s, (void**)&s->and_X, (size_t)m * s->stride * sizeof(float))) return -1;
-        if (solver_alloc(s, (void**)&s->and_F, (size_t)m * s->stride * sizeof(float))) return -1;
-        if (solver_alloc(s, (void**)&s->and_small, (size_t)(AND_MAX_M * AND_MAX_M * (s->num_chunks + 1) + 64) * sizeof(float))) return -1;
-        s->and_m = m;
-    }
-    if (qn_begin(s, dev_x0, threshold, eps, nullptr, st)) return -1;
-    if (g->N > 0) {
+static int and_ensure(psi_solver* s, int m) {
+    if (s->and_m >= m) return 0;
+    if (s->and_X) { cudaFree(s->and_X); cudaFree(s->and_F); cudaFree(s->and_small); s->and_X = s->and_F = s->and_small = nullptr; }
+    if (solver_alloc(s, (void**)&s->and_X, (size_t)m * s->stride * sizeof(float))) return -1;
+    if (solver_alloc(s, (void**)&s->and_F, (size_t)m * s->stride * sizeof(float))) return -1;
+    if (solver_alloc(s, (void**)&s->and_small, (size_t)(AND_MAX_M * AND_MAX_M * (s->num_chunks + 1) + 64) * sizeof(float))) return -1;
+    s->and_m = m;
+    return 0;
+}
+
+static int and_begin(psi_solver* s, const float* x0, int m, double lam, int threshold, double eps, double beta, float* xtrace, cudaStream_t st) {
+    if (m < 2 || m > AND_MAX_M) PSI_FAIL("anderson: m must be in [2, 8]");
+    if (threshold < 0 || threshold > s->cap) PSI_FAIL("anderson: threshold exceeds the solver workspace");
+    if (and_ensure(s, m)) return -1;
+    if (qn_begin(s, x0, threshold, eps, nullptr, st)) return -1;
+    s->xtrace = xtrace;
+    s->and_cur_m = m; s->and_lam = lam; s->and_beta = beta; s->and_e = 0;
+    if (s->numel > 0) {
         const size_t vb = s->stride * sizeof(float);
-        const SolverEpi noE{nullptr, nullptr, nullptr, nullptr};
         PSI_CK(cudaMemsetAsync(s->and_X, 0, (size_t)m * vb, st));
         PSI_CK(cudaMemsetAsync(s->and_F, 0, (size_t)m * vb, st));
-        // X[0] = x0 ; F[0] = f(x0) ; X[1] = F[0] ; F[1] = f(F[0])      (solver.py:227-230)
-        PSI_CK(cudaMemcpyAsync(s->and_X, dev_x0, s->numel * sizeof(float), cudaMemcpyDeviceToDevice, st));
-        if (launch_layer<false>(g, kind, s->and_X, dev_h0, s->and_F, noE, st)) return -1;
-        PSI_CK(cudaMemcpyAsync(s->and_X + s->stride, s->and_F, vb, cudaMemcpyDeviceToDevice, st));
-        if (launch_layer<false>(g, kind, s->and_X + s->stride, dev_h0, s->and_F + s->stride, noE, st)) return -1;
-        s->f_evals = 2; s->launches += 2;
-        float* part = s->and_small;                                    // [n*n][num_chunks]
-        float* alpha = s->and_small + (size_t)AND_MAX_M * AND_MAX_M * s->num_chunks;   // [AND_MAX_M]
-        const int poll = s->numel < (1 << 22) ? 8 : 2;
-        for (int k = 2; k < threshold; ++k) {
-            const int n = std::min(k, m);
-            const int slot = k % m;
-            k_and_gram<<<s->num_chunks, QN_THREADS, 0, st>>>(s->and_X, s->and_F, s->stride, n, part, s->num_chunks, &s->ctrl->done);
-            k_and_solve<<<1, 32, 0, st>>>(part, s->num_chunks, n, (float)lam, alpha, &s->ctrl->done);
-            k_and_mix<<<s->axpy_ctas, QN_THREADS, 0, st>>>(s->and_X, s->and_F, s->stride, n, slot, alpha, (float)beta, s->num_chunks, &s->ctrl->done);
-            PSI_CK_LAUNCH();
-            float* xs = s->and_X + (size_t)slot * s->stride;
-            float* fs = s->and_F + (size_t)slot * s->stride;
-            if (launch_layer<false>(g, kind, xs, dev_h0, fs, noE, st)) return -1;   // overwritten only while !done: guarded below
-            k_and_post<<<s->num_chunks, QN_THREADS, 0, st>>>(xs, fs, s->best, s->norm_part, s->num_chunks, &s->ctrl->done);
-            k_and_fin<<<1, 32, 0, st>>>(s->norm_part, s->num_chunks, s->ctrl, s->rel_trace, s->abs_trace, k, eps);
-            k_and_keep<<<s->axpy_ctas, QN_THREADS, 0, st>>>(xs, s->best, s->num_chunks, s->ctrl);
-            PSI_CK_LAUNCH();
-            s->f_evals += 1; s->launches += 7;
-            if ((k - 1) % poll == 0) {
-                if (qn_poll(s, st)) return -1;
-                if (s->h_ctrl->done) break;
-            }
-        }
+        PSI_CK(cudaMemcpyAsync(s->and_X, x0, s->numel * sizeof(float), cudaMemcpyDeviceToDevice, st));        // X[0] = x0 (solver.py:227)
+        if (xtrace != nullptr) PSI_CK(cudaMemcpyAsync(xtrace, s->and_X, vb, cudaMemcpyDeviceToDevice, st));     // xest_trace[0] = x0 (:243)
     }
+    return 0;
+}
+static inline float* and_in(psi_solver* s) { return s->and_X + (size_t)(s->and_e % s->and_cur_m) * s->stride; }
+static inline float* and_out(psi_solver* s) { return s->and_F + (size_t)(s->and_e % s->and_cur_m) * s->stride; }
+static inline int and_total_evals(const psi_solver* s) { return std::max(s->threshold, 2); }
+
+// bookkeeping after evaluation number s->and_e has been written to and_out(s)
+static int and_advance(psi_solver* s, cudaStream_t st) {
+    const int e = s->and_e, m = s->and_cur_m;
+    const size_t vb = s->stride * sizeof(float);
+    float* xs = and_in(s);
+    float* fs = and_out(s);
+    float* part = s->and_small;                                                           // [n*n][num_chunks]
+    float* alpha = s->and_small + (size_t)AND_MAX_M * AND_MAX_M * s->num_chunks;          // [AND_MAX_M]
+    s->f_evals += 1;
+    if (e == 0) {
+        PSI_CK(cudaMemcpyAsync(s->and_X + s->stride, s->and_F, vb, cudaMemcpyDeviceToDevice, st));             // X[1] = F[0] (:229)
+    } else if (e >= 2) {
+        k_and_post<<<s->num_chunks, QN_THREADS, 0, st>>>(xs, fs, s->best, s->norm_part, s->num_chunks, &s->ctrl->done);
+        k_and_fin<<<1, 32, 0, st>>>(s->norm_part, s->num_chunks, s->ctrl, s->rel_trace, s->abs_trace, e, s->eps);
+        k_and_keep<<<s->axpy_ctas, QN_THREADS, 0, st>>>(xs, s->best, s->num_chunks, s->ctrl);
+        PSI_CK_LAUNCH();
+        s->launches += 3;
+        if (s->xtrace != nullptr)                                                          // xest_trace.append(lowest_xest) (:273)
+            PSI_CK(cudaMemcpyAsync(s->xtrace + (size_t)(e - 1) * s->stride, s->best, vb, cudaMemcpyDeviceToDevice, st));
+    }
+    s->and_e = e + 1;
+    const int k = s->and_e;
+    if (k >= 2 && k < s->threshold) {
+        const int n = std::min(k, m);
+        k_and_gram<<<s->num_chunks, QN_THREADS, 0, st>>>(s->and_X, s->and_F, s->stride, n, part, s->num_chunks, &s->ctrl->done);
+        k_and_solve<<<1, 32, 0, st>>>(part, s->num_chunks, n, (float)s->and_lam, alpha, &s->ctrl->done);
+        k_and_mix<<<s->axpy_ctas, QN_THREADS, 0, st>>>(s->and_X, s->and_F, s->stride, n, k % m, alpha, (float)s->and_beta, s->num_chunks, &s->ctrl->done);
+        PSI_CK_LAUNCH();
+        s->launches += 3;
+    }
+    return 0;
+}
+
+static int and_finish(psi_solver* s, float* dev_result, psi_solve_stats_t* stats, double* rel_trace, double* abs_trace, cudaStream_t st) {
     if (qn_poll(s, st)) return -1;
     const QnCtrl& c = *s->h_ctrl;
+    const int threshold = s->threshold;
     const int ran = c.nstep >= 2 ? c.nstep - 1 : 0;       // trace entries written (k = 2 .. nstep)
     if (dev_result != nullptr && s->numel > 0)
         PSI_CK(cudaMemcpyAsync(dev_result, s->best, s->numel * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -986,6 +1025,108 @@ extern "C" int psi_solver_anderson(psi_solver_t* s, psi_graph_t* g, int kind, co
         PSI_CK(cudaStreamSynchronize(st));
         const double low = which == 0 ? c.best_rel : c.best_abs;
         for (int i = 0; i < threshold + 1; ++i) dst[i] = i < ran ? tmp[i] : (i < len ? low : std::numeric_limits<double>::quiet_NaN());
+    }
+    PSI_CK(cudaStreamSynchronize(st));
+    s->active = false;
+    return 0;
+}
+
+extern "C" int psi_solver_anderson(psi_solver_t* s, psi_graph_t* g, int kind, const float* dev_x0, const float* dev_h0, int m, double lam,
+                                   int threshold, double eps, double beta, float* dev_result, psi_solve_stats_t* stats,
+                                   double* rel_trace, double* abs_trace, float* dev_xtrace, void* stream) {
+    if (s == nullptr) PSI_FAIL("psi_solver_anderson: null solver");
+    if (check_kind(g, kind)) return -1;
+    if (g->N * PSI_D != s->numel) PSI_FAIL("psi_solver_anderson: solver workspace size does not match the graph");
+    if (g->part != nullptr) PSI_FAIL("psi_solver_anderson: mesh-partitioned graphs are solved with psi_solver_broyden");
+    cudaStream_t st = as_stream(stream);
+    if (and_begin(s, dev_x0, m, lam, threshold, eps, beta, dev_xtrace, st)) return -1;
+    if (g->N > 0) {
+        const SolverEpi noE{nullptr, nullptr, nullptr, nullptr};
+        const int poll = s->numel < (1 << 22) ? 8 : 2;
+        while (s->and_e < and_total_evals(s)) {
+            if (launch_layer<false>(g, kind, and_in(s), dev_h0, and_out(s), noE, st)) return -1;   // a no-op write target once done: guarded by the kernels below
+            s->launches += 2;
+            if (and_advance(s, st)) return -1;
+            if (s->and_e > 2 && (s->and_e - 2) % poll == 0) {
+                if (qn_poll(s, st)) return -1;
+                if (s->h_ctrl->done) break;
+            }
+        }
+    }
+    return and_finish(s, dev_result, stats, rel_trace, abs_trace, st);
+}
+
+// ---- step API (arbitrary operator): begin ; loop { fx = f(psi_anderson_x()) ; psi_anderson_feed(fx) -> done? } ; finish ----------
+extern "C" int psi_anderson_begin(psi_solver_t* s, const float* dev_x0, int m, double lam, int threshold, double eps, double beta,
+                                  float* dev_xtrace, void* stream) {
+    if (s == nullptr) PSI_FAIL("psi_anderson_begin: null solver");
+    return and_begin(s, dev_x0, m, lam, threshold, eps, beta, dev_xtrace, as_stream(stream));
+}
+extern "C" const float* psi_anderson_x(const psi_solver_t* s) {
+    return (s && s->and_X) ? s->and_X + (size_t)(s->and_e % s->and_cur_m) * s->stride : nullptr;
+}
+extern "C" int psi_anderson_feed(psi_solver_t* s, const float* dev_fx, int* done, void* stream) {
+    if (s == nullptr || !s->active) PSI_FAIL("psi_anderson_feed: call psi_anderson_begin first");
+    cudaStream_t st = as_stream(stream);
+    if (s->numel == 0 || s->and_e >= and_total_evals(s)) { if (done) *done = 1; return 0; }
+    if (dev_fx == nullptr) PSI_FAIL("psi_anderson_feed: null operator output");
+    PSI_CK(cudaMemcpyAsync(and_out(s), dev_fx, s->numel * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (and_advance(s, st)) return -1;
+    if (done != nullptr) {
+        *done = 0;
+        if (s->and_e > 2) { if (qn_poll(s, st)) return -1; *done = s->h_ctrl->done; }
+        if (s->and_e >= and_total_evals(s)) *done = 1;
+    }
+    return 0;
+}
+extern "C" int psi_anderson_finish(psi_solver_t* s, float* dev_result, psi_solve_stats_t* stats, double* rel_trace, double* abs_trace, void* stream) {
+    if (s == nullptr || !s->active) PSI_FAIL("psi_anderson_finish: call psi_anderson_begin first");
+    return and_finish(s, dev_result, stats, rel_trace, abs_trace, as_stream(stream));
+}
+
+// ---- Picard step API (arbitrary operator): begin ; loop { fx = f(psi_picard_x()) ; psi_picard_feed(fx) -> done? } ; finish ------
+extern "C" int psi_picard_begin(psi_solver_t* s, const float* dev_z0, int threshold, double eps, float* dev_xtrace, void* stream) {
+    if (s == nullptr) PSI_FAIL("psi_picard_begin: null solver");
+    if (threshold < 0 || threshold > s->cap) PSI_FAIL("psi_picard_begin: threshold exceeds the solver workspace");
+    cudaStream_t st = as_stream(stream);
+    if (qn_begin(s, dev_z0, threshold, eps, dev_xtrace, st)) return -1;       // xtrace row 0 = z0
+    s->and_e = 0;
+    return 0;
+}
+extern "C" const float* psi_picard_x(const psi_solver_t* s) { return s ? s->x : nullptr; }
+extern "C" int psi_picard_feed(psi_solver_t* s, const float* dev_fx, int* done, void* stream) {
+    if (s == nullptr || !s->active) PSI_FAIL("psi_picard_feed: call psi_picard_begin first");
+    cudaStream_t st = as_stream(stream);
+    if (s->numel == 0) { if (done) *done = 1; return 0; }
+    if (dev_fx == nullptr) PSI_FAIL("psi_picard_feed: null operator output");
+    // ‖z − z_prev‖², ‖z‖² partials (z = fx, z_prev = x), stop rule, then z becomes the iterate
+    const int nb = (int)((s->numel + QN_THREADS * 4 - 1) / (QN_THREADS * 4));
+    k_qn_post<<<nb, QN_THREADS, 0, st>>>(s->numel, dev_fx, s->x, s->g, s->dg, s->norm_part, &s->ctrl->done);
+    k_picard_fin<<<1, 32, 0, st>>>(s->norm_part, nb, s->ctrl, s->rel_trace, s->abs_trace, s->and_e, (float)s->eps, s->threshold);
+    PSI_CK_LAUNCH();
+    PSI_CK(cudaMemcpyAsync(s->x, dev_fx, s->numel * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (s->xtrace != nullptr)
+        PSI_CK(cudaMemcpyAsync(s->xtrace + (size_t)(s->and_e + 1) * s->stride, dev_fx, s->numel * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    s->and_e += 1; s->f_evals += 1; s->launches += 2;
+    if (qn_poll(s, st)) return -1;
+    if (done != nullptr) *done = s->h_ctrl->done;
+    return 0;
+}
+extern "C" int psi_picard_finish(psi_solver_t* s, float* dev_result, psi_solve_stats_t* stats, double* rel_trace, double* abs_trace, void* stream) {
+    if (s == nullptr || !s->active) PSI_FAIL("psi_picard_finish: call psi_picard_begin first");
+    cudaStream_t st = as_stream(stream);
+    if (qn_poll(s, st)) return -1;
+    const int evals = s->h_ctrl->nstep, threshold = s->threshold;
+    if (dev_result != nullptr && s->numel > 0) PSI_CK(cudaMemcpyAsync(dev_result, s->x, s->numel * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (stats != nullptr) {
+        stats->lowest = s->h_ctrl->best_rel; stats->nstep = std::max(evals - 1, 0); stats->steps_run = std::max(evals - 1, 0); stats->prot_break = 0;
+        stats->stop_reason = (evals - 1 < threshold) ? 1 : 0; stats->f_evals = evals; stats->launches = s->launches;
+    }
+    for (int which = 0; which < 2; ++which) {
+        double* dst = which == 0 ? rel_trace : abs_trace;
+        if (dst == nullptr) continue;
+        for (int i = 0; i < threshold + 1; ++i) dst[i] = std::numeric_limits<double>::quiet_NaN();
+        if (evals > 0) PSI_CK(cudaMemcpyAsync(dst, which == 0 ? s->rel_trace : s->abs_trace, std::min(evals, threshold + 1) * sizeof(double), cudaMemcpyDeviceToHost, st));
     }
     PSI_CK(cudaStreamSynchronize(st));
     s->active = false;

@@ -45,10 +45,11 @@ __device__ __forceinline__ void prepare_list(const GraphDev& G, const SellDev& L
         const int64_t slot = col0 + (int64_t)t * 32;
         const int4 rec = __ldg(L.recs + slot);
         if (rec.x >= 0) {
-            float hj[PSI_D], z[PSI_D];
+            float hj[PSI_D], z[PSI_D], Qv[PSI_D];
             load_row(h, rec.x, hj);
             if (active) {
-                edge_z<OWN, 3>(P, hj, rec, z);
+                edge_q<OWN>(hj, Qv);
+                edge_z<OWN, 3>(P, Qv, rec, z);
 #pragma unroll
                 for (int o = 0; o < PSI_D; ++o) {
                     S[o] += fmaxf(z[o], 0.f);
@@ -64,18 +65,21 @@ __device__ __forceinline__ void prepare_list(const GraphDev& G, const SellDev& L
                 if (!(tj & 1)) {
                     if (KIND == KIND_MIXED && (tj & 2)) {
                         edge_pre<2>(hj, Pj);
-                        edge_z<2, 3>(Pj, hi, rec, z);
+                        edge_q<2>(hi, Qv);
+                        edge_z<2, 3>(Pj, Qv, rec, z);
                         xm = relu_bits(z) | (1u << 10);
                     } else {
                         edge_pre<1>(hj, Pj);
-                        edge_z<1, 3>(Pj, hi, rec, z);
+                        edge_q<1>(hi, Qv);
+                        edge_z<1, 3>(Pj, Qv, rec, z);
                         xm = relu_bits(z);
                     }
                 }
             } else {                               // neighbour j = col: destination of Phi_to
                 if (!(tj & 1) && !(KIND == KIND_MIXED && (tj & 2))) {
                     edge_pre<0>(hj, Pj);
-                    edge_z<0, 3>(Pj, hi, rec, z);
+                    edge_q<0>(hi, Qv);
+                    edge_z<0, 3>(Pj, Qv, rec, z);
                     xm = relu_bits(z);
                 }
             }
@@ -269,86 +273,94 @@ k_vjp_phase_a(GraphDev G, VjpCacheDev C, const float* __restrict__ y, const int*
         (void)PRB;
     }
     store_row(C.Dloc, node, D);
-    store_row(C.Sb, (int64_t)node * 2 + 0, SbT);
-    store_row(C.Sb, (int64_t)node * 2 + 1, SbF);
+    store_row(C.Sb, node, SbT);                       // planar [2][N][10]: the gathers of phase B read contiguous rows
+    store_row(C.Sb, (int64_t)G.N + node, SbF);
+}
+
+// walk of one {neighbour, cross mask} list (written by k_vjp_prepare) with the cooperative row gather of layer.cuh.  WARP-UNIFORM.
+template <class RowIdx, class Body>
+__device__ __forceinline__ void walk_xmask(const SellDev& L, const float* src, int slice, int lane, float* st, const CoopMap& M,
+                                           RowIdx&& rowidx_of, Body&& body) {
+    const int64_t base = L.slice_off[slice];
+    const int width = (int)((L.slice_off[slice + 1] - base) >> 5);
+    if (width == 0) return;
+    const int2* p = reinterpret_cast<const int2*>(L.xmask) + base + lane;
+    const int2 none = make_int2(-1, 0);
+    int2 r0 = p[0];
+    int2 r1 = (width > 1) ? p[32] : none;
+    int i0 = r0.y ? rowidx_of(r0) : -1;
+    float2 v[5];
+    coop_issue_rw(src, i0, M, v);
+    for (int t = 0; t < width; ++t) {
+        coop_store(st, M, v);
+        __syncwarp();
+        const int2 r2 = (t + 2 < width) ? p[(int64_t)(t + 2) * 32] : none;
+        const int i1 = r1.y ? rowidx_of(r1) : -1;
+        if (t + 1 < width) coop_issue_rw(src, i1, M, v);
+        float q[PSI_D];
+        coop_row(st, lane, q);
+        __syncwarp();
+        if (i0 >= 0) body((uint32_t)r0.y, q);
+        r0 = r1; r1 = r2; i0 = i1;
+    }
 }
 
 template <int KIND, bool EPI>
-__global__ void __launch_bounds__(PSI_NODE_BLOCK)
+__global__ void __launch_bounds__(PSI_NODE_BLOCK, PSI_OP_MIN_CTAS)
 k_vjp_phase_b(GraphDev G, VjpCacheDev C, const float* __restrict__ y, const float* __restrict__ grad,
               float* __restrict__ out, SolverEpi E) {
+    __shared__ __align__(16) float stage[(PSI_NODE_BLOCK / 32) * PSI_STAGE_FLOATS];
     __shared__ float smem[2 * PSI_NODE_BLOCK / 32];
     if (EPI && *E.done) return;
     const int node = blockIdx.x * PSI_NODE_BLOCK + threadIdx.x;
-    const bool valid = node < G.N;
+    const int lane = threadIdx.x & 31;
+    const bool valid = node < G.n_compute;
     float yi[PSI_D], res[PSI_D];
-    if (valid) {
+#pragma unroll
+    for (int o = 0; o < PSI_D; ++o) { yi[o] = 0.f; res[o] = 0.f; }
+    if ((node & ~31) < G.n_compute) {                  // warp-uniform
         float accT[PSI_D], accF[PSI_D], accN[PSI_D];
 #pragma unroll
         for (int o = 0; o < PSI_D; ++o) { accT[o] = 0.f; accF[o] = 0.f; accN[o] = 0.f; }
-        // Both loops gather S̄ of the destination over the *other* list.  {neighbour, cross mask} pairs are read four slots at a
-        // time and the four S̄ rows are requested together: two dependent round trips per four edges instead of eight.
-        {   // row list of this node: edges (node, c) — node is the source of Phi_to messages into c
-            const SellDev& L = G.F;
-            const int64_t base = L.slice_off[node >> 5];
-            const int width = (int)((L.slice_off[(node >> 5) + 1] - base) >> 5);
-            const int2* xp = reinterpret_cast<const int2*>(L.xmask) + base + (node & 31);
-            for (int t0 = 0; t0 < width; t0 += 4) {
-                int2 jm[4];
+        CoopMap M;
+        coop_map(lane, M);
+        float* st = stage + (threadIdx.x >> 5) * PSI_STAGE_FLOATS;
+        const int slice = node >> 5;
+        const int N = G.N;
+        // Both walks gather S̄ of the destination over the *other* list: scatter of reverse-mode autograd turned into a gather.
+        // row list of this node: edges (node, c) — node is the source of Phi_to messages into c
+        walk_xmask(G.F, C.Sb, slice, lane, st, M,
+                   [&](const int2& jm) { return valid ? jm.x : -1; },
+                   [&](uint32_t xm, const float (&sb)[PSI_D]) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) jm[q] = (t0 + q < width) ? xp[(int64_t)(t0 + q) * 32] : make_int2(-1, 0);
-                float sb[4][PSI_D];
+                       for (int o = 0; o < PSI_D; ++o) accT[o] += ((xm >> o) & 1u) ? sb[o] : 0.f;
+                   });
+        // column list: edges (r, node) — node is the source of Phi_from / phi_neumann messages into r
+        walk_xmask(G.T, C.Sb, slice, lane, st, M,
+                   [&](const int2& jm) { return valid ? N + jm.x : -1; },
+                   [&](uint32_t xm, const float (&sb)[PSI_D]) {
+                       if (KIND == KIND_MIXED && (xm & (1u << 10))) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    if (jm[q].y) load_row_rw(C.Sb, (int64_t)jm[q].x * 2 + 0, sb[q]);
+                           for (int o = 0; o < PSI_D; ++o) accN[o] += ((xm >> o) & 1u) ? sb[o] : 0.f;
+                       } else {
 #pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    if (jm[q].y) {
-                        const uint32_t xm = (uint32_t)jm[q].y;
+                           for (int o = 0; o < PSI_D; ++o) accF[o] += ((xm >> o) & 1u) ? sb[o] : 0.f;
+                       }
+                   });
+        if (valid) {
+            load_row_rw(C.Dloc, node, res);
+            PSI_TMATVEC(cW.to.W1j, accT, res);
+            PSI_TMATVEC(cW.from.W1j, accF, res);
+            if (KIND == KIND_MIXED) { PSI_TMATVEC(cW.neu.W1j, accN, res); }
+            if (grad != nullptr) {
+                float gi[PSI_D];
+                load_row(grad, node, gi);
 #pragma unroll
-                        for (int o = 0; o < PSI_D; ++o) accT[o] += ((xm >> o) & 1u) ? sb[q][o] : 0.f;
-                    }
+                for (int o = 0; o < PSI_D; ++o) res[o] += gi[o];
             }
+            if (EPI) load_row(y, node, yi);
+            else store_row(out, node, res);
         }
-        {   // column list: edges (r, node) — node is the source of Phi_from / phi_neumann messages into r
-            const SellDev& L = G.T;
-            const int64_t base = L.slice_off[node >> 5];
-            const int width = (int)((L.slice_off[(node >> 5) + 1] - base) >> 5);
-            const int2* xp = reinterpret_cast<const int2*>(L.xmask) + base + (node & 31);
-            for (int t0 = 0; t0 < width; t0 += 4) {
-                int2 jm[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) jm[q] = (t0 + q < width) ? xp[(int64_t)(t0 + q) * 32] : make_int2(-1, 0);
-                float sb[4][PSI_D];
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    if (jm[q].y) load_row_rw(C.Sb, (int64_t)jm[q].x * 2 + 1, sb[q]);
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    if (jm[q].y) {
-                        const uint32_t xm = (uint32_t)jm[q].y;
-                        if (KIND == KIND_MIXED && (xm & (1u << 10))) {
-#pragma unroll
-                            for (int o = 0; o < PSI_D; ++o) accN[o] += ((xm >> o) & 1u) ? sb[q][o] : 0.f;
-                        } else {
-#pragma unroll
-                            for (int o = 0; o < PSI_D; ++o) accF[o] += ((xm >> o) & 1u) ? sb[q][o] : 0.f;
-                        }
-                    }
-            }
-        }
-        load_row_rw(C.Dloc, node, res);
-        PSI_TMATVEC(cW.to.W1j, accT, res);
-        PSI_TMATVEC(cW.from.W1j, accF, res);
-        if (KIND == KIND_MIXED) { PSI_TMATVEC(cW.neu.W1j, accN, res); }
-        if (grad != nullptr) {
-            float gi[PSI_D];
-            load_row(grad, node, gi);
-#pragma unroll
-            for (int o = 0; o < PSI_D; ++o) res[o] += gi[o];
-        }
-        if (EPI) load_row(y, node, yi);
-        else store_row(out, node, res);
     }
     if (EPI) solver_epilogue(E, node, valid, yi, res, smem);
 }

@@ -34,9 +34,9 @@ struct LayerWeights {
     float un_b2[PSI_D];
     float ln_g[PSI_D];                                       // LayerNorm affine
     float ln_b[PSI_D];
-    float gz_W[PSI_D][32]; float gz_b[PSI_D];                // DSGPS z_k
-    float gr_W[PSI_D][32]; float gr_b[PSI_D];                // DSGPS r_k
-    float gc_W[PSI_D][32]; float gc_b[PSI_D];                // DSGPS correction
+    float gz_W[PSI_D][33]; float gz_b[PSI_D];                // DSGPS z_k         Linear(3d+s, d), s = 2 (dirichlet) or 3 (mixed)
+    float gr_W[PSI_D][33]; float gr_b[PSI_D];                // DSGPS r_k
+    float gc_W[PSI_D][33]; float gc_b[PSI_D];                // DSGPS correction
     float enc_W1[PSI_D]; float enc_b1[PSI_D];                // encoder 1 -> d -> d
     float enc_W2[PSI_D][PSI_D]; float enc_b2[PSI_D];
     float dec_W1[PSI_D][PSI_D]; float dec_b1[PSI_D];         // decoder d -> d -> 1

@@ -107,6 +107,36 @@ def _cache_slot(batch):
     return d if isinstance(d, dict) else None
 
 
+# batch attributes whose contents psi_graph_create snapshots (deep copies), per layer kind
+_CAPTURED = {
+    N.KIND_DIRICHLET: ("edge_index", "edge_attr", "a_ij", "tags", "prb_data"),
+    N.KIND_DSGPS: ("edge_index", "edge_attr", "a_ij", "tags", "prb_data"),
+    N.KIND_MIXED: ("edge_index", "edge_attr", "a_ij", "tags", "prb_data", "unit_normal_vector"),
+    N.KIND_DSGPS_MIXED: ("edge_index", "edge_attr", "a_ij", "tags", "prb_data", "unit_normal_vector"),
+    N.KIND_DSS: ("edge_index", "a_ij_norm", "a_ij", "b_prime_norm"),
+}
+
+
+def _stamp(batch, kind: int):
+    """identity + in-place version + shape of every tensor the native handle snapshots.  The handle holds deep copies
+    (edge records, a_ij, tags, prb, normals), so a batch whose right-hand side, boundary data or normalisation was reassigned
+    or modified in place while ``edge_index`` stayed the same must rebuild — otherwise the native solves and the live-tensor
+    autograd path would evaluate different functions.  (``t.data`` writes do not bump ``_version``: call :func:`invalidate`.)"""
+    out = []
+    for name in _CAPTURED[kind]:
+        t = getattr(batch, name, None)
+        out.append(None if t is None else (t.data_ptr(), t._version, tuple(t.shape), str(t.device)))
+    return tuple(out)
+
+
+def invalidate(batch) -> None:
+    """drop every cached native graph of ``batch`` (after modifying captured tensors through ``.data`` or other version-less writes)"""
+    slot = _cache_slot(batch)
+    if slot is not None:
+        for k in [k for k in slot if k.startswith("_psi_graph_") or k.startswith("_psi_offdiag")]:
+            del slot[k]
+
+
 def graph_of(batch, kind: int) -> NativeGraph:
     """The (cached) native graph of a batch for a layer kind.
 
@@ -116,16 +146,17 @@ def graph_of(batch, kind: int) -> NativeGraph:
     slot = _cache_slot(batch)
     key = "_psi_graph_%d" % kind
     ei = batch.edge_index
+    stamp = _stamp(batch, kind)
     if slot is not None and key in slot:
-        g, stamp = slot[key]
-        if stamp == (ei.data_ptr(), tuple(ei.shape), ei.device):
+        g, old = slot[key]
+        if old == stamp:
             return g
     if not ei.is_cuda:
         raise RuntimeError("psi_gnn_b200: the batch must live on a CUDA device (no CPU fallback exists)")
     n = int(batch.num_nodes) if getattr(batch, "num_nodes", None) is not None else int(batch.x.shape[0])
     if kind == N.KIND_DSS:
         g = NativeGraph(n, ei, batch.a_ij_norm, getattr(batch, "a_ij", None), None, batch.b_prime_norm)
-    elif kind == N.KIND_MIXED:
+    elif kind in (N.KIND_MIXED, N.KIND_DSGPS_MIXED):
         g = NativeGraph(n, ei, batch.edge_attr, batch.a_ij, batch.tags, batch.prb_data, batch.unit_normal_vector)
     else:
         g = NativeGraph(n, ei, batch.edge_attr, batch.a_ij, batch.tags, batch.prb_data)
@@ -137,5 +168,5 @@ def graph_of(batch, kind: int) -> NativeGraph:
             part.comm = PT.Communicator(ei.device)
         PT.attach(g, part, part.comm)
     if slot is not None:
-        slot[key] = (g, (ei.data_ptr(), tuple(ei.shape), ei.device))
+        slot[key] = (g, stamp)
     return g

