@@ -456,6 +456,33 @@ def run_native_inference(args, rank, local, world, dev, emit_line=True, min_warm
     ws.profile(False)
     e2e()
     ms_e2e = _timed_steps(e2e, args.steps, world, dev, flush)
+    backward = None
+    if one_mesh:
+        # the implicit-adjoint solve y = Jᵀy + grad at the fixed point just found (native VJP kernels; on a partition the ghost rows of
+        # S̄ are exchanged between the two VJP phases), with a deterministic cotangent that is the same function of the global node id at
+        # every GPU count
+        from psi_gnn_b200 import solver as SV
+        gids = np.concatenate([host.partition.owned_global, host.partition.ghost_global]) if getattr(host, "partition", None) is not None \
+            else np.arange(host.num_nodes)
+        gid = torch.from_numpy(gids.astype(np.float32)).to(dev)
+        grad = (1e-3 * torch.sin(0.37 * gid[:, None] + torch.arange(10, device=dev)[None].float())).contiguous()
+        with torch.no_grad():
+            model.inference(dev_batch)
+        h_star = model.deqdss.last_forward["result"]
+        op = SV.VjpOperator(model.deqdss.f, h_star, dev_batch, grad)
+        y0 = torch.zeros_like(grad)
+        bstats = {}
+
+        def bw_solve():
+            o = SV.broyden(op, y0, threshold=cfg["bw_thres"], eps=cfg["bw_tol"])
+            bstats.update(steps_run=o["steps_run"], lowest=o["lowest"], nstep=o["nstep"], launches=o["launches"])
+
+        bw_solve()
+        ms_bw = _timed_steps(bw_solve, max(1, min(args.steps, 2)), world, dev, flush)
+        backward = {"ms_per_solve": round(ms_bw / max(1, min(args.steps, 2)), 3), "steps_run": bstats["steps_run"], "lowest": bstats["lowest"],
+                    "bw_tol": cfg["bw_tol"], "bw_thres": cfg["bw_thres"],
+                    "us_per_step": round(1e3 * ms_bw / max(1, min(args.steps, 2)) / max(bstats["steps_run"], 1), 2),
+                    "cotangent": "1e-3·sin(0.37·global node id + channel)"}
     sec = ms_total / 1e3
     peaks = {}
     try:
@@ -492,6 +519,15 @@ def run_native_inference(args, rank, local, world, dev, emit_line=True, min_warm
                      "alg_bytes_per_launch": round(d["bytes"] / max(d["launches"], 1), 1)},
         "kernels": kernels, "clocks": clocks,
     }
+    if backward is not None:
+        out["backward"] = backward
+    if world > 1 and one_mesh:
+        from psi_gnn_b200 import partition as PT
+        out["comm"] = {"transport": "peer-mapped mailboxes (CUDA IPC over NVLink): halo rows stored into the consumer's memory, inner products "
+                                    "exchanged inside the reduction kernel" if PT.USE_P2P else "grouped ncclSend/ncclRecv + ncclAllReduce",
+                       "halo_rows_sent_rank0": int(len(host.partition.send_index)), "halo_rows_received_rank0": int(n_ghost),
+                       "nvlink_bytes_per_step_rank0": int(len(host.partition.send_index)) * 48 + (world - 1) * 8 * (3 * 60 + 4),
+                       "note": "per Broyden step: 48 B per sent halo row + the 3(n−1)+4 fp64 sums to each other rank (n ≈ 60 on average)"}
     if not emit_line:
         return out
     if rank == 0:

@@ -91,13 +91,25 @@ int psi_graph_info(const psi_graph_t* g, int64_t info[8]);
  * Local numbering of a rank: owned nodes [0, n_owned), then ghost nodes grouped by owning peer in the order of peer_ranks.
  * The graph is created over owned + ghost nodes; after psi_graph_set_partition the operator produces the owned rows only, ghost rows
  * of the iterate are refreshed from their owners before every operator evaluation (ncclSend/ncclRecv on the caller's stream), and the
- * Broyden inner products and norms are all-reduced (2 small fp64 all-reduces per step).  NCCL is resolved with dlopen at run time. */
+ * Broyden inner products and norms are all-reduced (one exchange of 3(n-1)+4 fp64 sums per step).  The backward (VJP) solve exchanges
+ * the ghost rows of S̄ between its two phases instead.  NCCL is resolved with dlopen at run time. */
 int psi_comm_unique_id(char out[128]);                                   /* rank 0; broadcast the bytes to the other ranks */
 int psi_comm_create(psi_comm_t** out, int rank, int world, const char id[128]);
 int psi_comm_destroy(psi_comm_t* c);
 int psi_graph_set_partition(psi_graph_t* g, psi_comm_t* comm, int64_t n_owned, int n_peers, const int32_t* peer_ranks /* host */,
                             const int64_t* send_counts /* host, rows per peer */, const int64_t* recv_counts /* host */,
                             const int32_t* dev_send_index /* device: owned local rows to send, concatenated per peer */, void* stream);
+/* Peer-mapped mailboxes (NVLink/NVSwitch P2P through CUDA IPC): with them the halo rows are stored straight into the consumer's
+ * memory by the producing rank and the Broyden inner products are exchanged and summed inside the reduction kernel — no NCCL call and
+ * no packing kernel inside a solver step.  psi_part_mail_create allocates this rank's block and returns its 64-byte IPC handle and
+ * ghost-row count; after an all-gather of both (host side, e.g. torch.distributed) psi_part_mail_open maps every rank's block.
+ * remote_off[i] = position (rows) of this rank's rows in the ghost order of neighbour i.  Without these calls the partitioned solve
+ * uses grouped ncclSend/ncclRecv + ncclAllReduce. */
+int psi_part_mail_create(psi_graph_t* g, char handle_out[64], int64_t* total_recv_out);
+int psi_part_mail_open(psi_graph_t* g, const char* handles /* [world][64] */, const int64_t* total_recvs /* [world] */,
+                       const int64_t* remote_off /* [n_peers] */);
+/* 1 if a device-side wait of this partition timed out (a peer did not arrive within 4 s): results of that solve are invalid */
+int psi_part_error(const psi_graph_t* g);
 /* refresh the ghost rows of a [N, width] fp32 array (width 2, 10 or 20) from their owners */
 int psi_halo_exchange(psi_graph_t* g, float* dev_vec, int width, void* stream);
 

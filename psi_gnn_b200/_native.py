@@ -39,6 +39,9 @@ SIGNATURES = {
     "psi_comm_destroy": (c_int, [c_void_p]),
     "psi_graph_set_partition": (c_int, [c_void_p, c_void_p, c_int64, c_int, POINTER(c_int32), POINTER(c_int64), POINTER(c_int64), c_void_p, c_void_p]),
     "psi_halo_exchange": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
+    "psi_part_mail_create": (c_int, [c_void_p, ctypes.c_char_p, POINTER(c_int64)]),
+    "psi_part_mail_open": (c_int, [c_void_p, ctypes.c_char_p, POINTER(c_int64), POINTER(c_int64)]),
+    "psi_part_error": (c_int, [c_void_p]),
     "psi_layer_forward": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "psi_layers_unrolled": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "psi_vjp_prepare": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p]),

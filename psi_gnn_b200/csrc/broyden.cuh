@@ -31,6 +31,7 @@ struct QnCtrl {
     int pad_;
     double best_rel, best_abs, first_rel;
     double s, p;         // ⟨v_n,δg⟩, ⟨v_n,g_n⟩ of the current step (debug / forced-step API)
+    int* host_done;      // mapped pinned host word set to 1 when the solve stops: the host reads it without synchronising the stream
 };
 
 struct QnHistory {       // U and V stored as slabs of `slab_vecs` contiguous vectors of `stride` floats
@@ -107,7 +108,10 @@ __device__ __forceinline__ void qn_decide(int lane, double n1, double n2, QnCtrl
             stop = 4;
         }
         if (step >= threshold && stop == 0) stop = 5;      // while nstep < threshold
-        if (stop) { ctrl->stop_reason = stop; ctrl->done = 1; }
+        if (stop) {
+            ctrl->stop_reason = stop; ctrl->done = 1;
+            if (ctrl->host_done != nullptr) { *reinterpret_cast<volatile int*>(ctrl->host_done) = 1; __threadfence_system(); }
+        }
     }
 }
 
@@ -224,7 +228,8 @@ k_qn_post(int64_t numel, const float* __restrict__ fx, const float* __restrict__
     }
 }
 
-__global__ void k_qn_ctrl_init(QnCtrl* ctrl) {
+__global__ void k_qn_ctrl_init(QnCtrl* ctrl, int* host_done) {
+    ctrl->host_done = host_done;
     ctrl->done = 0; ctrl->improved = 0; ctrl->nstep = 0; ctrl->prot_break = 0; ctrl->stop_reason = 0;
     ctrl->best_step_rel = 0; ctrl->best_step_abs = 0; ctrl->pad_ = 0;
     ctrl->best_rel = 1e8; ctrl->best_abs = 1e8; ctrl->first_rel = 0.0; ctrl->s = 0.0; ctrl->p = 0.0;

@@ -65,6 +65,7 @@ struct psi_graph {
     void* p_tag = nullptr; void* p_prb = nullptr; void* p_nrm = nullptr;
     void* p_vjp = nullptr;
     float* p_q = nullptr;         // [3][N][10] pre-pass scratch of the layer kernel (W1j·h per edge MLP), allocated on first use
+    float* p_hstar = nullptr;     // [N][10] private copy of the linearisation point with refreshed ghost rows (mesh-partitioned VJP)
     float* p_scratch = nullptr;   // small per-graph scratch for residual partial sums
     struct Partition* part = nullptr;   // set by psi_graph_set_partition (mesh-partitioned solve)
     int64_t scratch_floats = 0;

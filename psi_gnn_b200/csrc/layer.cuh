@@ -4,11 +4,12 @@
 //                    concatenation [h_i, h_j, a], so its h_j block is a per-SOURCE quantity: the per-edge work
 //                    drops from 130 to 30 FMAs + 10 adds.
 //   k_layer_forward  one thread owns one destination node (one warp = one 32-node slice of the SELL lists):
-//     1. coalesced 16-byte edge records {j, a0, a1, a2}; the 32 neighbour rows Q[j] of a trip are gathered COOPERATIVELY: lane l
-//        loads float2 pieces l, l+32, … of the 32·40 B the warp needs (consecutive pieces of consecutive rows → a few cache lines
-//        per load instead of 32), stages them in shared memory and reads its own row back with two LDS.128 + one LDS.64.  The
-//        gather, not the FMAs, bounds this kernel (ncu: L1 wavefronts, profiles/r02_a_operator.md); rows of trip t+1 are in
-//        flight while trip t is consumed.
+//     1. coalesced 16-byte edge records {j, a0, a1, a2}; the 32 neighbour rows Q[j] of a trip (48-byte padded rows) are gathered
+//        COOPERATIVELY: lane l loads the 16-byte pieces l, l+32, l+64 of the 32·48 B the warp needs (consecutive pieces of
+//        consecutive rows → a few cache lines per load instead of 32), stages them in shared memory and reads its own row back with
+//        two LDS.128 + one LDS.64.  One thread gathering its own row made the kernel L1-wavefront bound (ncu:
+//        profiles/r02_a_operator.md); rows of trip t+1 are in flight while trip t is consumed.
+//     The contractions are packed fp32x2 FMAs (FFMA2: two output channels per issue slot, bit-identical to scalar fma chains).
 //     2. z_e = (P_i + Q_j) + W1a·a_e with P_i = b1 + W1i·h_i hoisted per destination; ReLU; summed per destination in CSR order
 //        (deterministic, no atomics); the second edge layer is applied once to the sum:
 //        Σ_e (W2·relu(z_e) + b2) = W2·Σ_e relu(z_e) + deg·b2
@@ -33,6 +34,23 @@ template <int KIND> struct KindTraits {
     static constexpr bool clamp = (KIND != KIND_DSS);              // Dirichlet rows copied from h0
 };
 
+// ---- packed matrix-vector products ------------------------------------------------------------------------------------
+// acc[q] (output channels 2q, 2q+1) += Σ_{i<NI} WT[i][2q..2q+1] · x[i]: the sequential fma chain over i of the scalar code, two
+// output channels per FFMA2 (the weight pair is one 8-byte constant operand, x[i] a broadcast scalar)
+template <int NI>
+__device__ __forceinline__ void mv2(const float (*WT)[PSI_D], const float* x, f2 (&acc)[PSI_D / 2]) {
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+        const f2 xx = pk(x[i], x[i]);
+#pragma unroll
+        for (int q = 0; q < PSI_D / 2; ++q) acc[q] = ffma2(pk(WT[i][2 * q], WT[i][2 * q + 1]), xx, acc[q]);
+    }
+}
+__device__ __forceinline__ void bias2(const float* b, f2 (&acc)[PSI_D / 2]) {
+#pragma unroll
+    for (int q = 0; q < PSI_D / 2; ++q) acc[q] = pk(b[2 * q], b[2 * q + 1]);
+}
+
 // ---- canonical rounding of the first edge layer -------------------------------------------------------------------
 // Every kernel that needs z (forward, VJP-prepare own and cross masks, parameter gradients) uses exactly these three chains, so
 // that a ReLU decision is the same wherever it is taken:
@@ -40,145 +58,191 @@ template <int KIND> struct KindTraits {
 //   Q[o] =          Σ_i W1j[o][i]·h_src[i]          (fma chain from zero)
 //   z[o] = fma(W1a[o][2], a2, fma(W1a[o][1], a1, fma(W1a[o][0], a0, P[o] + Q[o])))
 template <int WHICH>
-__device__ __forceinline__ void edge_pre(const float (&hd)[PSI_D], float (&P)[PSI_D]) {
-    const EdgeMLP& W = edge_mlp<WHICH>();
-#pragma unroll
-    for (int o = 0; o < PSI_D; ++o) {
-        float z = W.b1[o];
-#pragma unroll
-        for (int i = 0; i < PSI_D; ++i) z = fmaf(W.W1i[o][i], hd[i], z);
-        P[o] = z;
-    }
+__device__ __forceinline__ void edge_pre2(const float (&hd)[PSI_D], f2 (&P)[PSI_D / 2]) {
+    bias2(edge_mlp<WHICH>().b1, P);
+    mv2<PSI_D>(edge_mlp_t<WHICH>().W1iT, hd, P);
 }
 template <int WHICH>
-__device__ __forceinline__ void edge_q(const float (&hs)[PSI_D], float (&Q)[PSI_D]) {
-    const EdgeMLP& W = edge_mlp<WHICH>();
+__device__ __forceinline__ void edge_q2(const float (&hs)[PSI_D], f2 (&Q)[PSI_D / 2]) {
 #pragma unroll
-    for (int o = 0; o < PSI_D; ++o) {
-        float z = 0.f;
-#pragma unroll
-        for (int i = 0; i < PSI_D; ++i) z = fmaf(W.W1j[o][i], hs[i], z);
-        Q[o] = z;
-    }
+    for (int q = 0; q < PSI_D / 2; ++q) Q[q] = pk(0.f, 0.f);
+    mv2<PSI_D>(edge_mlp_t<WHICH>().W1jT, hs, Q);
 }
 template <int WHICH, int ATTR>
-__device__ __forceinline__ void edge_z(const float (&P)[PSI_D], const float (&Q)[PSI_D], const int4& rec, float (&z)[PSI_D]) {
-    const EdgeMLP& W = edge_mlp<WHICH>();
-    const float a0 = __int_as_float(rec.y), a1 = __int_as_float(rec.z), a2 = __int_as_float(rec.w);
+__device__ __forceinline__ void edge_z2(const f2 (&P)[PSI_D / 2], const f2 (&Q)[PSI_D / 2], const int4& rec, f2 (&z)[PSI_D / 2]) {
+    const EdgeMLPT& W = edge_mlp_t<WHICH>();
+    const float a[3] = {__int_as_float(rec.y), __int_as_float(rec.z), __int_as_float(rec.w)};
 #pragma unroll
-    for (int o = 0; o < PSI_D; ++o) {
-        float t = P[o] + Q[o];
-        t = fmaf(W.W1a[o][0], a0, t);
-        if (ATTR > 1) t = fmaf(W.W1a[o][1], a1, t);
-        if (ATTR > 2) t = fmaf(W.W1a[o][2], a2, t);
-        z[o] = t;
-    }
+    for (int q = 0; q < PSI_D / 2; ++q) z[q] = fadd2(P[q], Q[q]);
+    mv2<ATTR>(W.W1aT, a, z);
 }
 // second edge layer on the aggregated hidden sums: mp = W2·S + deg·b2
 template <int WHICH>
 __device__ __forceinline__ void edge_post(const float (&S)[PSI_D], int deg, float (&mp)[PSI_D]) {
-    const EdgeMLP& W = edge_mlp<WHICH>();
     const float fdeg = (float)deg;
+    f2 acc[PSI_D / 2];
+    bias2(edge_mlp<WHICH>().b2, acc);
 #pragma unroll
-    for (int o = 0; o < PSI_D; ++o) {
-        float t = fdeg * W.b2[o];
-#pragma unroll
-        for (int i = 0; i < PSI_D; ++i) t = fmaf(W.W2[o][i], S[i], t);
-        mp[o] = t;
-    }
+    for (int q = 0; q < PSI_D / 2; ++q) acc[q] = fmul2(pk(fdeg, fdeg), acc[q]);
+    mv2<PSI_D>(edge_mlp_t<WHICH>().W2T, S, acc);
+    unpack10(acc, mp);
+}
+// float-array forms (VJP prepare, parameter gradients)
+template <int WHICH>
+__device__ __forceinline__ void edge_pre(const float (&hd)[PSI_D], float (&P)[PSI_D]) {
+    f2 p2[PSI_D / 2];
+    edge_pre2<WHICH>(hd, p2);
+    unpack10(p2, P);
+}
+template <int WHICH>
+__device__ __forceinline__ void edge_q(const float (&hs)[PSI_D], float (&Q)[PSI_D]) {
+    f2 q2[PSI_D / 2];
+    edge_q2<WHICH>(hs, q2);
+    unpack10(q2, Q);
+}
+template <int WHICH, int ATTR>
+__device__ __forceinline__ void edge_z(const float (&P)[PSI_D], const float (&Q)[PSI_D], const int4& rec, float (&z)[PSI_D]) {
+    f2 p2[PSI_D / 2], q2[PSI_D / 2], z2[PSI_D / 2];
+    pack10(P, p2);
+    pack10(Q, q2);
+    edge_z2<WHICH, ATTR>(p2, q2, rec, z2);
+    unpack10(z2, z);
 }
 
-// ---- pre-pass: Q[w][node] = W1j_w · h[node] ------------------------------------------------------------------------
+// ---- pre-pass: Q[w][node] = W1j_w · h[node], rows padded to PSI_QPITCH floats (16-byte aligned rows for the gather) ------------
+// One warp per 32 nodes.  The 32 input rows (1280 contiguous bytes) are read with coalesced 8-byte loads and transposed through
+// shared memory; the output rows go back the same way (coalesced 16-byte stores).
 template <int NQ>
 __global__ void __launch_bounds__(PSI_NODE_BLOCK) k_layer_pre(int N, const float* __restrict__ h, float* __restrict__ Q, const int* __restrict__ done) {
+    __shared__ __align__(16) float stage[(PSI_NODE_BLOCK / 32) * PSI_STAGE_FLOATS];
     if (done != nullptr && *done) return;
-    const int node = blockIdx.x * PSI_NODE_BLOCK + threadIdx.x;
-    if (node >= N) return;
-    float hi[PSI_D], q[PSI_D];
-    load_row(h, node, hi);
-    edge_q<0>(hi, q);
-    store_row(Q, node, q);
-    edge_q<1>(hi, q);
-    store_row(Q, (int64_t)N + node, q);
-    if (NQ > 2) {
-        edge_q<2>(hi, q);
-        store_row(Q, 2 * (int64_t)N + node, q);
+    const int lane = threadIdx.x & 31;
+    const int node0 = blockIdx.x * PSI_NODE_BLOCK + (threadIdx.x & ~31);
+    if (node0 >= N) return;                                        // warp-uniform
+    const int rows = min(32, N - node0);
+    float* st = stage + (threadIdx.x >> 5) * PSI_STAGE_FLOATS;
+    const float2* src = reinterpret_cast<const float2*>(h + (int64_t)node0 * PSI_D);
+#pragma unroll
+    for (int p = 0; p < 5; ++p) {
+        const int k = p * 32 + lane;
+        if (k < rows * 5) reinterpret_cast<float2*>(st)[k] = __ldg(src + k);
+    }
+    __syncwarp();
+    float hi[PSI_D];
+#pragma unroll
+    for (int q = 0; q < PSI_D / 2; ++q) {
+        const float2 t = reinterpret_cast<const float2*>(st)[lane * 5 + q];
+        hi[2 * q] = t.x; hi[2 * q + 1] = t.y;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int w = 0; w < NQ; ++w) {
+        f2 q2[PSI_D / 2];
+        if (w == 0) edge_q2<0>(hi, q2);
+        else if (w == 1) edge_q2<1>(hi, q2);
+        else edge_q2<2>(hi, q2);
+        float q[PSI_D];
+        unpack10(q2, q);
+        float4* row = reinterpret_cast<float4*>(st + lane * PSI_QPITCH);
+        row[0] = make_float4(q[0], q[1], q[2], q[3]);
+        row[1] = make_float4(q[4], q[5], q[6], q[7]);
+        row[2] = make_float4(q[8], q[9], 0.f, 0.f);
+        __syncwarp();
+        float4* dst = reinterpret_cast<float4*>(Q + ((int64_t)w * N + node0) * PSI_QPITCH);
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+            const int k = p * 32 + lane;
+            if (k < rows * 3) dst[k] = reinterpret_cast<const float4*>(st)[k];
+        }
+        __syncwarp();
     }
 }
 
 // ---- cooperative row gather ---------------------------------------------------------------------------------------
-// A trip needs 32 rows of 10 floats (one per lane).  They are fetched as 160 float2 pieces: lane l fetches pieces l + 32p
-// (p = 0..4); piece k belongs to row-slot k / 5 (the lane that wants it), column pair k % 5.  Staged at a 12-float row pitch so
-// that the read-back is 16-byte aligned and bank-conflict free.
-#define PSI_STAGE_PITCH 12
-#define PSI_STAGE_FLOATS (32 * PSI_STAGE_PITCH)
+// A trip needs 32 rows of PSI_QPITCH = 12 floats (one per lane).  They are fetched as 96 16-byte pieces: lane l fetches pieces
+// l + 32p (p = 0..2); piece k belongs to row-slot k / 3 (the lane that wants it), quarter k % 3.  Consecutive lanes read consecutive
+// pieces of consecutive rows: a handful of cache lines per load instruction instead of 32.  The pieces are staged in shared memory
+// in order (conflict-free 16-byte stores); lane l reads its row back at float offset 12·l (conflict-free as well).
+// Latency: rows are requested TWO trips ahead of their use (two rotating register sets), edge records three trips ahead (four
+// sets) — with rows one trip ahead the kernel sat on the long scoreboard 53 % of the time at 18 resident warps per SM (ncu,
+// profiles/r02_a_operator.md); a cp.async (LDGSTS) ring instead of registers doubled the shared-memory wavefronts and was slower.
 struct CoopMap {
-    int r[5];      // lane whose row piece p of this lane belongs to: (32p + lane) / 5
-    int lane;
+    int r[3];      // lane whose row piece p of this lane belongs to: (32p + lane) / 3
+    int c[3];      // quarter of the row: (32p + lane) % 3
 };
 __device__ __forceinline__ void coop_map(int lane, CoopMap& M) {
-    M.lane = lane;
 #pragma unroll
-    for (int p = 0; p < 5; ++p) M.r[p] = (p * 32 + lane) / 5;
+    for (int p = 0; p < 3; ++p) { M.r[p] = (p * 32 + lane) / 3; M.c[p] = (p * 32 + lane) - 3 * M.r[p]; }
 }
-// float offset of piece p inside its source row: 2·((32p + lane) − 5r) ; inside the stage: 12r + that = 2r + 2·lane + 64p
-__device__ __forceinline__ int coop_src_off(const CoopMap& M, int p) { return 2 * (p * 32 + M.lane - 5 * M.r[p]); }
-__device__ __forceinline__ int coop_stage_off(const CoopMap& M, int p) { return 2 * (M.r[p] + M.lane) + 64 * p; }
-// rowidx: the row (in units of 10 floats from `src`) this lane wants for the trip, or −1
-__device__ __forceinline__ void coop_issue(const float* __restrict__ src, int rowidx, const CoopMap& M, float2 (&v)[5]) {
+struct __align__(16) WarpStage {
+    float rows[PSI_STAGE_FLOATS];
+};
+// pub: the row (in units of PSI_QPITCH floats from `src`) this lane wants for the trip, clamped to a valid row (≥ 0)
+__device__ __forceinline__ void coop_issue(const float* __restrict__ src, int pub, const CoopMap& M, float4 (&v)[3]) {
 #pragma unroll
-    for (int p = 0; p < 5; ++p) {
-        const int rr = __shfl_sync(0xffffffffu, rowidx, M.r[p]);
-        v[p] = (rr >= 0) ? __ldg(reinterpret_cast<const float2*>(src + (int64_t)rr * PSI_D + coop_src_off(M, p))) : make_float2(0.f, 0.f);
+    for (int p = 0; p < 3; ++p) {
+        const unsigned rr = (unsigned)__shfl_sync(0xffffffffu, pub, M.r[p]);
+        v[p] = __ldg(reinterpret_cast<const float4*>(src + (size_t)rr * PSI_QPITCH) + M.c[p]);
     }
 }
-// same through the coherent path (for buffers the compiler must not assume read-only)
-__device__ __forceinline__ void coop_issue_rw(const float* src, int rowidx, const CoopMap& M, float2 (&v)[5]) {
+__device__ __forceinline__ void coop_store(float* st, int lane, const float4 (&v)[3]) {
 #pragma unroll
-    for (int p = 0; p < 5; ++p) {
-        const int rr = __shfl_sync(0xffffffffu, rowidx, M.r[p]);
-        v[p] = (rr >= 0) ? *reinterpret_cast<const float2*>(src + (int64_t)rr * PSI_D + coop_src_off(M, p)) : make_float2(0.f, 0.f);
-    }
+    for (int p = 0; p < 3; ++p) reinterpret_cast<float4*>(st)[p * 32 + lane] = v[p];
 }
-__device__ __forceinline__ void coop_store(float* st, const CoopMap& M, const float2 (&v)[5]) {
-#pragma unroll
-    for (int p = 0; p < 5; ++p) *reinterpret_cast<float2*>(st + coop_stage_off(M, p)) = v[p];
+__device__ __forceinline__ void coop_row2(const float* st, int lane, f2 (&q)[PSI_D / 2]) {
+    const float4 a = *reinterpret_cast<const float4*>(st + lane * PSI_QPITCH);
+    const float4 b = *reinterpret_cast<const float4*>(st + lane * PSI_QPITCH + 4);
+    const float2 c = *reinterpret_cast<const float2*>(st + lane * PSI_QPITCH + 8);
+    q[0] = pk(a.x, a.y); q[1] = pk(a.z, a.w); q[2] = pk(b.x, b.y); q[3] = pk(b.z, b.w); q[4] = pk(c.x, c.y);
 }
-__device__ __forceinline__ void coop_row(const float* st, int lane, float (&q)[PSI_D]) {
-    const float4 a = *reinterpret_cast<const float4*>(st + lane * PSI_STAGE_PITCH);
-    const float4 b = *reinterpret_cast<const float4*>(st + lane * PSI_STAGE_PITCH + 4);
-    const float2 c = *reinterpret_cast<const float2*>(st + lane * PSI_STAGE_PITCH + 8);
-    q[0] = a.x; q[1] = a.y; q[2] = a.z; q[3] = a.w; q[4] = b.x; q[5] = b.y; q[6] = b.z; q[7] = b.w; q[8] = c.x; q[9] = c.y;
-}
+template <class REC> __device__ __forceinline__ REC ld_rec(const REC* p);
+template <> __device__ __forceinline__ int4 ld_rec<int4>(const int4* p) { return __ldg(p); }
+template <> __device__ __forceinline__ int2 ld_rec<int2>(const int2* p) { return __ldg(p); }
 
 // Walks the slice column of every lane of the warp over one SELL list.  WARP-UNIFORM: all 32 lanes must call it (the trip count is
-// the slice width).  rowidx_of(j) → row index into `src` or −1 when this lane does not want the row; body(rec, row) is called for
-// every wanted record in CSR order.
+// the slice width).  REC is the record type (int4 message records / int2 {neighbour, mask} pairs); key(rec) → row index into `src`
+// (≥ 0; lanes that do not want a row return 0); body(rec, row) is called UNCONDITIONALLY for every trip — also for the padding
+// records of short columns — so the caller's arithmetic must make those a no-op (the message kernels rely on relu(NaN) =
+// fmaxf(NaN, 0) = 0 with the padding attributes 0xFFFFFFFF = NaN; see aggregate()).  Keeping the body free of divergent control
+// flow saves the reconvergence barriers and a register copy of every accumulator per trip.  The loop is unrolled by four so that
+// the rotation of the register sets costs no moves.
+template <class REC, class Key, class Body>
+__device__ __forceinline__ void walk_ring(const REC* __restrict__ recs, int width, const float* __restrict__ src, int lane, WarpStage& W,
+                                          const CoopMap& M, Key&& key, Body&& body) {
+    if (width == 0) return;
+    const REC* p = recs + lane;
+    float* st = W.rows;
+    REC R[4];
+    float4 v[2][3];
+#pragma unroll
+    for (int m = 0; m < 3; ++m) R[m] = ld_rec(p + 32 * min(m, width - 1));       // clamped: a duplicate of the last record is never consumed
+    R[3] = R[2];
+    coop_issue(src, key(R[0]), M, v[0]);
+    coop_issue(src, key(R[1]), M, v[1]);
+    for (int t0 = 0; t0 < width; t0 += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int t = t0 + u;
+            if (t < width) {                                   // warp-uniform
+                coop_store(st, lane, v[u % 2]);                // rows of trip t (requested at trip t − 2)
+                __syncwarp();
+                R[(u + 3) % 4] = ld_rec(p + 32 * min(t + 3, width - 1));
+                if (t + 2 < width) coop_issue(src, key(R[(u + 2) % 4]), M, v[u % 2]);
+                f2 q[PSI_D / 2];
+                coop_row2(st, lane, q);
+                __syncwarp();
+                body(R[u], q);
+            }
+        }
+    }
+}
+
 template <class RowIdx, class Body>
-__device__ __forceinline__ void walk_list(const SellDev& L, const float* __restrict__ src, int slice, int lane, float* st, const CoopMap& M,
+__device__ __forceinline__ void walk_list(const SellDev& L, const float* __restrict__ src, int slice, int lane, WarpStage& W, const CoopMap& M,
                                           RowIdx&& rowidx_of, Body&& body) {
     const int64_t base = L.slice_off[slice];
     const int width = (int)((L.slice_off[slice + 1] - base) >> 5);
-    if (width == 0) return;
-    const int4* p = L.recs + base + lane;
-    const int4 none = make_int4(-1, 0, 0, 0);
-    int4 r0 = __ldg(p);
-    int4 r1 = (width > 1) ? __ldg(p + 32) : none;
-    int i0 = (r0.x >= 0) ? rowidx_of(r0.x) : -1;
-    float2 v[5];
-    coop_issue(src, i0, M, v);
-    for (int t = 0; t < width; ++t) {
-        coop_store(st, M, v);
-        __syncwarp();
-        const int4 r2 = (t + 2 < width) ? __ldg(p + (int64_t)(t + 2) * 32) : none;
-        const int i1 = (r1.x >= 0) ? rowidx_of(r1.x) : -1;
-        if (t + 1 < width) coop_issue(src, i1, M, v);          // rows of the next trip fly while this one is consumed
-        float q[PSI_D];
-        coop_row(st, lane, q);
-        __syncwarp();
-        if (i0 >= 0) body(r0, q);
-        r0 = r1; r1 = r2; i0 = i1;
-    }
+    walk_ring(L.recs + base, width, src, lane, W, M, [&](const int4& r) { return r.x >= 0 ? rowidx_of(r.x) : 0; }, body);
 }
 
 __device__ __forceinline__ float sigmoidf_acc(float s) { return 1.0f / (1.0f + expf(-s)); }
@@ -205,28 +269,23 @@ __device__ __forceinline__ void layer_norm10(const float (&r)[PSI_D], float (&ou
 template <int PRB>
 __device__ __forceinline__ void update_mlp(const float (&hi)[PSI_D], const float (&mT)[PSI_D], const float (&mF)[PSI_D],
                                            const float (&prb)[3], float (&m)[PSI_D], uint32_t& hmask, float (&hid)[PSI_D]) {
+    f2 acc[PSI_D / 2];
+    bias2(cW.up_b1, acc);
+    mv2<PSI_D>(cWT.up_W1T, hi, acc);
+    mv2<PSI_D>(cWT.up_W1T + PSI_D, mT, acc);
+    mv2<PSI_D>(cWT.up_W1T + 2 * PSI_D, mF, acc);
+    mv2<PRB>(cWT.up_W1T + 3 * PSI_D, prb, acc);
+    float t[PSI_D];
+    unpack10(acc, t);
     hmask = 0;
 #pragma unroll
     for (int o = 0; o < PSI_D; ++o) {
-        float t = cW.up_b1[o];
-#pragma unroll
-        for (int i = 0; i < PSI_D; ++i) t = fmaf(cW.up_W1[o][i], hi[i], t);
-#pragma unroll
-        for (int i = 0; i < PSI_D; ++i) t = fmaf(cW.up_W1[o][PSI_D + i], mT[i], t);
-#pragma unroll
-        for (int i = 0; i < PSI_D; ++i) t = fmaf(cW.up_W1[o][2 * PSI_D + i], mF[i], t);
-#pragma unroll
-        for (int i = 0; i < PRB; ++i) t = fmaf(cW.up_W1[o][3 * PSI_D + i], prb[i], t);
-        if (t > 0.f) hmask |= (1u << o);
-        hid[o] = fmaxf(t, 0.f);
+        if (t[o] > 0.f) hmask |= (1u << o);
+        hid[o] = fmaxf(t[o], 0.f);
     }
-#pragma unroll
-    for (int o = 0; o < PSI_D; ++o) {
-        float t = cW.up_b2[o];
-#pragma unroll
-        for (int i = 0; i < PSI_D; ++i) t = fmaf(cW.up_W2[o][i], hid[i], t);
-        m[o] = t;
-    }
+    bias2(cW.up_b2, acc);
+    mv2<PSI_D>(cWT.up_W2T, hid, acc);
+    unpack10(acc, m);
 }
 template <int PRB>
 __device__ __forceinline__ void update_mlp(const float (&hi)[PSI_D], const float (&mT)[PSI_D], const float (&mF)[PSI_D],
@@ -259,28 +318,23 @@ __device__ __forceinline__ float gate(const float (&hi)[PSI_D], const float (&mT
 // update_neumann: MLP(cat[h, mp_neu, prb(3), normal(2)])  (mixed/psignn/model.py:214,231-232)
 __device__ __forceinline__ void neumann_mlp(const float (&hi)[PSI_D], const float (&mN)[PSI_D], const float (&prb)[3],
                                             const float (&nv)[2], float (&m)[PSI_D], uint32_t& hmask, float (&hid)[PSI_D]) {
+    f2 acc[PSI_D / 2];
+    bias2(cW.un_b1, acc);
+    mv2<PSI_D>(cWT.un_W1T, hi, acc);
+    mv2<PSI_D>(cWT.un_W1T + PSI_D, mN, acc);
+    mv2<3>(cWT.un_W1T + 2 * PSI_D, prb, acc);
+    mv2<2>(cWT.un_W1T + 2 * PSI_D + 3, nv, acc);
+    float t[PSI_D];
+    unpack10(acc, t);
     hmask = 0;
 #pragma unroll
     for (int o = 0; o < PSI_D; ++o) {
-        float t = cW.un_b1[o];
-#pragma unroll
-        for (int i = 0; i < PSI_D; ++i) t = fmaf(cW.un_W1[o][i], hi[i], t);
-#pragma unroll
-        for (int i = 0; i < PSI_D; ++i) t = fmaf(cW.un_W1[o][PSI_D + i], mN[i], t);
-#pragma unroll
-        for (int i = 0; i < 3; ++i) t = fmaf(cW.un_W1[o][2 * PSI_D + i], prb[i], t);
-#pragma unroll
-        for (int i = 0; i < 2; ++i) t = fmaf(cW.un_W1[o][2 * PSI_D + 3 + i], nv[i], t);
-        if (t > 0.f) hmask |= (1u << o);
-        hid[o] = fmaxf(t, 0.f);
+        if (t[o] > 0.f) hmask |= (1u << o);
+        hid[o] = fmaxf(t[o], 0.f);
     }
-#pragma unroll
-    for (int o = 0; o < PSI_D; ++o) {
-        float t = cW.un_b2[o];
-#pragma unroll
-        for (int i = 0; i < PSI_D; ++i) t = fmaf(cW.un_W2[o][i], hid[i], t);
-        m[o] = t;
-    }
+    bias2(cW.un_b2, acc);
+    mv2<PSI_D>(cWT.un_W2T, hid, acc);
+    unpack10(acc, m);
 }
 __device__ __forceinline__ void neumann_mlp(const float (&hi)[PSI_D], const float (&mN)[PSI_D], const float (&prb)[3],
                                             const float (&nv)[2], float (&m)[PSI_D], uint32_t& hmask) {
@@ -306,46 +360,80 @@ __device__ __forceinline__ int node_class(const GraphDev& G, int node, int limit
 }
 
 // Aggregated messages of one node: mT = ΣΦ→ (interior), mF = ΣΦ← (interior) or ΣΦ_neumann (Neumann rows).  WARP-UNIFORM.
+// Lanes that do not aggregate over a list (Dirichlet rows, Neumann rows over list T, rows beyond the produced range) run the same
+// instructions on row 0 and discard the result.  Padding records contribute relu(NaN) = 0 to S and nothing to deg.
 template <int KIND>
-__device__ __forceinline__ void aggregate(const GraphDev& G, const float* __restrict__ Q, int node, int cls, const float (&hi)[PSI_D],
-                                          float* st, const CoopMap& M, float (&mT)[PSI_D], float (&mF)[PSI_D]) {
+__device__ __forceinline__ void aggregate(const GraphDev& G, const float* __restrict__ h, const float* __restrict__ Q, int node, int cls,
+                                          WarpStage& st, const CoopMap& M, float (&mT)[PSI_D], float (&mF)[PSI_D]) {
     constexpr int ATTR = KindTraits<KIND>::ATTR;
+    constexpr bool NEU = KindTraits<KIND>::has_neumann;
     const int lane = threadIdx.x & 31, slice = node >> 5;
     const int N = G.N;
-    float P[PSI_D], S[PSI_D];
+    f2 P[PSI_D / 2], S[PSI_D / 2];
+    float Sf[PSI_D], hi[PSI_D];
     int deg = 0;
+    // S += relu(z): the ReLU has no packed form (two FMNMX), the accumulation has
+    auto relu_acc = [&](const int4& rec, const f2 (&z)[PSI_D / 2]) {
+#pragma unroll
+        for (int q = 0; q < PSI_D / 2; ++q) {
+            float a, b;
+            upk(z[q], a, b);
+            S[q] = fadd2(S[q], pk(fmaxf(a, 0.f), fmaxf(b, 0.f)));
+        }
+        deg += (rec.x >= 0) ? 1 : 0;
+    };
     // ---- list T: messages Φ→ into interior destinations (neighbour = row index of the entry) ----
 #pragma unroll
-    for (int o = 0; o < PSI_D; ++o) { S[o] = 0.f; P[o] = 0.f; }
-    if (cls == 0) edge_pre<0>(hi, P);
+    for (int q = 0; q < PSI_D / 2; ++q) { S[q] = pk(0.f, 0.f); P[q] = pk(0.f, 0.f); }
+    if (cls == 0) {
+        load_row(h, node, hi);                   // re-read per list instead of held across the walks (register pressure)
+        edge_pre2<0>(hi, P);
+    }
     walk_list(G.T, Q, slice, lane, st, M,
-              [&](int j) { return cls == 0 ? j : -1; },
-              [&](const int4& rec, const float (&q)[PSI_D]) {
-                  float z[PSI_D];
-                  edge_z<0, ATTR>(P, q, rec, z);
-#pragma unroll
-                  for (int o = 0; o < PSI_D; ++o) S[o] += fmaxf(z[o], 0.f);
-                  ++deg;
+              [&](int j) { return cls == 0 ? j : 0; },
+              [&](const int4& rec, const f2 (&q)[PSI_D / 2]) {
+                  f2 z[PSI_D / 2];
+                  edge_z2<0, ATTR>(P, q, rec, z);
+                  relu_acc(rec, z);
               });
-    if (cls == 0) edge_post<0>(S, deg, mT);
+    unpack10(S, Sf);
+    if (cls == 0) edge_post<0>(Sf, deg, mT);
+    asm volatile("" ::: "memory");               // keep the compiler from carrying the first read of the row across the walk
     // ---- list F: messages Φ← into interior destinations, Φ_neumann into Neumann destinations ----
 #pragma unroll
-    for (int o = 0; o < PSI_D; ++o) S[o] = 0.f;
+    for (int q = 0; q < PSI_D / 2; ++q) S[q] = pk(0.f, 0.f);
     deg = 0;
-    if (cls == 0) edge_pre<1>(hi, P);
-    if (KindTraits<KIND>::has_neumann && cls == 2) edge_pre<2>(hi, P);
-    walk_list(G.F, Q, slice, lane, st, M,
-              [&](int j) { return cls == 0 ? N + j : ((KindTraits<KIND>::has_neumann && cls == 2) ? 2 * N + j : -1); },
-              [&](const int4& rec, const float (&q)[PSI_D]) {
-                  float z[PSI_D];
-                  if (KindTraits<KIND>::has_neumann && cls == 2) edge_z<2, ATTR>(P, q, rec, z);
-                  else edge_z<1, ATTR>(P, q, rec, z);
-#pragma unroll
-                  for (int o = 0; o < PSI_D; ++o) S[o] += fmaxf(z[o], 0.f);
-                  ++deg;
-              });
-    if (cls == 0) edge_post<1>(S, deg, mF);
-    if (KindTraits<KIND>::has_neumann && cls == 2) edge_post<2>(S, deg, mF);
+    if (cls == 0) {
+        load_row(h, node, hi);
+        edge_pre2<1>(hi, P);
+    }
+    if (NEU && cls == 2) {
+        load_row(h, node, hi);
+        edge_pre2<2>(hi, P);
+    }
+    if (NEU) {
+        // the Neumann rows of a warp use another edge MLP: W1a differs per lane class, so this walk keeps a (divergent) branch
+        walk_list(G.F, Q, slice, lane, st, M,
+                  [&](int j) { return cls == 0 ? N + j : (cls == 2 ? 2 * N + j : 0); },
+                  [&](const int4& rec, const f2 (&q)[PSI_D / 2]) {
+                      f2 z[PSI_D / 2];
+                      if (cls == 2) edge_z2<2, ATTR>(P, q, rec, z);
+                      else edge_z2<1, ATTR>(P, q, rec, z);
+                      relu_acc(rec, z);
+                  });
+    } else {
+        walk_list(G.F, Q, slice, lane, st, M,
+                  [&](int j) { return cls == 0 ? N + j : 0; },
+                  [&](const int4& rec, const f2 (&q)[PSI_D / 2]) {
+                      f2 z[PSI_D / 2];
+                      edge_z2<1, ATTR>(P, q, rec, z);
+                      relu_acc(rec, z);
+                  });
+    }
+    unpack10(S, Sf);
+    if (cls == 0) edge_post<1>(Sf, deg, mF);
+    if (NEU && cls == 2) edge_post<2>(Sf, deg, mF);
+    asm volatile("" ::: "memory");
 }
 
 // GRU-style node update of DSGPS (dirichlet/dsgps/model.py:148-155): H + σ(Z c)·tanh(C·cat[σ(R c)·H, to, from, prb])
@@ -358,23 +446,27 @@ __device__ __forceinline__ void dsgps_update(const float (&hi)[PSI_D], const flo
 #pragma unroll
     for (int i = 0; i < 3; ++i) c[30 + i] = prb[i];
     float zk[PSI_D], rk[PSI_D];
+    {
+        f2 az[PSI_D / 2], ar[PSI_D / 2];
+        bias2(cW.gz_b, az);
+        bias2(cW.gr_b, ar);
+        mv2<30 + PRB>(cWT.gzT, c, az);
+        mv2<30 + PRB>(cWT.grT, c, ar);
+        float a[PSI_D], b[PSI_D];
+        unpack10(az, a);
+        unpack10(ar, b);
 #pragma unroll
-    for (int o = 0; o < PSI_D; ++o) {
-        float a = cW.gz_b[o], b = cW.gr_b[o];
-#pragma unroll
-        for (int i = 0; i < 30 + PRB; ++i) { a = fmaf(cW.gz_W[o][i], c[i], a); b = fmaf(cW.gr_W[o][i], c[i], b); }
-        zk[o] = sigmoidf_acc(a);
-        rk[o] = sigmoidf_acc(b);
+        for (int o = 0; o < PSI_D; ++o) { zk[o] = sigmoidf_acc(a[o]); rk[o] = sigmoidf_acc(b[o]); }
     }
 #pragma unroll
     for (int i = 0; i < PSI_D; ++i) c[i] = rk[i] * hi[i];                       // cat[reset*H, to, from, prb]
+    f2 ac[PSI_D / 2];
+    bias2(cW.gc_b, ac);
+    mv2<30 + PRB>(cWT.gcT, c, ac);
+    float a[PSI_D];
+    unpack10(ac, a);
 #pragma unroll
-    for (int o = 0; o < PSI_D; ++o) {
-        float a = cW.gc_b[o];
-#pragma unroll
-        for (int i = 0; i < 30 + PRB; ++i) a = fmaf(cW.gc_W[o][i], c[i], a);
-        out[o] = fmaf(zk[o], tanhf(a), hi[o]);                                  // H + alpha*corr
-    }
+    for (int o = 0; o < PSI_D; ++o) out[o] = fmaf(zk[o], tanhf(a[o]), hi[o]);   // H + alpha*corr
 }
 
 // One application of the layer for one node (after the aggregation).  `hi` is the node's own row of h.
@@ -458,7 +550,7 @@ template <int KIND, bool EPI>
 __global__ void __launch_bounds__(PSI_NODE_BLOCK, PSI_OP_MIN_CTAS)
 k_layer_forward(GraphDev G, const float* __restrict__ h, const float* __restrict__ h0, const float* __restrict__ Q, float* __restrict__ out,
                 SolverEpi E) {
-    __shared__ __align__(16) float stage[(PSI_NODE_BLOCK / 32) * PSI_STAGE_FLOATS];
+    __shared__ WarpStage stage[PSI_NODE_BLOCK / 32];
     __shared__ float smem[2 * PSI_NODE_BLOCK / 32];
     if (EPI && *E.done) return;
     const int node = blockIdx.x * PSI_NODE_BLOCK + threadIdx.x;
@@ -470,14 +562,14 @@ k_layer_forward(GraphDev G, const float* __restrict__ h, const float* __restrict
     // a warp whose slice lies entirely beyond the produced rows has nothing to gather (warp-uniform condition)
     if ((node & ~31) < G.n_compute) {
         const int cls = node_class<KIND>(G, node, G.n_compute);
-        if (valid) load_row(h, node, hi);
         CoopMap M;
         coop_map(lane, M);
         float mT[PSI_D], mF[PSI_D];
 #pragma unroll
         for (int o = 0; o < PSI_D; ++o) { mT[o] = 0.f; mF[o] = 0.f; }
-        aggregate<KIND>(G, Q, node, cls, hi, stage + (threadIdx.x >> 5) * PSI_STAGE_FLOATS, M, mT, mF);
+        aggregate<KIND>(G, h, Q, node, cls, stage[threadIdx.x >> 5], M, mT, mF);
         if (valid) {
+            load_row(h, node, hi);
             node_update<KIND>(G, h0, node, cls, hi, mT, mF, fx);
             if (!EPI || out != nullptr) store_row(out, node, fx);   // Picard keeps f(x) itself
         }

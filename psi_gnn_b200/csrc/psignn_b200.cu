@@ -27,24 +27,44 @@ static inline unsigned node_grid(int64_t N) { return (unsigned)((N + PSI_NODE_BL
 
 extern "C" int psi_version(void) { return 100; }
 extern "C" const char* psi_last_error(void) { return g_psi_err.c_str(); }
-extern "C" int psi_weights_floats(void) { return (int)(sizeof(LayerWeights) / sizeof(float)); }
+extern "C" int psi_weights_floats(void) { return (int)((sizeof(LayerWeights) + sizeof(LayerWeightsT)) / sizeof(float)); }
+#define PSI_WBLOB_FLOATS ((sizeof(LayerWeights) + sizeof(LayerWeightsT)) / sizeof(float))
+
+// one packed block = LayerWeights followed by LayerWeightsT (the transposed copies for the packed-FMA kernels)
+static int upload_block(const float* dev_blob, cudaStream_t st) {
+    PSI_CK(cudaMemcpyToSymbolAsync(cW, dev_blob, sizeof(LayerWeights), 0, cudaMemcpyDeviceToDevice, st));
+    PSI_CK(cudaMemcpyToSymbolAsync(cWT, dev_blob + sizeof(LayerWeights) / sizeof(float), sizeof(LayerWeightsT), 0, cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
 
 extern "C" int psi_weights_upload(const float* dev_blob, int n_floats, void* stream) {
     if (dev_blob == nullptr) PSI_FAIL("psi_weights_upload: null blob");
     if (n_floats != psi_weights_floats()) PSI_FAIL("psi_weights_upload: blob has the wrong number of floats");
-    PSI_CK(cudaMemcpyToSymbolAsync(cW, dev_blob, sizeof(LayerWeights), 0, cudaMemcpyDeviceToDevice, as_stream(stream)));
-    return 0;
+    return upload_block(dev_blob, as_stream(stream));
 }
 
 // ================================================================================================
 // graph
 // ================================================================================================
+static void part_release(Partition* P) {
+    psi_free_async(P->send_index, nullptr);
+    psi_free_async(P->send_buf, nullptr);
+    if (P->mail != nullptr) {
+        cudaDeviceSynchronize();                       // no kernel of ours may still be writing into a peer's block or reading ours
+        for (int r = 0; r < PSI_MAX_WORLD; ++r)
+            if (P->peer_mail[r] != nullptr && P->peer_mail[r] != P->mail) cudaIpcCloseMemHandle(P->peer_mail[r]);
+        cudaFree(P->mail);
+        if (P->d_peers) cudaFree(P->d_peers);
+        if (P->d_counter) cudaFree(P->d_counter);
+        if (P->d_error) cudaFree(P->d_error);
+    }
+}
+
 static void graph_free(psi_graph* g) {
     void* ps[] = {g->p_recs_T, g->p_recs_F, g->p_recs_Ar, g->p_recs_Ac, g->p_off_T, g->p_off_F, g->p_off_Ar, g->p_off_Ac,
-                  g->p_xm_T, g->p_xm_F, g->p_tag, g->p_prb, g->p_nrm, g->p_vjp, g->p_scratch, g->p_q};
+                  g->p_xm_T, g->p_xm_F, g->p_tag, g->p_prb, g->p_nrm, g->p_vjp, g->p_scratch, g->p_q, g->p_hstar};
     if (g->part != nullptr) {
-        psi_free_async(g->part->send_index, nullptr);
-        psi_free_async(g->part->send_buf, nullptr);
+        part_release(g->part);
         delete g->part;
     }
     for (void* p : ps)
@@ -196,16 +216,123 @@ extern "C" int psi_graph_set_partition(psi_graph_t* g, psi_comm_t* comm, int64_t
             psi_malloc_async((void**)&P->send_buf, P->total_send * 20 * sizeof(float), st) != cudaSuccess) { delete P; PSI_FAIL("psi_graph_set_partition: out of device memory"); }
         PSI_CK(cudaMemcpyAsync(P->send_index, dev_send_index, P->total_send * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
     }
-    if (g->part != nullptr) { psi_free_async(g->part->send_index, st); psi_free_async(g->part->send_buf, st); delete g->part; }
+    if (g->part != nullptr) { part_release(g->part); delete g->part; }
     g->part = P;
     g->dev.n_compute = (int)n_owned;
     return 0;
+}
+
+// ---- peer-mapped mailboxes: create my block (returns its IPC handle), then map every rank's block ------------------------------
+extern "C" int psi_part_mail_create(psi_graph_t* g, char handle_out[64], int64_t* total_recv_out) {
+    if (g == nullptr || g->part == nullptr) PSI_FAIL("psi_part_mail_create: the graph has no partition");
+    Partition* P = g->part;
+    const int world = P->comm->world;
+    if (world > PSI_MAX_WORLD) PSI_FAIL("psi_part_mail_create: world size exceeds PSI_MAX_WORLD");
+    if (P->mail == nullptr) {
+        const size_t bytes = mail_bytes(world, P->total_recv);
+        PSI_CK(cudaMalloc(&P->mail, bytes));
+        PSI_CK(cudaMemset(P->mail, 0, bytes));
+        PSI_CK(cudaMalloc((void**)&P->d_counter, 8 * sizeof(unsigned int)));
+        PSI_CK(cudaMemset(P->d_counter, 0, 8 * sizeof(unsigned int)));
+        PSI_CK(cudaMalloc((void**)&P->d_error, sizeof(int)));
+        PSI_CK(cudaMemset(P->d_error, 0, sizeof(int)));
+        PSI_CK(cudaDeviceSynchronize());
+    }
+    cudaIpcMemHandle_t h;
+    PSI_CK(cudaIpcGetMemHandle(&h, P->mail));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    memcpy(handle_out, &h, 64);
+    if (total_recv_out) *total_recv_out = P->total_recv;
+    return 0;
+}
+
+// handles: [world][64] IPC handles of every rank's block (own entry ignored); total_recvs: [world]; remote_off: [n_peers] = position
+// of MY rows in the ghost order of neighbour i (rows)
+extern "C" int psi_part_mail_open(psi_graph_t* g, const char* handles, const int64_t* total_recvs, const int64_t* remote_off) {
+    if (g == nullptr || g->part == nullptr || g->part->mail == nullptr) PSI_FAIL("psi_part_mail_open: call psi_part_mail_create first");
+    Partition* P = g->part;
+    const int world = P->comm->world, rank = P->comm->rank;
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) { P->peer_mail[r] = P->mail; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles + (size_t)r * 64, 64);
+        PSI_CK(cudaIpcOpenMemHandle(&P->peer_mail[r], h, cudaIpcMemLazyEnablePeerAccess));
+    }
+    std::vector<PeerDev> pd(P->peers.size());
+    for (size_t i = 0; i < P->peers.size(); ++i) {
+        const int q = P->peers[i];
+        char* base = (char*)P->peer_mail[q];
+        MailHeader* hq = (MailHeader*)base;
+        float* xg = (float*)(base + mail_xg_off(world));
+        float* sg = (float*)(base + mail_sg_off(world, total_recvs[q]));
+        pd[i].xg = xg + remote_off[i] * PSI_QPITCH;
+        pd[i].sg0 = sg + remote_off[i] * PSI_QPITCH;
+        pd[i].sg1 = sg + (total_recvs[q] + remote_off[i]) * PSI_QPITCH;
+        pd[i].halo_flag = &hq->halo_seq[rank];
+        pd[i].sb_flag = &hq->sb_seq[rank];
+        pd[i].send_off = (int)P->send_off[i]; pd[i].send_count = (int)P->send_count[i];
+        pd[i].rank = q; pd[i].recv_off = (int)P->recv_off[i]; pd[i].recv_count = (int)P->recv_count[i];
+    }
+    if (P->d_peers) cudaFree(P->d_peers);
+    PSI_CK(cudaMalloc((void**)&P->d_peers, std::max<size_t>(1, pd.size()) * sizeof(PeerDev)));
+    if (!pd.empty()) PSI_CK(cudaMemcpy(P->d_peers, pd.data(), pd.size() * sizeof(PeerDev), cudaMemcpyHostToDevice));
+    PartDev& D = P->dev;
+    D.n_peers = (int)pd.size(); D.rank = rank; D.world = world; D.peers = P->d_peers; D.send_index = P->send_index;
+    D.hdr = (MailHeader*)P->mail;
+    D.xg = (float*)((char*)P->mail + mail_xg_off(world));
+    D.sg = (float*)((char*)P->mail + mail_sg_off(world, P->total_recv));
+    D.total_recv = P->total_recv; D.total_send = P->total_send; D.n_owned = P->n_owned; D.N = g->N;
+    for (int r = 0; r < world; ++r) {
+        char* base = (char*)P->peer_mail[r];
+        D.red_dst[r] = (double*)(base + PSI_MAIL_RED_OFF);
+        D.red_flag_dst[r] = &((MailHeader*)base)->red_seq[0][rank];
+    }
+    D.counter = P->d_counter; D.error = P->d_error;
+    if (D.n_peers > 32) PSI_FAIL("psi_part_mail_open: more than 32 neighbour ranks");
+    P->p2p = true;
+    return 0;
+}
+
+// 1 if a device-side exchange of this partition timed out (the peers did not arrive): the solve's results are invalid
+extern "C" int psi_part_error(const psi_graph_t* g) {
+    if (g == nullptr || g->part == nullptr || g->part->d_error == nullptr) return 0;
+    int e = 0;
+    cudaMemcpy(&e, g->part->d_error, sizeof(int), cudaMemcpyDeviceToHost);
+    return e;
+}
+
+// ghost rows of the iterate (which = 0, [N,10] rows) or of the two S̄ planes (which = 1, [2][N][12]) from their owners
+static int halo_refresh(psi_graph* g, float* vec, int which, const int* done, cudaStream_t st) {
+    Partition* P = g->part;
+    if (P == nullptr || P->comm == nullptr || P->peers.empty()) return 0;
+    if (P->p2p) {
+        PartDev D = P->dev;
+        D.N = g->N;
+        if (which == 0) {
+            const unsigned long long seq = P->next(P->cnt_halo);
+            if (P->total_send > 0) k_halo_put<0><<<(unsigned)((P->total_send + 127) / 128), 128, 0, st>>>(D, vec, seq, done);
+            else k_halo_put<0><<<1, 128, 0, st>>>(D, vec, seq, done);
+            k_halo_get<0><<<(unsigned)std::max<int64_t>(1, (P->total_recv + 127) / 128), 128, 0, st>>>(D, vec, seq, const_cast<int*>(done));
+        } else {
+            const unsigned long long seq = P->next(P->cnt_sb);
+            if (P->total_send > 0) k_halo_put<1><<<(unsigned)((P->total_send + 127) / 128), 128, 0, st>>>(D, vec, seq, done);
+            else k_halo_put<1><<<1, 128, 0, st>>>(D, vec, seq, done);
+            k_halo_get<1><<<(unsigned)std::max<int64_t>(1, (P->total_recv + 127) / 128), 128, 0, st>>>(D, vec, seq, const_cast<int*>(done));
+        }
+        PSI_CK_LAUNCH();
+        return 0;
+    }
+    // fallback without mapped peer memory: pack + grouped ncclSend/ncclRecv
+    if (which == 0) return halo_exchange(P, vec, PSI_D, done, st);
+    if (halo_exchange(P, vec, PSI_QPITCH, done, st)) return -1;
+    return halo_exchange(P, vec + g->N * PSI_QPITCH, PSI_QPITCH, done, st);
 }
 
 // refresh the ghost rows of a [N, width] array from their owners (no-op for an unpartitioned graph)
 extern "C" int psi_halo_exchange(psi_graph_t* g, float* dev_vec, int width, void* stream) {
     if (g == nullptr) PSI_FAIL("psi_halo_exchange: null graph");
     if (width != 10 && width != 20 && width != 2) PSI_FAIL("psi_halo_exchange: width must be 2, 10 or 20");
+    if (width == 10) return halo_refresh(g, dev_vec, 0, nullptr, as_stream(stream));
     return halo_exchange(g->part, dev_vec, width, nullptr, as_stream(stream));
 }
 
@@ -230,8 +357,8 @@ static int graph_q(const psi_graph* cg, cudaStream_t st, float** q) {
     psi_graph* g = const_cast<psi_graph*>(cg);
     if (g->p_q == nullptr) {
         const int64_t N1 = g->N > 0 ? g->N : 1;
-        PSI_CK(psi_malloc_async((void**)&g->p_q, (size_t)3 * N1 * PSI_D * sizeof(float), st));
-        g->bytes += 3 * N1 * PSI_D * 4;
+        PSI_CK(psi_malloc_async((void**)&g->p_q, (size_t)3 * N1 * PSI_QPITCH * sizeof(float), st));
+        g->bytes += 3 * N1 * PSI_QPITCH * 4;
     }
     *q = g->p_q;
     return 0;
@@ -278,11 +405,11 @@ extern "C" int psi_layers_unrolled(const psi_graph_t* g, int kind, const float* 
     if (g->N > 0 && (dev_h == dev_out || dev_h == dev_work || dev_out == dev_work)) PSI_FAIL("psi_layers_unrolled: buffers must be distinct");
     cudaStream_t st = as_stream(stream);
     const SolverEpi noE{nullptr, nullptr, nullptr, nullptr};
-    const size_t wf = sizeof(LayerWeights) / sizeof(float);
+    const size_t wf = PSI_WBLOB_FLOATS;
     const float* src = dev_h;
     for (int k = 0; k < n_layers; ++k) {
         if (k == 0 || n_blobs > 1)
-            PSI_CK(cudaMemcpyToSymbolAsync(cW, dev_blobs + (size_t)(n_blobs > 1 ? k : 0) * wf, sizeof(LayerWeights), 0, cudaMemcpyDeviceToDevice, st));
+            if (upload_block(dev_blobs + (size_t)(n_blobs > 1 ? k : 0) * wf, st)) return -1;
         // ping-pong so that the last layer lands in dev_out
         float* dst = ((n_layers - 1 - k) % 2 == 0) ? dev_out : dev_work;
         if (launch_layer<false>(g, kind, src, dev_h0, dst, noE, st)) return -1;
@@ -294,16 +421,16 @@ extern "C" int psi_layers_unrolled(const psi_graph_t* g, int kind, const float* 
 static int vjp_alloc(psi_graph* g, cudaStream_t st) {
     if (g->p_vjp != nullptr) return 0;
     const int64_t N = g->N > 0 ? g->N : 1;
-    const int64_t floats = N * (10 + 1 + 1 + 10 + 30 + 1 + 20 + 10);
+    const int64_t floats = N * (10 + 1 + 1 + 10 + 30 + 1 + 2 * PSI_QPITCH + 10);
     PSI_CK(psi_malloc_async(&g->p_vjp, floats * sizeof(float), st));
     PSI_CK(psi_malloc_async(&g->p_xm_T, (g->slots_T > 0 ? g->slots_T : 1) * sizeof(int2), st));
     PSI_CK(psi_malloc_async(&g->p_xm_F, (g->slots_F > 0 ? g->slots_F : 1) * sizeof(int2), st));
     float* p = (float*)g->p_vjp;
     VjpCacheDev& C = g->vjp;
+    C.Sb = p; p += N * 2 * PSI_QPITCH;          // first: its rows are read with 16-byte loads (the base is 256-byte aligned)
     C.rhat = p; p += N * 10;
     C.m = p; p += N * 10;
     C.cnt = p; p += N * 30;
-    C.Sb = p; p += N * 20;
     C.Dloc = p; p += N * 10;
     C.rstd = p; p += N;
     C.alpha = p; p += N;
@@ -318,10 +445,19 @@ extern "C" int psi_vjp_prepare(psi_graph_t* g, int kind, const float* dev_hstar,
     (void)dev_h0;   // the Dirichlet rows of f do not depend on h: h0 never enters the Jacobian
     if (check_kind(g, kind)) return -1;
     if (kind != PSI_KIND_DIRICHLET && kind != PSI_KIND_MIXED) PSI_FAIL("psi_vjp_prepare: VJP exists for the PSI-GNN layers only");
-    if (g->part != nullptr) PSI_FAIL("psi_vjp_prepare: the backward solve of a mesh-partitioned graph is not implemented");
     if (g->N > 0 && dev_hstar == nullptr) PSI_FAIL("psi_vjp_prepare: null pointer");
     cudaStream_t st = as_stream(stream);
     if (vjp_alloc(g, st)) return -1;
+    if (g->part != nullptr && g->N > 0) {
+        // mesh partition: the linearisation point needs the neighbours' rows of H* — take a private copy and refresh its ghost rows
+        if (g->p_hstar == nullptr) {
+            PSI_CK(psi_malloc_async((void**)&g->p_hstar, (size_t)g->N * PSI_D * sizeof(float), st));
+            g->bytes += g->N * PSI_D * 4;
+        }
+        PSI_CK(cudaMemcpyAsync(g->p_hstar, dev_hstar, (size_t)g->N * PSI_D * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        if (halo_refresh(g, g->p_hstar, 0, nullptr, st)) return -1;
+        dev_hstar = g->p_hstar;
+    }
     if (g->N > 0) {
         PSI_CK(cudaMemsetAsync(g->p_xm_T, 0, (g->slots_T > 0 ? g->slots_T : 1) * sizeof(int2), st));
         PSI_CK(cudaMemsetAsync(g->p_xm_F, 0, (g->slots_F > 0 ? g->slots_F : 1) * sizeof(int2), st));
@@ -336,15 +472,14 @@ extern "C" int psi_vjp_prepare(psi_graph_t* g, int kind, const float* dev_hstar,
 
 template <bool EPI>
 static int launch_vjp(psi_graph* g, int kind, const float* y, const float* grad, float* out, SolverEpi E, cudaStream_t st) {
-    if (g->N == 0) return 0;
-    const unsigned grid = node_grid(g->N);
-    if (kind == PSI_KIND_DIRICHLET) {
-        k_vjp_phase_a<KIND_DIRICHLET><<<grid, PSI_NODE_BLOCK, 0, st>>>(g->dev, g->vjp, y, E.done);
-        k_vjp_phase_b<KIND_DIRICHLET, EPI><<<grid, PSI_NODE_BLOCK, 0, st>>>(g->dev, g->vjp, y, grad, out, E);
-    } else {
-        k_vjp_phase_a<KIND_MIXED><<<grid, PSI_NODE_BLOCK, 0, st>>>(g->dev, g->vjp, y, E.done);
-        k_vjp_phase_b<KIND_MIXED, EPI><<<grid, PSI_NODE_BLOCK, 0, st>>>(g->dev, g->vjp, y, grad, out, E);
-    }
+    if (g->dev.n_compute == 0) return 0;
+    const unsigned grid = node_grid(g->dev.n_compute);
+    if (kind == PSI_KIND_DIRICHLET) k_vjp_phase_a<KIND_DIRICHLET><<<grid, PSI_NODE_BLOCK, 0, st>>>(g->dev, g->vjp, y, E.done);
+    else k_vjp_phase_a<KIND_MIXED><<<grid, PSI_NODE_BLOCK, 0, st>>>(g->dev, g->vjp, y, E.done);
+    // mesh partition: S̄ of the ghost rows comes from their owners between the two phases (y itself is needed on owned rows only)
+    if (g->part != nullptr && halo_refresh(g, g->vjp.Sb, 1, E.done, st)) return -1;
+    if (kind == PSI_KIND_DIRICHLET) k_vjp_phase_b<KIND_DIRICHLET, EPI><<<grid, PSI_NODE_BLOCK, 0, st>>>(g->dev, g->vjp, y, grad, out, E);
+    else k_vjp_phase_b<KIND_MIXED, EPI><<<grid, PSI_NODE_BLOCK, 0, st>>>(g->dev, g->vjp, y, grad, out, E);
     PSI_CK_LAUNCH();
     return 0;
 }
@@ -421,6 +556,9 @@ struct psi_solver {
     float *partial = nullptr, *coef = nullptr, *norm_part = nullptr;
     QnCtrl* ctrl = nullptr;               // device
     QnCtrl* h_ctrl = nullptr;             // pinned host mirror
+    int* h_done = nullptr;                // mapped pinned word the device sets when a solve stops (read by the host without a sync)
+    int* d_done_host = nullptr;           // its device-side address
+    cudaEvent_t ahead[4] = {nullptr, nullptr, nullptr, nullptr};   // run-ahead window of the fused loops
     double *rel_trace = nullptr, *abs_trace = nullptr;
     QnHistory hist{};
     int slabs_alloc = 0;
@@ -435,6 +573,7 @@ struct psi_solver {
     int64_t act_numel = 0, last_act = -1; int act_chunks = 0, act_dchunks = 0;
     double* dbuf = nullptr;               // [3·cap + 8] fp64 sums all-reduced over the ranks of a partitioned solve
     psi_comm* comm = nullptr;             // communicator of the current solve (nullptr: single rank)
+    Partition* part = nullptr;            // partition of the current solve (peer-mapped mailboxes when part->p2p)
     // optional per-kernel-class timing with CUDA events on the launching stream (psi_solver_profile)
     int profile = 0;
     std::vector<cudaEvent_t> ev;          // [((step * PROF_CLASSES) + cls) * 2 + {begin,end}]
@@ -515,10 +654,14 @@ extern "C" int psi_solver_create(psi_solver_t** out, int64_t numel, int max_thre
     rc |= solver_alloc(s, (void**)&s->coef, (size_t)3 * s->cap * sizeof(float));
     rc |= solver_alloc(s, (void**)&s->norm_part, (size_t)2 * s->norm_cap * sizeof(float));
     rc |= solver_alloc(s, (void**)&s->ctrl, sizeof(QnCtrl));
-    rc |= solver_alloc(s, (void**)&s->dbuf, (size_t)(3 * s->cap + 8) * sizeof(double));
+    rc |= solver_alloc(s, (void**)&s->dbuf, (size_t)(2 * (3 * s->cap + 8) + 16) * sizeof(double));
     rc |= solver_alloc(s, (void**)&s->rel_trace, (size_t)(s->cap + 2) * sizeof(double));
     rc |= solver_alloc(s, (void**)&s->abs_trace, (size_t)(s->cap + 2) * sizeof(double));
     if (!rc && cudaMallocHost((void**)&s->h_ctrl, sizeof(QnCtrl)) != cudaSuccess) { g_psi_err = "psi_solver_create: pinned allocation failed"; rc = -1; }
+    if (!rc && (cudaHostAlloc((void**)&s->h_done, sizeof(int), cudaHostAllocMapped) != cudaSuccess ||
+                cudaHostGetDevicePointer((void**)&s->d_done_host, s->h_done, 0) != cudaSuccess)) { g_psi_err = "psi_solver_create: mapped allocation failed"; rc = -1; }
+    for (int i = 0; i < 4 && !rc; ++i)
+        if (cudaEventCreateWithFlags(&s->ahead[i], cudaEventDisableTiming) != cudaSuccess) { g_psi_err = "psi_solver_create: event creation failed"; rc = -1; }
     if (rc) { psi_solver_destroy(s); return -1; }
     float* vecs[] = {s->x, s->g, s->dg, s->dx, s->best, s->fx};
     for (float* v : vecs) cudaMemset(v, 0, vb);
@@ -540,10 +683,12 @@ extern "C" int psi_solver_destroy(psi_solver_t* s) {
     for (void* p : ps)
         if (p) cudaFree(p);
     for (int i = 0; i < QN_MAX_SLABS; ++i) {
-        if (s->hist.U[i]) cudaFree(s->hist.U[i]);
-        if (s->hist.V[i]) cudaFree(s->hist.V[i]);
+        if (s->hist.U[i]) cudaFreeAsync(s->hist.U[i], nullptr);
+        if (s->hist.V[i]) cudaFreeAsync(s->hist.V[i], nullptr);
     }
     if (s->h_ctrl) cudaFreeHost(s->h_ctrl);
+    if (s->h_done) cudaFreeHost(s->h_done);
+    for (int i = 0; i < 4; ++i) if (s->ahead[i]) cudaEventDestroy(s->ahead[i]);
     for (cudaEvent_t e : s->ev) cudaEventDestroy(e);
     delete s;
     return 0;
@@ -572,8 +717,9 @@ extern "C" int psi_solver_profile_read(const psi_solver_t* s, double out[9]) {
     return 0;
 }
 
-// make sure history vector index k (0-based) has storage
-static int hist_ensure(psi_solver* s, int k) {
+// make sure history vector index k (0-based) has storage.  Slabs come from the stream-ordered pool and are zeroed on the solve's
+// stream: growing the history inside a running loop costs no device synchronisation (a plain cudaMalloc would drain the queue)
+static int hist_ensure(psi_solver* s, int k, cudaStream_t st) {
     const int slab = k / s->hist.slab_vecs;
     if (slab >= QN_MAX_SLABS) PSI_FAIL("solver history exhausted");
     while (s->slabs_alloc <= slab) {
@@ -581,11 +727,12 @@ static int hist_ensure(psi_solver* s, int k) {
         const int vecs = std::min(s->hist.slab_vecs, s->cap - first);
         if (vecs <= 0) PSI_FAIL("solver history exhausted");
         const size_t b = (size_t)vecs * s->stride * sizeof(float);
-        if (solver_alloc(s, (void**)&s->hist.U[s->slabs_alloc], b)) return -1;
-        if (solver_alloc(s, (void**)&s->hist.V[s->slabs_alloc], b)) return -1;
+        PSI_CK(psi_malloc_async((void**)&s->hist.U[s->slabs_alloc], b, st));
+        PSI_CK(psi_malloc_async((void**)&s->hist.V[s->slabs_alloc], b, st));
+        s->bytes += 2 * (int64_t)b;
         // the padding beyond the active extent is read by the streaming kernels (times zero) and never written: keep it finite
-        PSI_CK(cudaMemset(s->hist.U[s->slabs_alloc], 0, b));
-        PSI_CK(cudaMemset(s->hist.V[s->slabs_alloc], 0, b));
+        PSI_CK(cudaMemsetAsync(s->hist.U[s->slabs_alloc], 0, b, st));
+        PSI_CK(cudaMemsetAsync(s->hist.V[s->slabs_alloc], 0, b, st));
         ++s->slabs_alloc;
     }
     return 0;
@@ -599,6 +746,7 @@ static int qn_begin(psi_solver* s, const float* x0, int threshold, double eps, f
     if (s->numel > 0 && x0 == nullptr) PSI_FAIL("null x0");
     s->threshold = threshold; s->eps = eps; s->n = 0; s->launches = 0; s->f_evals = 0; s->xtrace = xtrace; s->active = true;
     s->comm = (comm != nullptr && comm->world > 1) ? comm : nullptr;
+    s->part = nullptr;
     s->act_numel = (act_numel < 0 || act_numel > s->numel) ? s->numel : act_numel;
     s->act_chunks = (int)((s->act_numel + QN_CHUNK - 1) / QN_CHUNK);
     s->act_dchunks = (int)((s->act_numel + DOTS_CH - 1) / DOTS_CH);
@@ -614,7 +762,8 @@ static int qn_begin(psi_solver* s, const float* x0, int threshold, double eps, f
         }
         s->last_act = s->act_numel;
     }
-    k_qn_ctrl_init<<<1, 1, 0, st>>>(s->ctrl);
+    *s->h_done = 0;
+    k_qn_ctrl_init<<<1, 1, 0, st>>>(s->ctrl, s->d_done_host);
     PSI_CK_LAUNCH();
     if (s->numel > 0) {
         PSI_CK(cudaMemcpyAsync(s->x, x0, s->numel * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -638,12 +787,14 @@ static int qn_first(psi_solver* s, cudaStream_t st) {
 // bookkeeping of step n (1-based) after the operator epilogue produced g_n, δg and the norm partials
 static int qn_update(psi_solver* s, int n, int norm_blocks, cudaStream_t st) {
     const int nhist = n - 1;
-    if (hist_ensure(s, n - 1)) return -1;
+    if (hist_ensure(s, n - 1, st)) return -1;
     const double vec = (double)s->act_numel * 4.0;
     // pass 1 (also at nhist = 0: it carries ⟨δx,δg⟩ and ⟨δx,g⟩, from which s and p of this step follow)
     prof_begin(s, n, 1, (2.0 * nhist + 3.0) * vec, st);
+    int kr = DOTS_KR;                       // finest of {32, 16, 8} history vectors per work item that still gives every SM an item
+    while (kr > 8 && (int64_t)s->act_dchunks * ((nhist + kr - 1) / kr) < 2 * (int64_t)s->tma_ctas) kr >>= 1;
     k_qn_dots_tma<<<s->tma_ctas, TMA_THREADS, dots_tma_smem(), st>>>(s->hist, nhist, s->dx, s->dg, s->g, s->partial, s->act_dchunks,
-                                                                     &s->ctrl->done);
+                                                                     &s->ctrl->done, kr);
     prof_end(s, n, 1, st);
     PSI_CK_LAUNCH();
     const int fin_blocks = std::max(1, std::min(2 * s->tma_ctas, (nhist * 3 + 2 + 7) / 8));   // one warp per row of the partial matrix
@@ -651,8 +802,15 @@ static int qn_update(psi_solver* s, int n, int norm_blocks, cudaStream_t st) {
         k_qn_fin1<<<fin_blocks, 256, 0, st>>>(nhist, s->partial, s->act_dchunks, s->coef, s->cap, s->dbuf, s->norm_part, norm_blocks, s->ctrl,
                                               s->rel_trace, s->abs_trace, n, s->eps, 1e3 * PSI_D, s->threshold);
         PSI_CK_LAUNCH();
+    } else if (s->part != nullptr && s->part->p2p) {
+        // mesh-partitioned over peer-mapped memory: reduction, exchange of the 3(n−1)+4 fp64 sums and the stop rules in ONE kernel
+        if (3 * nhist + 4 > PSI_RED_MAX) PSI_FAIL("threshold exceeds the reduce slots of the partitioned solve");
+        PartDev D = s->part->dev;
+        k_qn_fin1_p2p<<<fin_blocks, 256, 0, st>>>(D, nhist, s->partial, s->act_dchunks, s->coef, s->cap, s->dbuf, s->norm_part, norm_blocks, s->ctrl,
+                                                  s->rel_trace, s->abs_trace, n, s->eps, 1e3 * PSI_D, s->threshold, s->part->next(s->part->cnt_red));
+        PSI_CK_LAUNCH();
     } else {
-        // mesh-partitioned: local fp64 sums → ONE all-reduce of 3(n−1)+4 doubles per step → coefficients and stop rules (identical on every rank)
+        // mesh-partitioned, NCCL fallback: local fp64 sums → ONE all-reduce of 3(n−1)+4 doubles per step → coefficients and stop rules
         k_qn_fin1_local<<<fin_blocks, 256, 0, st>>>(nhist, s->partial, s->act_dchunks, s->dbuf, s->norm_part, norm_blocks, s->ctrl);
         PSI_CK_LAUNCH();
         if (allreduce_f64(s->comm, s->dbuf, (size_t)3 * nhist + 4, st)) return -1;
@@ -729,7 +887,8 @@ static int op_eval(psi_solver* s, psi_graph* g, int kind, int op, const float* a
     const int step = s->f_evals;          // evaluation 0 yields g_0, evaluation n belongs to step n
     s->f_evals += 1;
     int rc;
-    if (g->part != nullptr && halo_exchange(g->part, s->x, PSI_D, &s->ctrl->done, st)) return -1;
+    // the layer operator reads the neighbours' rows of the iterate (ghost rows from their owners); the VJP exchanges S̄ between its phases
+    if (g->part != nullptr && op == PSI_OP_LAYER && halo_refresh(g, s->x, 0, &s->ctrl->done, st)) return -1;
     prof_begin(s, step, 0, s->op_bytes, st);
     if (op == PSI_OP_LAYER) {
         s->launches += 2;
@@ -763,19 +922,29 @@ extern "C" int psi_solver_broyden(psi_solver_t* s, psi_graph_t* g, int kind, int
     if (g->N * PSI_D != s->numel) PSI_FAIL("psi_solver_broyden: solver workspace size does not match the graph");
     if (g->N > 0 && dev_aux == nullptr && !(op == PSI_OP_LAYER && kind == PSI_KIND_DSS)) PSI_FAIL("psi_solver_broyden: null aux (h0 / grad)");
     cudaStream_t st = as_stream(stream);
-    if (g->part != nullptr && op != PSI_OP_LAYER) PSI_FAIL("psi_solver_broyden: the mesh-partitioned solve supports the layer operator");
     if (qn_begin(s, dev_x0, threshold, eps, dev_xtrace, st, (int64_t)g->dev.n_compute * PSI_D, g->part ? g->part->comm : nullptr)) return -1;
+    s->part = (s->comm != nullptr) ? g->part : nullptr;
+    if (s->part != nullptr) s->part->new_epoch();
     s->op_bytes = operator_bytes(g, kind, op);
     const int norm_blocks = (int)node_grid(g->dev.n_compute);
     if (g->N > 0) {
         if (op_eval(s, g, kind, op, dev_aux, nullptr, st)) return -1;        // g_0 = op(x_0) − x_0
         if (qn_first(s, st)) return -1;
-        // poll the device-side stop flag every `poll` steps; kernels of steps past the stop are no-ops
-        const int poll = s->numel < (1 << 22) ? 16 : 4;
+        // The host runs at most AHEAD steps in front of the device (an event per step) and reads the stop word the device writes into
+        // mapped host memory — no stream synchronisation, no copy; kernels of the (≤ AHEAD − 1) steps queued past the stop are no-ops.
+        // A mesh-partitioned solve must leave the loop at the SAME step on every rank (the NCCL fallback enqueues real sends and
+        // receives for every queued step): there the stop flag is polled at fixed steps instead.
+        constexpr int AHEAD = 3;
+        const bool lockstep = (s->comm != nullptr);
         for (int n = 1; n <= threshold; ++n) {
+            if (!lockstep && n > AHEAD) {
+                PSI_CK(cudaEventSynchronize(s->ahead[(n - AHEAD) % 4]));
+                if (*reinterpret_cast<volatile int*>(s->h_done)) break;
+            }
             if (op_eval(s, g, kind, op, dev_aux, nullptr, st)) return -1;
             if (qn_update(s, n, norm_blocks, st)) return -1;
-            if (n % poll == 0 && n < threshold) {
+            if (!lockstep) PSI_CK(cudaEventRecord(s->ahead[n % 4], st));
+            else if (n % 4 == 0 && n < threshold) {
                 if (qn_poll(s, st)) return -1;
                 if (s->h_ctrl->done) break;
             }
@@ -849,11 +1018,11 @@ extern "C" int psi_broyden_forced_step(psi_solver_t* s, int n, const float* dev_
     if (n < 1 || n > s->cap) PSI_FAIL("psi_broyden_forced_step: n out of range");
     if (s->numel == 0) return 0;
     cudaStream_t st = as_stream(stream);
-    if (hist_ensure(s, n - 1)) return -1;
+    if (hist_ensure(s, n - 1, st)) return -1;
     s->threshold = s->cap + 1; s->eps = 0.0; s->xtrace = nullptr; s->launches = 0; s->f_evals = 0; s->comm = nullptr;
     s->act_numel = s->numel; s->act_chunks = (int)((s->numel + QN_CHUNK - 1) / QN_CHUNK); s->act_dchunks = (int)((s->numel + DOTS_CH - 1) / DOTS_CH);
     s->last_act = -1;   // the next solve re-establishes the zero padding
-    k_qn_ctrl_init<<<1, 1, 0, st>>>(s->ctrl);
+    k_qn_ctrl_init<<<1, 1, 0, st>>>(s->ctrl, nullptr);
     for (int k = 0; k < n - 1; ++k) {
         float* du = s->hist.U[k / s->hist.slab_vecs] + (int64_t)(k % s->hist.slab_vecs) * s->stride;
         float* dv = s->hist.V[k / s->hist.slab_vecs] + (int64_t)(k % s->hist.slab_vecs) * s->stride;

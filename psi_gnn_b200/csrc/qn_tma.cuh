@@ -16,12 +16,11 @@
 #define TMA_THREADS (TMA_CONSUMERS + 32)     // + 1 producer warp
 #define DOTS_CH 4096                         // elements per chunk (16 KB per vector), four float4 per consumer thread
 #define DOTS_STAGES 6                        // 6 × (16 KB U + 16 KB V) = 192 KB
-#define DOTS_KR 32                           // history vectors per work item
+#define DOTS_KR 32                           // history vectors per work item (upper bound; the launch picks 8, 16 or 32)
 #define DOTS_KB 8                            // ks per cross-warp reduction batch
 #define AXPY_TILE 2048                       // max elements per tile (8 KB per vector), two float4 per consumer thread
 #define AXPY_STAGES 11                       // 11 × (8 KB U + 8 KB V) = 176 KB
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
@@ -60,7 +59,7 @@ struct TmaRing {
 // partial[(k*3+q)*num_chunks + chunk], num_chunks = stride / DOTS_CH
 __global__ void __launch_bounds__(TMA_THREADS, 1)
 k_qn_dots_tma(QnHistory H, int nhist, const float* __restrict__ dx, const float* __restrict__ dg, const float* __restrict__ g,
-              float* __restrict__ partial, int num_chunks, const int* __restrict__ done) {
+              float* __restrict__ partial, int num_chunks, const int* __restrict__ done, int kr) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* ring = reinterpret_cast<float*>(smem_raw);                                   // [STAGES][2][DOTS_CH]
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)DOTS_STAGES * 2 * DOTS_CH * sizeof(float));
@@ -74,7 +73,9 @@ k_qn_dots_tma(QnHistory H, int nhist, const float* __restrict__ dx, const float*
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    const int kranges = max(1, (nhist + DOTS_KR - 1) / DOTS_KR);       // at least one item per chunk: it also carries ⟨δx,δg⟩, ⟨δx,g⟩
+    // kr history vectors per work item: small problems (few chunks) get finer items so that every SM has work — each (vector, chunk)
+    // dot product is formed inside one item whatever kr is, so the results do not depend on it
+    const int kranges = max(1, (nhist + kr - 1) / kr);                 // at least one item per chunk: it also carries ⟨δx,δg⟩, ⟨δx,g⟩
     const int items = num_chunks * kranges;
     if (warp == TMA_CONSUMERS / 32) {
         // ---- producer ----
@@ -82,7 +83,7 @@ k_qn_dots_tma(QnHistory H, int nhist, const float* __restrict__ dx, const float*
             uint32_t fill = 0;
             for (int item = blockIdx.x; item < items; item += gridDim.x) {
                 const int c = item % num_chunks, r = item / num_chunks;
-                const int k0 = r * DOTS_KR, k1 = min(nhist, k0 + DOTS_KR);
+                const int k0 = r * kr, k1 = min(nhist, k0 + kr);
                 const int64_t e0 = (int64_t)c * DOTS_CH;
                 for (int k = k0; k < k1; ++k, ++fill) {
                     const uint32_t s = fill % DOTS_STAGES, use = fill / DOTS_STAGES;
@@ -101,7 +102,7 @@ k_qn_dots_tma(QnHistory H, int nhist, const float* __restrict__ dx, const float*
     int buf = 0, xbuf = 0;
     for (int item = blockIdx.x; item < items; item += gridDim.x) {
         const int c = item % num_chunks, r = item / num_chunks;
-        const int k0 = r * DOTS_KR, k1 = min(nhist, k0 + DOTS_KR);
+        const int k0 = r * kr, k1 = min(nhist, k0 + kr);
         const int64_t e0 = (int64_t)c * DOTS_CH;
         const float4* pdx = reinterpret_cast<const float4*>(dx + e0);
         const float4* pdg = reinterpret_cast<const float4*>(dg + e0);

@@ -100,7 +100,7 @@ template <int KIND>
 __global__ void __launch_bounds__(PSI_NODE_BLOCK)
 k_vjp_prepare(GraphDev G, VjpCacheDev C, const float* __restrict__ h) {
     const int node = blockIdx.x * PSI_NODE_BLOCK + threadIdx.x;
-    if (node >= G.N) return;
+    if (node >= G.n_compute) return;                  // mesh partition: the cache of a ghost row lives with its owner
     constexpr int PRB = (KIND == KIND_MIXED) ? 3 : 2;
     float hi[PSI_D];
     load_row(h, node, hi);
@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(PSI_NODE_BLOCK)
 k_vjp_phase_a(GraphDev G, VjpCacheDev C, const float* __restrict__ y, const int* __restrict__ done) {
     if (done != nullptr && *done) return;
     const int node = blockIdx.x * PSI_NODE_BLOCK + threadIdx.x;
-    if (node >= G.N) return;
+    if (node >= G.n_compute) return;                  // mesh partition: S̄ of the ghost rows arrives from their owners
     constexpr int PRB = (KIND == KIND_MIXED) ? 3 : 2;
     const uint8_t tg = G.tag[node];
     float D[PSI_D], SbT[PSI_D], SbF[PSI_D];
@@ -273,43 +273,15 @@ k_vjp_phase_a(GraphDev G, VjpCacheDev C, const float* __restrict__ y, const int*
         (void)PRB;
     }
     store_row(C.Dloc, node, D);
-    store_row(C.Sb, node, SbT);                       // planar [2][N][10]: the gathers of phase B read contiguous rows
-    store_row(C.Sb, (int64_t)G.N + node, SbF);
-}
-
-// walk of one {neighbour, cross mask} list (written by k_vjp_prepare) with the cooperative row gather of layer.cuh.  WARP-UNIFORM.
-template <class RowIdx, class Body>
-__device__ __forceinline__ void walk_xmask(const SellDev& L, const float* src, int slice, int lane, float* st, const CoopMap& M,
-                                           RowIdx&& rowidx_of, Body&& body) {
-    const int64_t base = L.slice_off[slice];
-    const int width = (int)((L.slice_off[slice + 1] - base) >> 5);
-    if (width == 0) return;
-    const int2* p = reinterpret_cast<const int2*>(L.xmask) + base + lane;
-    const int2 none = make_int2(-1, 0);
-    int2 r0 = p[0];
-    int2 r1 = (width > 1) ? p[32] : none;
-    int i0 = r0.y ? rowidx_of(r0) : -1;
-    float2 v[5];
-    coop_issue_rw(src, i0, M, v);
-    for (int t = 0; t < width; ++t) {
-        coop_store(st, M, v);
-        __syncwarp();
-        const int2 r2 = (t + 2 < width) ? p[(int64_t)(t + 2) * 32] : none;
-        const int i1 = r1.y ? rowidx_of(r1) : -1;
-        if (t + 1 < width) coop_issue_rw(src, i1, M, v);
-        float q[PSI_D];
-        coop_row(st, lane, q);
-        __syncwarp();
-        if (i0 >= 0) body((uint32_t)r0.y, q);
-        r0 = r1; r1 = r2; i0 = i1;
-    }
+    store_row12(C.Sb, node, SbT);                     // planar [2][N][12]: the gathers of phase B read contiguous 16-byte aligned rows
+    store_row12(C.Sb, (int64_t)G.N + node, SbF);
 }
 
 template <int KIND, bool EPI>
 __global__ void __launch_bounds__(PSI_NODE_BLOCK, PSI_OP_MIN_CTAS)
 k_vjp_phase_b(GraphDev G, VjpCacheDev C, const float* __restrict__ y, const float* __restrict__ grad,
               float* __restrict__ out, SolverEpi E) {
-    __shared__ __align__(16) float stage[(PSI_NODE_BLOCK / 32) * PSI_STAGE_FLOATS];
+    __shared__ WarpStage stage[PSI_NODE_BLOCK / 32];
     __shared__ float smem[2 * PSI_NODE_BLOCK / 32];
     if (EPI && *E.done) return;
     const int node = blockIdx.x * PSI_NODE_BLOCK + threadIdx.x;
@@ -324,29 +296,49 @@ k_vjp_phase_b(GraphDev G, VjpCacheDev C, const float* __restrict__ y, const floa
         for (int o = 0; o < PSI_D; ++o) { accT[o] = 0.f; accF[o] = 0.f; accN[o] = 0.f; }
         CoopMap M;
         coop_map(lane, M);
-        float* st = stage + (threadIdx.x >> 5) * PSI_STAGE_FLOATS;
+        WarpStage& W = stage[threadIdx.x >> 5];
         const int slice = node >> 5;
         const int N = G.N;
-        // Both walks gather S̄ of the destination over the *other* list: scatter of reverse-mode autograd turned into a gather.
+        // Both walks gather S̄ of the destination over the *other* list ({neighbour, cross mask} pairs written by k_vjp_prepare; a
+        // zero mask — padding slots, Dirichlet destinations — selects nothing): the scatter of reverse-mode autograd as a gather.
         // row list of this node: edges (node, c) — node is the source of Phi_to messages into c
-        walk_xmask(G.F, C.Sb, slice, lane, st, M,
-                   [&](const int2& jm) { return valid ? jm.x : -1; },
-                   [&](uint32_t xm, const float (&sb)[PSI_D]) {
+        {
+            const int64_t base = G.F.slice_off[slice];
+            const int width = (int)((G.F.slice_off[slice + 1] - base) >> 5);
+            walk_ring(reinterpret_cast<const int2*>(G.F.xmask) + base, width, C.Sb, lane, W, M,
+                      [&](const int2& jm) { return jm.y ? jm.x : 0; },
+                      [&](const int2& jm, const f2 (&q2)[PSI_D / 2]) {
+                          float sb[PSI_D];
+                          unpack10(q2, sb);
+                          const uint32_t xm = (uint32_t)jm.y;
 #pragma unroll
-                       for (int o = 0; o < PSI_D; ++o) accT[o] += ((xm >> o) & 1u) ? sb[o] : 0.f;
-                   });
+                          for (int o = 0; o < PSI_D; ++o) accT[o] += ((xm >> o) & 1u) ? sb[o] : 0.f;
+                      });
+        }
         // column list: edges (r, node) — node is the source of Phi_from / phi_neumann messages into r
-        walk_xmask(G.T, C.Sb, slice, lane, st, M,
-                   [&](const int2& jm) { return valid ? N + jm.x : -1; },
-                   [&](uint32_t xm, const float (&sb)[PSI_D]) {
-                       if (KIND == KIND_MIXED && (xm & (1u << 10))) {
+        {
+            const int64_t base = G.T.slice_off[slice];
+            const int width = (int)((G.T.slice_off[slice + 1] - base) >> 5);
+            walk_ring(reinterpret_cast<const int2*>(G.T.xmask) + base, width, C.Sb, lane, W, M,
+                      [&](const int2& jm) { return jm.y ? N + jm.x : 0; },
+                      [&](const int2& jm, const f2 (&q2)[PSI_D / 2]) {
+                          float sb[PSI_D];
+                          unpack10(q2, sb);
+                          const uint32_t xm = (uint32_t)jm.y;
+                          if (KIND == KIND_MIXED) {
+                              const bool neu = xm & (1u << 10);
 #pragma unroll
-                           for (int o = 0; o < PSI_D; ++o) accN[o] += ((xm >> o) & 1u) ? sb[o] : 0.f;
-                       } else {
+                              for (int o = 0; o < PSI_D; ++o) {
+                                  const float v = ((xm >> o) & 1u) ? sb[o] : 0.f;
+                                  accN[o] += neu ? v : 0.f;
+                                  accF[o] += neu ? 0.f : v;
+                              }
+                          } else {
 #pragma unroll
-                           for (int o = 0; o < PSI_D; ++o) accF[o] += ((xm >> o) & 1u) ? sb[o] : 0.f;
-                       }
-                   });
+                              for (int o = 0; o < PSI_D; ++o) accF[o] += ((xm >> o) & 1u) ? sb[o] : 0.f;
+                          }
+                      });
+        }
         if (valid) {
             load_row_rw(C.Dloc, node, res);
             PSI_TMATVEC(cW.to.W1j, accT, res);

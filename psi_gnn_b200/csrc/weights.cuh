@@ -20,7 +20,7 @@ struct EdgeMLP {
     float b2[PSI_D];
 };  // 350 floats
 
-struct LayerWeights {
+struct __align__(16) LayerWeights {
     EdgeMLP to, from, neu;                                   // phi_to, phi_from, phi_neumann
     float gate_w[33];                                        // alpha: Linear(3d+s, 1)   (model.py:275)
     float gate_b;
@@ -42,13 +42,41 @@ struct LayerWeights {
     float dec_W1[PSI_D][PSI_D]; float dec_b1[PSI_D];         // decoder d -> d -> 1
     float dec_W2[PSI_D]; float dec_b2;
     float dss_alpha;                                         // DSS constant step (config["alpha"])
-    float pad_[2];
+    float pad_[4];                                           // sizeof = 3200 floats: a multiple of 16 bytes
 };
 
 static_assert(sizeof(EdgeMLP) == 350 * 4, "EdgeMLP layout");
-static_assert(sizeof(LayerWeights) % 8 == 0, "LayerWeights size");
+static_assert(sizeof(LayerWeights) == 3200 * 4, "LayerWeights size");
+
+// Transposed ([input][output]) copies of the matrices the forward kernels contract over their INPUT index: two adjacent output
+// channels (o, o+1) then form one 8-byte constant operand of a packed FFMA2.  Packed by psi_gnn_b200/weights.py behind the
+// LayerWeights block (same blob); the biases are vectors and are read pairwise from LayerWeights itself.
+struct EdgeMLPT {
+    float W1iT[PSI_D][PSI_D];
+    float W1jT[PSI_D][PSI_D];
+    float W1aT[3][PSI_D];
+    float W2T[PSI_D][PSI_D];
+};  // 330 floats
+struct __align__(16) LayerWeightsT {
+    EdgeMLPT to, from, neu;
+    float up_W1T[33][PSI_D];
+    float up_W2T[PSI_D][PSI_D];
+    float un_W1T[25][PSI_D];
+    float un_W2T[PSI_D][PSI_D];
+    float gzT[33][PSI_D];
+    float grT[33][PSI_D];
+    float gcT[33][PSI_D];
+};
+static_assert(sizeof(EdgeMLPT) == 330 * 4, "EdgeMLPT layout");
+static_assert(sizeof(LayerWeightsT) == 2760 * 4, "LayerWeightsT layout");
 
 __constant__ LayerWeights cW;   // single translation unit (psignn_b200.cu)
+__constant__ LayerWeightsT cWT;
+
+template <int WHICH> __device__ __forceinline__ const EdgeMLPT& edge_mlp_t();
+template <> __device__ __forceinline__ const EdgeMLPT& edge_mlp_t<0>() { return cWT.to; }
+template <> __device__ __forceinline__ const EdgeMLPT& edge_mlp_t<1>() { return cWT.from; }
+template <> __device__ __forceinline__ const EdgeMLPT& edge_mlp_t<2>() { return cWT.neu; }
 
 template <int WHICH> __device__ __forceinline__ const EdgeMLP& edge_mlp();
 template <> __device__ __forceinline__ const EdgeMLP& edge_mlp<0>() { return cW.to; }

@@ -202,4 +202,35 @@ def attach(graph, part: MeshPartition, comm: Communicator):
     graph.partition = part
     graph.comm = comm          # keep the communicator alive as long as the graph
     part.comm = comm
+    if comm.world > 1 and USE_P2P:
+        _open_mailboxes(graph, part, comm)
     return graph
+
+
+USE_P2P = True       # peer-mapped mailboxes (CUDA IPC over NVLink); False = grouped ncclSend/ncclRecv + ncclAllReduce
+
+
+def _open_mailboxes(graph, part: MeshPartition, comm: Communicator):
+    """collective over the ranks of ``comm``: every rank allocates its mailbox, the IPC handles, ghost counts and ghost layouts are
+    all-gathered through ``torch.distributed`` (host side, once per graph), then every rank maps its peers' blocks"""
+    import torch.distributed as dist
+    from . import _native as N
+    lib = N.load()
+    buf = ctypes.create_string_buffer(64)
+    tr = c_int64(0)
+    with torch.cuda.device(graph.device):
+        N.check(lib.psi_part_mail_create(graph.handle, buf, byref(tr)), "psi_part_mail_create")
+    recv_off, o = {}, 0
+    for q, c in zip(part.peers, part.recv_counts):
+        recv_off[int(q)] = o
+        o += int(c)
+    mine = {"handle": bytes(buf.raw), "total_recv": int(tr.value), "recv_off": recv_off}
+    everyone = [None] * comm.world
+    dist.all_gather_object(everyone, mine)
+    handles = b"".join(e["handle"] for e in everyone)
+    totals = (c_int64 * comm.world)(*[e["total_recv"] for e in everyone])
+    n = len(part.peers)
+    remote = (c_int64 * max(n, 1))(*[everyone[q]["recv_off"][comm.rank] for q in part.peers])
+    with torch.cuda.device(graph.device):
+        N.check(lib.psi_part_mail_open(graph.handle, handles, totals, remote), "psi_part_mail_open")
+    dist.barrier()           # nobody stores into a block before every rank has mapped it

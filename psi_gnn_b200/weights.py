@@ -23,14 +23,33 @@ FIELDS = (
        ("gz_W", D * 33), ("gz_b", D), ("gr_W", D * 33), ("gr_b", D), ("gc_W", D * 33), ("gc_b", D),
        ("enc_W1", D), ("enc_b1", D), ("enc_W2", D * D), ("enc_b2", D),
        ("dec_W1", D * D), ("dec_b1", D), ("dec_W2", D), ("dec_b2", 1),
-       ("dss_alpha", 1), ("pad", 2)]
+       ("dss_alpha", 1), ("pad", 4)]
 )
 OFFSETS: Dict[str, int] = {}
 _o = 0
 for _n, _s in FIELDS:
     OFFSETS[_n] = _o
     _o += _s
-TOTAL_FLOATS = _o          # 3198; checked against psi_weights_floats() at load time
+MAIN_FLOATS = _o           # 3200 = sizeof(LayerWeights) / 4
+
+# struct LayerWeightsT: transposed ([input][output]) copies for the packed-FMA forward kernels — (source field, rows=out, pitch, inputs)
+_EDGE_T = [("W1i", D, D, D), ("W1j", D, D, D), ("W1a", D, 3, 3), ("W2", D, D, D)]
+TRANSPOSED = (
+    [("%s.%s" % (m, n), r, p, c) for m in ("to", "from", "neu") for n, r, p, c in _EDGE_T]
+    + [("up_W1", D, 33, 33), ("up_W2", D, D, D), ("un_W1", D, 25, 25), ("un_W2", D, D, D),
+       ("gz_W", D, 33, 33), ("gr_W", D, 33, 33), ("gc_W", D, 33, 33)]
+)
+TOTAL_FLOATS = MAIN_FLOATS + sum(c * r for _, r, _, c in TRANSPOSED)      # 5960; checked against psi_weights_floats() at load time
+
+
+def finish(blob: torch.Tensor) -> torch.Tensor:
+    """fill the LayerWeightsT tail of a packed block from its LayerWeights head (generic: works for every layer kind)"""
+    o = MAIN_FLOATS
+    for name, rows, pitch, cols in TRANSPOSED:
+        src = blob[OFFSETS[name]:OFFSETS[name] + rows * pitch].view(rows, pitch)[:, :cols]
+        blob[o:o + cols * rows] = src.t().reshape(-1)
+        o += cols * rows
+    return blob
 
 
 def _put(blob: torch.Tensor, name: str, t: torch.Tensor, rows: Optional[int] = None, width: Optional[int] = None):
@@ -100,7 +119,7 @@ def pack_psignn(P: Mapping[str, torch.Tensor], mixed: bool, device, f_prefix: st
         _put(blob, "un_W2", P[f"{f}.update_neumann.mlp.2.weight"], D, D)
         _put(blob, "un_b2", P[f"{f}.update_neumann.mlp.2.bias"])
     _autoencoder(blob, P)
-    return blob
+    return finish(blob)
 
 
 def pack_dss(P: Mapping[str, torch.Tensor], k: int, alpha: float, device) -> torch.Tensor:
@@ -116,7 +135,7 @@ def pack_dss(P: Mapping[str, torch.Tensor], k: int, alpha: float, device) -> tor
     if f"decoder_list.{k}.mlp.mlp.0.weight" in P:
         _decoder(blob, P, f"decoder_list.{k}.mlp.mlp")
     blob[OFFSETS["dss_alpha"]] = float(alpha)
-    return blob
+    return finish(blob)
 
 
 def pack_dsgps(P: Mapping[str, torch.Tensor], device) -> torch.Tensor:
@@ -136,7 +155,7 @@ def pack_dsgps(P: Mapping[str, torch.Tensor], device) -> torch.Tensor:
         _put(blob, "un_W2", P["update_neumann.mlp.2.weight"], D, D)
         _put(blob, "un_b2", P["update_neumann.mlp.2.bias"])
     _autoencoder(blob, P)
-    return blob
+    return finish(blob)
 
 
 _EPOCH = [0]        # bumped by invalidate(); part of every module's pack-cache key

@@ -49,6 +49,22 @@ def main():
             print(" | vs fp64-tight truth: ours %.3e, ref %.3e, permuted ref %.3e" % (
                 rel_err(u, g.t("u64")), rel_err(g.t("u"), g.t("u64")), rel_err(g.t("perm_u"), g.t("u64"))), end="")
         print()
+        if g.has("u64"):
+            # our own run-to-run spread: the same solve with the edge list permuted (other summation orders inside the SELL rows)
+            from psi_gnn_b200.synthetic import GraphData
+            devs, nst = [], []
+            for k in range(8):
+                perm = torch.randperm(b.edge_index.shape[1], generator=torch.Generator().manual_seed(2000 + k)).to(DEV)
+                bp = GraphData()
+                bp.__dict__.update({k_: v_ for k_, v_ in b.__dict__.items() if not k_.startswith("_psi")})
+                bp.edge_index, bp.edge_attr, bp.a_ij = b.edge_index[:, perm].contiguous(), b.edge_attr[perm].contiguous(), b.a_ij[perm].contiguous()
+                o2 = m.deqdss.inference(h0, bp)
+                devs.append(rel_err(m._decode_native(o2["result"]), g.t("u64")))
+                nst.append(o2["nstep"])
+            print("    ours under 8 edge permutations: nstep %s | u vs fp64-tight truth %s" % (sorted(nst), " ".join("%.2e" % d for d in sorted(devs))))
+            if g.has("spread_u_dev64"):
+                print("    reference under 8 edge permutations: nstep %s | u vs truth %s" % (
+                    sorted(int(x) for x in g["spread_nstep"]), " ".join("%.2e" % d for d in sorted(g["spread_u_dev64"]))))
         if not g.has("train_v"):
             continue
         # training step, free-running and teacher-forced

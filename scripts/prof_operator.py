@@ -42,6 +42,20 @@ def main():
         h = f(h, h0, b)
     y = torch.randn_like(h)
     op = VjpOperator(f, h, b, torch.zeros_like(h))
+    if os.environ.get("PSI_CHECK_DET"):
+        # bitwise run-to-run determinism at this size: layer, VJP, whole forward solve
+        with torch.no_grad():
+            a1, a2, a3 = f(h, h0, b), f(h, h0, b), f(h, h0, b)
+        v1, v2 = op(y), op(y)
+        s1 = m.deqdss.inference(h0, b)
+        s2 = m.deqdss.inference(h0, b)
+        s3 = m.deqdss.inference(h0, b)
+        print("determinism %s: layer %s %s | vjp %s | solve steps %d %d %d, results equal %s %s, rel traces equal %s" % (
+            which, torch.equal(a1, a2), torch.equal(a1, a3), torch.equal(v1, v2), s1["steps_run"], s2["steps_run"], s3["steps_run"],
+            torch.equal(s1["result"], s2["result"]), torch.equal(s1["result"], s3["result"]), s1["rel_trace"] == s2["rel_trace"]))
+        if s1["rel_trace"] != s2["rel_trace"]:
+            d = [i for i, (p_, q_) in enumerate(zip(s1["rel_trace"], s2["rel_trace"])) if p_ != q_]
+            print("   first differing step", d[0], s1["rel_trace"][d[0]], s2["rel_trace"][d[0]])
 
     def timed(fn):
         ts = []

@@ -31,7 +31,7 @@ class Golden:
     def __init__(self, name):
         self.name = name
         self.z = np.load(os.path.join(GOLDEN, name + ".npz"))
-        self.mixed = name.startswith("mixed")
+        self.mixed = "mixed" in name
 
     def __getitem__(self, k):
         return self.z[k]

@@ -87,6 +87,60 @@ def main():
             ok = ok and err < 2e-2       # unaligned cuts: a chaotic neighbour trajectory, same fixed point
         else:                                                  # step cap hit on a large mesh: comparable best residuals
             ok = ok and 0.2 < out["lowest"] / ref["lowest"] < 5.0
+    # ---- backward (implicit-adjoint) solve on the partition: y = Jᵀy + grad at the same H* on every layout ------------------------
+    from psi_gnn_b200 import solver as S
+    aligned = mesh.num_nodes >= 2 * partition.ALIGN_NODES * world
+    nfull = mesh.num_nodes
+    hs_full = torch.zeros(nfull, 10, device=dev)
+    if rank == 0:
+        hs_full[order] = ref["result"]                                   # single-GPU fixed point, global numbering
+    dist.broadcast(hs_full, src=0)
+    gid = torch.arange(nfull, device=dev, dtype=torch.float32)
+    grad_full = (1e-3 * torch.sin(0.37 * gid[:, None] + torch.arange(10, device=dev)[None].float())).contiguous()
+    y_full = torch.cos(0.11 * gid[:, None] + 0.5 * torch.arange(10, device=dev)[None].float()).contiguous()
+    opp = S.VjpOperator(model.deqdss.f, hs_full[ids].contiguous(), loc, grad_full[ids].contiguous())
+    one_loc = opp(y_full[ids].contiguous())[:part.n_owned]               # one application of Jᵀy + grad (S̄ ghost rows exchanged inside)
+    bw_loc = S.broyden(opp, torch.zeros(loc.num_nodes, 10, device=dev), threshold=int(g["cfg.bw_thres"]), eps=float(g["cfg.bw_tol"]))
+    if N.load().psi_part_error(gr.handle):
+        raise SystemExit("device-side exchange timed out on rank %d" % rank)
+
+    def gather_rows(t_owned):
+        pad = torch.zeros(mx, 10, device=dev)
+        pad[:part.n_owned] = t_owned
+        outs = [torch.zeros(mx, 10, device=dev) for _ in range(world)]
+        dist.all_gather(outs, pad)
+        return outs
+
+    one_all = gather_rows(one_loc)
+    bw_all = gather_rows(bw_loc["result"][:part.n_owned])
+    if rank == 0:
+        opf = S.VjpOperator(model.deqdss.f, hs_full[order].contiguous(), full, grad_full[order].contiguous())
+        one_ref = torch.zeros(nfull, 10, device=dev)
+        one_ref[order] = opf(y_full[order].contiguous())
+        bw_ref = S.broyden(opf, torch.zeros(nfull, 10, device=dev), threshold=int(g["cfg.bw_thres"]), eps=float(g["cfg.bw_tol"]))
+        y_ref = torch.zeros(nfull, 10, device=dev)
+        y_ref[order] = bw_ref["result"]
+        one_glob, y_glob = torch.zeros(nfull, 10, device=dev), torch.zeros(nfull, 10, device=dev)
+        for r in range(world):
+            n = int(sizes[r])
+            one_glob[idx[r][:n]] = one_all[r][:n]
+            y_glob[idx[r][:n]] = bw_all[r][:n]
+        e_one = float((one_glob - one_ref).norm() / one_ref.norm())
+        e_bw = float((y_glob - y_ref).norm() / y_ref.norm())
+        mb = min(bw_loc["steps_run"], bw_ref["steps_run"])
+        ta, tb = np.asarray(bw_loc["rel_trace"][:mb]), np.asarray(bw_ref["rel_trace"][:mb])
+        fin = np.isfinite(ta) & np.isfinite(tb)
+        dtr = np.abs(ta[fin] - tb[fin]) / tb[fin]
+        same_nonfinite = bool(np.array_equal(np.isfinite(ta), np.isfinite(tb)))     # a solve that blows up must blow up at the same step
+        mdev = float(dtr.max()) if dtr.size else 0.0
+        print("partitioned VJP: one application rel diff %.2e | backward solve steps %d (single GPU %d), lowest %.2e (%.2e), max rel-trace "
+              "deviation %.1e (non-finite entries at the same steps: %s), adjoint rel diff %.2e" % (
+                  e_one, bw_loc["steps_run"], bw_ref["steps_run"], bw_loc["lowest"], bw_ref["lowest"], mdev, same_nonfinite, e_bw))
+        ok = ok and e_one < 1e-6
+        if aligned:
+            ok = ok and bw_loc["steps_run"] == bw_ref["steps_run"] and same_nonfinite and mdev < 1e-6 and e_bw < 1e-5
+        else:
+            ok = ok and np.isfinite(e_bw) and e_bw < max(1e-3, 400 * max(bw_loc["lowest"], bw_ref["lowest"]))
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.broadcast(flag, src=0)
     dist.destroy_process_group()

@@ -758,13 +758,25 @@ def _stable_prefix(a, b, tol):
     return int(bad[0]) if bad.size else k
 
 
+def _edge_permuted(b, seed):
+    from psi_gnn_b200.synthetic import GraphData
+    perm = torch.randperm(b.edge_index.shape[1], generator=torch.Generator().manual_seed(seed)).to(b.edge_index.device)
+    bp = GraphData()
+    bp.__dict__.update({k: v for k, v in b.__dict__.items() if not k.startswith("_psi")})
+    bp.edge_index, bp.edge_attr, bp.a_ij = b.edge_index[:, perm].contiguous(), b.edge_attr[perm].contiguous(), b.a_ij[perm].contiguous()
+    return bp
+
+
 def test_config_forward_solve(cfg_golden):
     """free-running forward solve at configuration size (32 ≈500-node meshes = C0/C1 and one 8-GPU shard of C3; 8 ≈2 k-node mixed
-    meshes = C4 sample), protocol of SURVEY §8c (3):
-      * the first 20 rel-trace entries within 1e-3 of the reference (over the prefix on which the reference agrees with ITSELF under an
-        edge permutation to 3e-4 — beyond it the secant updates have amplified rounding noise in the reference too);
-      * converged like the reference; step count within ±5 % / ±3 of the interval spanned by the reference's own two runs;
-      * ‖u − u_fp64,tight‖/‖u‖ ≤ 1.25 × the reference-fp32's own deviation from that truth (the larger of its two runs);
+    meshes = C4 sample), protocol of SURVEY §8c (3).  A single free-running solve is one draw of a chaotic process — the fixtures
+    hold ten runs of the REFERENCE ITSELF (edge list permuted: same graph, same weights), whose step counts span 74…102 and whose
+    distances to the fp64-tight fixed point span 1.0e-3…2.2e-3 on cfg_c1 — so the CUDA path is sampled the same way (5 edge
+    permutations) and held to the reference's own spread:
+      * the first 20 rel-trace entries within 1e-3 of the reference, over the prefix on which the reference agrees with ITSELF under an
+        edge permutation to 3e-4 (measured: 10 steps; beyond it the secant updates have amplified rounding noise in the reference too);
+      * converged like the reference; every step count within ±5 % / ±3 of the interval spanned by the reference's runs;
+      * ‖u − u_fp64,tight‖/‖u‖: median over our runs ≤ 1.25 × the largest deviation of the reference's runs, no run beyond 2 ×;
       * physics residual within the same band."""
     g = cfg_golden
     m = g.model(DEV)
@@ -780,24 +792,33 @@ def test_config_forward_solve(cfg_golden):
     assert np.all(np.abs(got - ref_rel[:k]) <= 1e-3 * ref_rel[:k]), (k, got, ref_rel[:k])
     eps = float(g["cfg.fw_tol"])
     ref_conv = float(g["fw_lowest"]) < eps
-    assert (out["lowest"] < eps) == ref_conv or out["lowest"] < eps
     assert bool(out["prot_break"]) == bool(int(g["fw_prot_break"]))
-    lo, hi = sorted((int(g["fw_nstep"]), int(g["perm_fw_nstep"])))
+    # the reference's own runs
+    ref_steps = [int(g["fw_nstep"]), int(g["perm_fw_nstep"])] + ([int(x) for x in g["spread_nstep"]] if g.has("spread_nstep") else [])
+    ref_devs = [rel_err(g.t("u"), g.t("u64")), rel_err(g.t("perm_u"), g.t("u64"))] + ([float(x) for x in g["spread_u_dev64"]] if g.has("spread_u_dev64") else [])
+    lo, hi = min(ref_steps), max(ref_steps)
     tol = max(3, int(round(0.05 * int(g["fw_nstep"]))))
-    u = m._decode_native(out["result"])
-    d_ours = rel_err(u, g.t("u64"))
-    d_ref = max(rel_err(g.t("u"), g.t("u64")), rel_err(g.t("perm_u"), g.t("u64")))
-    print("config %s: nstep %d (reference %d, permuted reference %d, allowed [%d, %d]); u vs fp64-tight truth %.3e (reference %.3e / %.3e); "
-          "rel trace checked over %d steps (reference self-stable over %d)" % (
-              g.name, out["nstep"], int(g["fw_nstep"]), int(g["perm_fw_nstep"]), lo - tol, hi + tol, d_ours,
-              rel_err(g.t("u"), g.t("u64")), rel_err(g.t("perm_u"), g.t("u64")), k, stable))
-    assert d_ours <= 1.25 * d_ref, (d_ours, d_ref)
-    if ref_conv:
-        assert lo - tol <= out["nstep"] <= hi + tol, (out["nstep"], lo, hi, tol)
+    # ours: the stored edge order + 4 permutations
+    runs = [(out, b)] + [(None, _edge_permuted(b, 3000 + i)) for i in range(4)]
+    devs, steps, resid = [], [], []
     r64 = m.residual_loss(g.t("u64", DEV).float(), b).item()
-    r_ours = m.residual_loss(u, b).item()
+    for o, bb in runs:
+        o = o if o is not None else m.deqdss.inference(h0, bb)
+        u = m._decode_native(o["result"])
+        devs.append(rel_err(u, g.t("u64")))
+        steps.append(o["nstep"])
+        resid.append(abs(m.residual_loss(u, b).item() - r64))
+        if ref_conv:
+            assert o["lowest"] < eps
+    print("config %s: nstep %s (reference runs %s, allowed [%d, %d]); u vs fp64-tight truth %s (reference runs %.2e … %.2e); rel trace "
+          "checked over %d steps (reference self-stable over %d)" % (g.name, steps, sorted(ref_steps), lo - tol, hi + tol,
+                                                                    " ".join("%.2e" % d for d in devs), min(ref_devs), max(ref_devs), k, stable))
+    assert float(np.median(devs)) <= 1.25 * max(ref_devs), (devs, ref_devs)
+    assert max(devs) <= 2.0 * max(ref_devs), (devs, ref_devs)
+    if ref_conv:
+        assert all(lo - tol <= s_ <= hi + tol for s_ in steps), (steps, lo, hi, tol)
     r_ref = max(abs(float(g["residual"]) - r64), abs(m.residual_loss(g.t("perm_u", DEV), b).item() - r64))
-    assert abs(r_ours - r64) <= 1.25 * r_ref + 1e-6 * abs(r64)
+    assert float(np.median(resid)) <= 1.25 * r_ref + 1e-6 * abs(r64)
 
 
 def _cfg_train(g, monkeypatch, pinned):

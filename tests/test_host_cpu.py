@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
 def test_weight_block_layout():
     from psi_gnn_b200 import _native as N
     from psi_gnn_b200 import weights as W
-    assert N.load().psi_weights_floats() == W.TOTAL_FLOATS == 3168
+    assert N.load().psi_weights_floats() == W.TOTAL_FLOATS == 3200 + 2760      # struct LayerWeights + struct LayerWeightsT
     g = Golden("mixed_seed0")
     P = g.params()
     blob = W.pack_psignn(P, True, "cpu")
@@ -42,6 +42,11 @@ def test_weight_block_layout():
     un = P["deqdss.f.update_neumann.mlp.0.weight"]
     assert torch.equal(blob[o["un_W1"]:o["un_W1"] + 250].view(10, 25), un)
     assert torch.equal(blob[o["dec_W2"]:o["dec_W2"] + 10], P["autoencoder.decoder.mlp.mlp.2.weight"].reshape(-1))
+    # the transposed tail (packed-FMA kernels): [input][output] copies of the same matrices
+    t0 = W.MAIN_FLOATS
+    assert torch.equal(blob[t0:t0 + 100].view(10, 10), P["deqdss.f.phi_to_list.0.mlp.mlp.0.weight"][:, 0:10].t())
+    upT = t0 + 3 * 330
+    assert torch.equal(blob[upT:upT + 330].view(33, 10), up.t())
     # dirichlet: prb width 2 → the 33rd column of the gate/update rows stays zero
     gd = Golden("dirichlet_seed0")
     bd = W.pack_psignn(gd.params(), False, "cpu")
@@ -65,7 +70,7 @@ def test_constructor_signatures():
     assert list(inspect.signature(M.DeepEquilibrium.__init__).parameters)[1:] == ["function", "config_deq"]
     assert list(inspect.signature(S.broyden).parameters)[:7] == ["f", "x0", "threshold", "eps", "stop_mode", "ls", "name"]
     assert list(inspect.signature(S.anderson).parameters)[:8] == ["f", "x0", "m", "lam", "threshold", "eps", "stop_mode", "beta"]
-    assert list(inspect.signature(S.forward_iteration).parameters) == ["f", "z0", "eps", "threshold"]
+    assert list(inspect.signature(S.forward_iteration).parameters)[:4] == ["f", "z0", "eps", "threshold"]      # + keep_trace, **kwargs (accepted, as the drop-in DeepEquilibrium.inference forwards keep_trace to every solver)
 
 
 def test_no_cpu_fallback(golden):
@@ -134,7 +139,7 @@ def test_weight_block_layout_baselines():
     gg = Golden("dsgps_ckpt")
     Pg = gg.params()
     bg = W.pack_dsgps(Pg, "cpu")
-    assert torch.equal(bg[o["gz_W"]:o["gz_W"] + 320].view(10, 32), Pg["z_k.mlp.0.weight"])
+    assert torch.equal(bg[o["gz_W"]:o["gz_W"] + 330].view(10, 33)[:, :32], Pg["z_k.mlp.0.weight"])        # row pitch 33: the mixed family has 33 inputs
     assert torch.equal(bg[o["gc_b"]:o["gc_b"] + 10], Pg["correction.mlp.0.bias"])
     assert torch.equal(bg[o["enc_W1"]:o["enc_W1"] + 10], Pg["autoencoder.encoder.mlp.mlp.0.weight"].reshape(-1))
 
