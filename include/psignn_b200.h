@@ -127,6 +127,15 @@ int psi_vjp_prepare(psi_graph_t* g, int kind, const float* dev_hstar, const floa
 int psi_vjp_apply(psi_graph_t* g, int kind, const float* dev_y, const float* dev_grad,
                   float* dev_out, void* stream);
 
+/* Parameter gradient of one application of f at the prepared point: theta_bar = (d f / d theta)^T y_bar, the walk that the reference's
+ * loss.backward() makes from new_H_star = f(H*) to the parameters (dirichlet/psignn/model.py:204-205; mixed :146-147).  dev_out: flat
+ * fp32 vector of psi_weights_floats() floats in the layout of the packed weight block (gradient of field X at the offset of X);
+ * dev_jty (optional): J^T y_bar.  tab_dst/tab_y/tab_x [n_tab]: table of psi_gnn_b200/weights.py (parameter = sum over nodes of
+ * record[tab_y] * record[tab_x], record layout from psi_pgrad_layout).  Deterministic (no atomics). */
+int psi_param_grad(psi_graph_t* g, int kind, const float* dev_hstar, const float* dev_ybar, const int32_t* dev_tab_dst,
+                   const int32_t* dev_tab_y, const int32_t* dev_tab_x, int n_tab, float* dev_out, float* dev_jty, void* stream);
+int psi_pgrad_layout(int32_t out[16]);
+
 /* ---- physics residual, encoder, decoder ------------------------------------------------------- */
 /* r = A u - y (all nnz incl. diagonal); *dev_mean_sq = mean(r^2); dev_r may be NULL */
 int psi_residual(const psi_graph_t* g, const float* dev_u, const float* dev_y, float* dev_r,
@@ -199,6 +208,10 @@ const float* psi_anderson_x(const psi_solver_t* s);               /* device poin
 int psi_anderson_feed(psi_solver_t* s, const float* dev_fx, int* done, void* stream);
 int psi_anderson_finish(psi_solver_t* s, float* dev_result, psi_solve_stats_t* stats, double* rel_trace, double* abs_trace,
                         void* stream);
+/* teacher-forced single Anderson update for parity tests: window of n (<= m) vectors X, F ([n, numel] each) in; the production kernels
+ * form the Gram matrix, solve the bordered system and mix: dev_xnew = beta*sum(alpha_i F_i) + (1-beta)*sum(alpha_i X_i), dev_alpha [n] */
+int psi_anderson_forced_step(psi_solver_t* s, int m, int n, int slot, double lam, double beta, const float* dev_X, const float* dev_F,
+                             float* dev_xnew, float* dev_alpha, void* stream);
 int psi_picard_begin(psi_solver_t* s, const float* dev_z0, int threshold, double eps, float* dev_xtrace, void* stream);
 const float* psi_picard_x(const psi_solver_t* s);
 int psi_picard_feed(psi_solver_t* s, const float* dev_fx, int* done, void* stream);

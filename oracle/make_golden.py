@@ -225,11 +225,13 @@ def make_fixture(family: str, weights: str, n_graphs: int, seed0: int, h: float,
 
 
 def make_baseline_fixture(family: str, n_graphs: int, seed0: int, h: float, name: str):
-    """DSS / DSGPS ``inference`` of the unmodified reference with the shipped checkpoints (config 2)."""
+    """DSS / DSGPS ``inference`` and the unrolled training ``forward`` + ``backward`` of the unmodified reference with the shipped
+    checkpoints (config 2)."""
     model_mod, _, _ = ref_shim.load_reference(family)
     ck = ref_shim.load_checkpoint(ref_shim.CHECKPOINTS[family], family)
     cfg = dict(ck["hyperparameters"])
-    batch = synthetic.make_batch(n_graphs, seed0=seed0, h=h)
+    mixed = family.startswith("mixed")
+    batch = synthetic.make_batch(n_graphs, seed0=seed0, h=h, mixed=mixed)
     dss = family.endswith("dss")
     if dss:
         batch = synthetic.to_dss(batch)
@@ -247,7 +249,8 @@ def make_baseline_fixture(family: str, n_graphs: int, seed0: int, h: float, name
     fx["cfg.k"] = np.int64(cfg["k"])
     fx["cfg.alpha"] = np.float64(cfg["alpha"])
     with torch.no_grad():
-        u = model.inference(batch)
+        # mixed/dsgps/model.py has no `inference` method: the last state of its forward is the same quantity
+        u = model.inference(batch) if hasattr(model, "inference") else model(batch)[0][str(cfg["k"])]
         fx["u"] = u.numpy()
         # one layer in isolation (layer 0 from a non-trivial state)
         gen = torch.Generator().manual_seed(99)
@@ -263,16 +266,35 @@ def make_baseline_fixture(family: str, n_graphs: int, seed0: int, h: float, name
             fr = model.phi_from(H, batch.edge_index, batch.edge_attr)
             c = torch.cat([H, to, fr, batch.prb_data], 1)
             out = H + model.z_k(c) * model.correction(torch.cat([model.r_k(c) * H, to, fr, batch.prb_data], 1))
-            d = torch.where(batch.tags == 1)[0]
+            if mixed:
+                neu = model.phi_neumann(H, batch.edge_index, batch.edge_attr)
+                upd = model.update_neumann(torch.cat([H, neu, batch.prb_data, batch.unit_normal_vector], 1))
+                n_ = torch.where(batch.tags[:, 2] == 1)[0]
+                out[n_, :] = upd[n_, :]
+                d = torch.where(batch.tags[:, 1] == 1)[0]
+            else:
+                d = torch.where(batch.tags == 1)[0]
             out[d, :] = H0[d, :]
             fx["layer_h0"] = H0.numpy()
         fx["layer_in"] = H.numpy()
         fx["layer_out"] = out.numpy()
+    # unrolled training forward + backward of the reference (dirichlet/dss/model.py:59-104, */dsgps/model.py:48-131)
+    model.train()
+    model.zero_grad()
+    U, loss_dic = model(batch)
+    loss_dic["train_loss"].backward()
+    fx["train_loss"] = np.float64(loss_dic["train_loss"].item())
+    fx["train_u_last"] = U[str(cfg["k"])].detach().numpy()
+    fx["train_res_last"] = np.float64(loss_dic["residual_loss"][str(cfg["k"])].item())
+    for k_, p_ in model.named_parameters():
+        fx["train_grad." + k_] = (p_.grad if p_.grad is not None else torch.zeros_like(p_)).numpy()
+    fx["cfg.gamma"] = np.float64(cfg["gamma"])
     # the oracle restatement must agree with the reference here too
     P = {k: v for k, v in model.state_dict().items()}
-    with torch.no_grad():
-        ou = O.dss_inference(P, batch, cfg["k"], cfg["alpha"]) if dss else O.dsgps_inference(P, batch, cfg["k"])
-    assert float((ou - u).norm() / u.norm()) < 1e-5, "oracle != reference (%s)" % family
+    if not mixed:
+        with torch.no_grad():
+            ou = O.dss_inference(P, batch, cfg["k"], cfg["alpha"]) if dss else O.dsgps_inference(P, batch, cfg["k"])
+        assert float((ou - u).norm() / u.norm()) < 1e-5, "oracle != reference (%s)" % family
     os.makedirs(OUT, exist_ok=True)
     path = os.path.join(OUT, name + ".npz")
     np.savez_compressed(path, **fx)
@@ -280,10 +302,66 @@ def make_baseline_fixture(family: str, n_graphs: int, seed0: int, h: float, name
                                                         os.path.relpath(path, ROOT), os.path.getsize(path) / 1024))
 
 
+def append_anderson_forced():
+    """append teacher-forced Anderson states (window X, F entering the update of steps 2, 5, 12, 25 of an m = 3 run; the reference's
+    formulas of solver.py:250-255 evaluated in fp32 and in fp64 on those inputs) to tests/golden/dirichlet_ckpt_small.npz"""
+    path = os.path.join(OUT, 'dirichlet_ckpt_small.npz')
+    z = dict(np.load(path))
+    b = synthetic.GraphData()
+    for k, v in z.items():
+        if k.startswith('batch.') and k != 'batch.num_nodes':
+            setattr(b, k[6:], torch.from_numpy(v))
+    b.num_nodes = int(z['batch.num_nodes'])
+    torch.set_flush_denormal(True)
+    with tempfile.TemporaryDirectory() as d:
+        model, solver_mod, cfg = build_model('dirichlet/psignn', 'ckpt', d)
+        f = model.deqdss.f
+        with torch.no_grad():
+            h0 = model.autoencoder.encoder(b.x)
+            fn = lambda H: f(H, h0, b)
+            m, lam, beta = 3, 1e-4, 1.0
+            nd = h0.numel()
+            X = torch.zeros(1, m, nd); F = torch.zeros(1, m, nd)
+            X[:, 0] = h0.reshape(1, -1); F[:, 0] = fn(h0).reshape(1, -1)
+            X[:, 1] = F[:, 0]; F[:, 1] = fn(F[:, 0].reshape_as(h0)).reshape(1, -1)
+            H = torch.zeros(1, m + 1, m + 1); H[:, 0, 1:] = H[:, 1:, 0] = 1
+            y = torch.zeros(1, m + 1, 1); y[:, 0] = 1
+            steps = []
+            for k in range(2, 26):
+                n = min(k, m)
+                G = F[:, :n] - X[:, :n]
+                H[:, 1:n + 1, 1:n + 1] = torch.bmm(G, G.transpose(1, 2)) + lam * torch.eye(n)[None]
+                alpha = torch.linalg.solve(H[:, :n + 1, :n + 1], y[:, :n + 1])[:, 1:n + 1, 0]
+                xnew = beta * (alpha[:, None] @ F[:, :n])[:, 0] + (1 - beta) * (alpha[:, None] @ X[:, :n])[:, 0]
+                if k in (2, 5, 12, 25):
+                    G64 = G.double()
+                    H64 = torch.zeros(1, n + 1, n + 1, dtype=torch.float64); H64[:, 0, 1:] = H64[:, 1:, 0] = 1
+                    H64[:, 1:, 1:] = torch.bmm(G64, G64.transpose(1, 2)) + lam * torch.eye(n, dtype=torch.float64)[None]
+                    y64 = torch.zeros(1, n + 1, 1, dtype=torch.float64); y64[:, 0] = 1
+                    a64 = torch.linalg.solve(H64, y64)[:, 1:, 0]
+                    x64 = beta * (a64[:, None] @ F[:, :n].double())[:, 0] + (1 - beta) * (a64[:, None] @ X[:, :n].double())[:, 0]
+                    pre = 'andf%d_' % k
+                    z[pre + 'X'] = X[0, :n].numpy().copy(); z[pre + 'F'] = F[0, :n].numpy().copy()
+                    z[pre + 'x32'] = xnew[0].numpy().copy(); z[pre + 'x64'] = x64[0].numpy(); z[pre + 'alpha64'] = a64[0].numpy()
+                    z[pre + 'slot'] = np.int64(k % m); z[pre + 'n'] = np.int64(n)
+                    steps.append(k)
+                    print(k, 'fp32 vs fp64', float((xnew[0].double() - x64[0]).norm() / x64[0].norm()), 'alpha', a64[0].tolist())
+                X[:, k % m] = xnew
+                F[:, k % m] = fn(xnew.reshape_as(h0)).reshape(1, -1)
+            z['andf_steps'] = np.asarray(steps, np.int64); z['andf_m'] = np.int64(m); z['andf_lam'] = np.float64(lam); z['andf_beta'] = np.float64(beta)
+    np.savez_compressed(path, **z)
+    print('saved', os.path.getsize(path))
+
+
+
 def main():
+    if "--anderson-forced" in sys.argv:
+        append_anderson_forced()
+        return
     if "--baselines-only" in sys.argv:
         make_baseline_fixture("dirichlet/dss", 2, 30, 0.09, "dss_ckpt")
         make_baseline_fixture("dirichlet/dsgps", 2, 30, 0.09, "dsgps_ckpt")
+        make_baseline_fixture("mixed/dsgps", 2, 30, 0.09, "dsgps_mixed_ckpt")
         return
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     make_fixture("dirichlet/psignn", "ckpt", 3, 0, 0.075, "dirichlet_ckpt", forced=())
@@ -293,6 +371,8 @@ def main():
     make_fixture("mixed/psignn", "seed0", 2, 10, 0.11, "mixed_seed0")
     make_baseline_fixture("dirichlet/dss", 2, 30, 0.09, "dss_ckpt")
     make_baseline_fixture("dirichlet/dsgps", 2, 30, 0.09, "dsgps_ckpt")
+    make_baseline_fixture("mixed/dsgps", 2, 30, 0.09, "dsgps_mixed_ckpt")
+    append_anderson_forced()
 
 
 if __name__ == "__main__":

@@ -139,4 +139,5 @@ CHECKPOINTS = {
     "mixed/psignn": "mixed/psignn/results/best_model/ckpt/best_model.pt",
     "dirichlet/dss": "dirichlet/dss/results/dss_results/ckpt/best_model.pt",
     "dirichlet/dsgps": "dirichlet/dsgps/results/constant_dataset/30_ite_gamma_0_9/ckpt/best_model.pt",
+    "mixed/dsgps": "mixed/dsgps/results/30_ite_lamb_0_gamma_0_9/ckpt/best_model.pt",
 }

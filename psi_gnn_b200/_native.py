@@ -46,6 +46,8 @@ SIGNATURES = {
     "psi_layers_unrolled": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "psi_vjp_prepare": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "psi_vjp_apply": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "psi_param_grad": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "psi_pgrad_layout": (c_int, [POINTER(c_int32)]),
     "psi_residual": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "psi_spmv_t": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "psi_encode": (c_int, [c_int64, c_void_p, c_void_p, c_void_p]),
@@ -73,6 +75,7 @@ SIGNATURES = {
     "psi_anderson_x": (c_void_p, [c_void_p]),
     "psi_anderson_feed": (c_int, [c_void_p, c_void_p, POINTER(c_int), c_void_p]),
     "psi_anderson_finish": (c_int, [c_void_p, c_void_p, POINTER(SolveStats), POINTER(c_double), POINTER(c_double), c_void_p]),
+    "psi_anderson_forced_step": (c_int, [c_void_p, c_int, c_int, c_int, c_double, c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "psi_picard_begin": (c_int, [c_void_p, c_void_p, c_int, c_double, c_void_p, c_void_p]),
     "psi_picard_x": (c_void_p, [c_void_p]),
     "psi_picard_feed": (c_int, [c_void_p, c_void_p, POINTER(c_int), c_void_p]),

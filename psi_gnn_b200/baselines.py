@@ -5,8 +5,10 @@
 ``ModelDSGPS`` (reference dirichlet/dsgps/model.py:27-163): k steps of one GRU-gated recurrent layer + autoencoder.
 
 Class names, constructor signatures and ``state_dict`` keys are the reference's, so its checkpoints load; ``inference`` runs
-entirely on the extension (one weight-block upload + one layer launch per unrolled step).  The unrolled *training*
-forward/backward of the baselines is outside the accelerated path ("layer kernel reuse only").
+entirely on the extension (one weight-block upload + one layer launch per unrolled step).  ``forward`` (the unrolled training
+forward with the per-layer losses of the reference, differentiable) evaluates every layer through the differentiable torch form of
+the same layer (``_Phi`` + ``nn.Linear``): the baselines' unrolled backward has no native kernel ("layer kernel reuse
+only"); the residuals use the native SpMV.  ``ModelDSGPSMixed`` is the mixed-boundary variant (reference mixed/dsgps/model.py).
 """
 from __future__ import annotations
 
@@ -16,7 +18,7 @@ import torch.nn as nn
 from . import _native as N
 from . import weights as W
 from .graph import graph_of
-from .model import MLP, Autoencoder, Phi_from, Phi_to, initialize_weights_xavier
+from .model import MLP, Autoencoder, Phi_from, Phi_to, _ResidualLoss, initialize_weights_xavier
 
 
 class Psi(nn.Module):
@@ -96,11 +98,32 @@ class DeepStatisticalSolver(nn.Module):
         return _decode(out)
 
     def forward(self, batch):
-        raise NotImplementedError("psi_gnn_b200: the unrolled DSS training forward is outside the accelerated path; "
-                                  "use inference() (dirichlet/dss/model.py:106-127)")
+        """unrolled training forward (reference dirichlet/dss/model.py:59-104): k layers with per-layer decoders, flux-form residual of
+        every intermediate state weighted by gamma^(k-1-update).  Returns (U dict, loss_dic) like the reference."""
+        if not batch.edge_index.is_cuda:
+            raise RuntimeError("psi_gnn_b200: CUDA tensors required — there is no CPU path")
+        cfg = self.config
+        H, U, cumul_res, cumul_mse = {}, {}, {}, {}
+        total_loss = None
+        H['0'] = torch.zeros([batch.num_nodes, cfg["latent_dim"]], dtype=torch.float, device=batch.x.device)
+        U['0'] = self.decoder_list[0](H['0']) + batch.x * 0
+        cumul_res['0'] = self.residual_loss(U['0'], batch.edge_index, batch.a_ij, batch.b_prime)
+        cumul_mse['0'] = self.mse_loss(U['0'], batch.x)
+        for update in range(cfg["k"]):
+            h = H[str(update)]
+            mess_to = self.phi_to_list[update](h, batch.edge_index, batch.a_ij_norm)
+            mess_from = self.phi_from_list[update](h, batch.edge_index, batch.a_ij_norm)
+            correction = self.psi_list[update](torch.cat([h, mess_to, mess_from, batch.b_prime_norm], dim=1))
+            H[str(update + 1)] = h + cfg["alpha"] * correction
+            U[str(update + 1)] = self.decoder_list[update](H[str(update + 1)])
+            cumul_res[str(update + 1)] = self.residual_loss(U[str(update + 1)], batch.edge_index, batch.a_ij, batch.b_prime)
+            cumul_mse[str(update + 1)] = self.mse_loss(U[str(update + 1)], batch.x)
+            term = cumul_res[str(update + 1)] * cfg["gamma"] ** (cfg["k"] - update - 1)
+            total_loss = term if total_loss is None else total_loss + term
+        return U, {"train_loss": total_loss, "residual_loss": cumul_res, "mse_loss": cumul_mse}
 
     def residual_loss(self, U, edge_index, a_ij, y):
-        """flux-form residual of the reference (dirichlet/dss/model.py:129-148) — plain torch ops, monitoring only"""
+        """flux-form residual of the reference (dirichlet/dss/model.py:129-148)"""
         frm, to = edge_index
         p1 = (1 - y[:, 1:2]) * (-y[:, 0:1]) + y[:, 1:2] * (U - y[:, 2:3])
         flux = torch.zeros_like(U).index_add(0, frm, a_ij.reshape(-1, 1) * (U[to] - U[frm]))
@@ -109,6 +132,8 @@ class DeepStatisticalSolver(nn.Module):
 
 class ModelDSGPS(nn.Module):
     """config keys: latent_dim, k, alpha, gamma (reference dirichlet/dsgps/main.py)."""
+    KIND = N.KIND_DSGPS
+    SECOND = 2
 
     def __init__(self, config):
         super().__init__()
@@ -117,9 +142,9 @@ class ModelDSGPS(nn.Module):
         self.laynorm = nn.LayerNorm(d)
         self.phi_to = Phi_to([2 * d + 3, d, d], nn.ReLU())
         self.phi_from = Phi_from([2 * d + 3, d, d], nn.ReLU())
-        self.z_k = MLPActivation([3 * d + 2, d], nn.Sigmoid())
-        self.r_k = MLPActivation([3 * d + 2, d], nn.Sigmoid())
-        self.correction = MLPActivation([3 * d + 2, d], nn.Tanh())
+        self.z_k = MLPActivation([3 * d + self.SECOND, d], nn.Sigmoid())
+        self.r_k = MLPActivation([3 * d + self.SECOND, d], nn.Sigmoid())
+        self.correction = MLPActivation([3 * d + self.SECOND, d], nn.Tanh())
         self.autoencoder = Autoencoder([1, d, d], nn.ReLU())
         self.mse_loss = nn.MSELoss()
         self._blob = (None, None, None)
@@ -129,7 +154,7 @@ class ModelDSGPS(nn.Module):
             raise RuntimeError("psi_gnn_b200: CUDA tensors required — there is no CPU path")
         if self.config["latent_dim"] != W.D:
             raise NotImplementedError("psi_gnn_b200: the fused kernel is built for latent_dim=10")
-        g = graph_of(batch, N.KIND_DSGPS)
+        g = graph_of(batch, self.KIND)
         dev = batch.edge_index.device
         P = W.named_tensors(self)
         key = (W.version_key(P), str(dev))
@@ -146,10 +171,84 @@ class ModelDSGPS(nn.Module):
             return _decode(H0)
         work, out = torch.empty_like(H0), torch.empty_like(H0)
         with torch.cuda.device(dev):
-            N.check(N.load().psi_layers_unrolled(g.handle, N.KIND_DSGPS, N.ptr(self._blob[1]), 1, steps, N.ptr(H0), N.ptr(H0), N.ptr(work),
+            N.check(N.load().psi_layers_unrolled(g.handle, self.KIND, N.ptr(self._blob[1]), 1, steps, N.ptr(H0), N.ptr(H0), N.ptr(work),
                                                  N.ptr(out), N.stream_ptr()), "psi_layers_unrolled")
         return _decode(out)
 
+    def _step(self, h, h0, batch, dmask, nmask):
+        """one recurrent step in differentiable torch form (dirichlet/dsgps/model.py:64-78, mixed/dsgps/model.py:76-97)"""
+        mess_to = self.phi_to(h, batch.edge_index, batch.edge_attr)
+        mess_from = self.phi_from(h, batch.edge_index, batch.edge_attr)
+        c = torch.cat([h, mess_to, mess_from, batch.prb_data], dim=1)
+        alpha, reset = self.z_k(c), self.r_k(c)
+        corr = self.correction(torch.cat([reset * h, mess_to, mess_from, batch.prb_data], dim=1))
+        nxt = h + alpha * corr
+        if self.KIND == N.KIND_DSGPS_MIXED:
+            mp_neu = self.phi_neumann(h, batch.edge_index, batch.edge_attr)
+            upd = self.update_neumann(torch.cat([h, mp_neu, batch.prb_data, batch.unit_normal_vector], dim=1))
+            nxt = torch.where(nmask, upd, nxt)
+        return torch.where(dmask, h0, nxt)
+
+    def residual_loss(self, u, batch):
+        """mean((A u − y)²) on the native SpMV kernels (forward and backward), reference dirichlet/dsgps/model.py:165-176"""
+        return _ResidualLoss.apply(u, batch.y, graph_of(batch, self.KIND))
+
     def forward(self, batch):
-        raise NotImplementedError("psi_gnn_b200: the unrolled DSGPS training forward is outside the accelerated path; "
-                                  "use inference() (dirichlet/dsgps/model.py:133-163)")
+        """unrolled training forward with the per-step losses of the reference (dirichlet/dsgps/model.py:48-131, mixed/dsgps/
+        model.py:48-131): returns (U dict, loss_dic).  The mixed reference computes the encoder / autoencoder losses on detached
+        states, the dirichlet one by freezing the decoder / encoder parameters — both are reproduced."""
+        if not batch.edge_index.is_cuda:
+            raise RuntimeError("psi_gnn_b200: CUDA tensors required — there is no CPU path")
+        cfg = self.config
+        mixed = self.KIND == N.KIND_DSGPS_MIXED
+        t = batch.tags
+        dmask = ((t[:, 1] if mixed else t.reshape(-1)) == 1)[:, None]
+        nmask = (t[:, 2] == 1)[:, None] if mixed else None
+        index_dirichlet = torch.where(dmask[:, 0])[0]
+        H, U = {}, {}
+        cumul_res, cumul_mse, cumul_enc, cumul_autoenc, cumul_mse_dirichlet = {}, {}, {}, {}, {}
+        total_loss = None
+        U['0'] = batch.x
+        cumul_res['0'] = self.residual_loss(U['0'], batch)
+        cumul_mse['0'] = self.mse_loss(U['0'], batch.sol)
+        H['0'] = self.autoencoder.encoder(U['0'])
+        enc, dec = self.autoencoder.encoder, self.autoencoder.decoder
+        for update in range(cfg["k"]):
+            key = str(update + 1)
+            H[key] = self._step(H[str(update)], H['0'], batch, dmask, nmask)
+            U[key] = dec(H[key])
+            cumul_res[key] = self.residual_loss(U[key], batch)
+            cumul_mse[key] = self.mse_loss(U[key], batch.sol)
+            if mixed:
+                u_d, h_d = U[key].detach(), H[key].detach()
+                cumul_enc[key] = self.mse_loss(enc(u_d), h_d)
+                cumul_autoenc[key] = self.mse_loss(dec(enc(u_d).detach()), u_d)
+            else:
+                for p in dec.parameters():
+                    p.requires_grad = False
+                cumul_enc[key] = self.mse_loss(self.autoencoder(H[key], sens="latent"), H[key])
+                for p in dec.parameters():
+                    p.requires_grad = True
+                for p in enc.parameters():
+                    p.requires_grad = False
+                cumul_autoenc[key] = self.mse_loss(self.autoencoder(U[key], sens="physics"), U[key])
+                for p in enc.parameters():
+                    p.requires_grad = True
+            cumul_mse_dirichlet[key] = self.mse_loss(U[key][index_dirichlet, :], batch.sol[index_dirichlet, :])
+            term = cumul_res[key] * cfg["gamma"] ** (cfg["k"] - update - 1) + cumul_enc[key] + cumul_autoenc[key]
+            total_loss = term if total_loss is None else total_loss + term
+        return U, {"train_loss": total_loss, "residual_loss": cumul_res, "encoder_loss": cumul_enc, "autoencoder_loss": cumul_autoenc,
+                   "mse_dirichlet": cumul_mse_dirichlet, "mse_loss": cumul_mse}
+
+
+class ModelDSGPSMixed(ModelDSGPS):
+    """mixed Dirichlet/Neumann DSGPS (reference mixed/dsgps/model.py:27-131): 3-column second member and one-hot tags, Neumann rows
+    overwritten by ``update_neumann(cat[H, Σphi_neumann, prb, n̂])`` before the Dirichlet clamp.  Native layer kind 4."""
+    KIND = N.KIND_DSGPS_MIXED
+    SECOND = 3
+
+    def __init__(self, config):
+        super().__init__(config)
+        d = config["latent_dim"]
+        self.phi_neumann = Phi_from([2 * d + 3, d, d], nn.ReLU())
+        self.update_neumann = MLP([2 * d + 5, d, d], nn.ReLU())

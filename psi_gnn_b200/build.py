@@ -45,6 +45,15 @@ def is_current() -> bool:
         return f.read().strip() == source_hash()
 
 
+def build_variant(path: str, defines) -> str:
+    """an experimental build with extra -D macros into another file (select it with PSI_GNN_B200_LIB=<path>); used for A/B timing"""
+    cmd = [_nvcc()] + NVCC_FLAGS + ["-D" + d for d in defines] + ["-o", path, os.path.join(CSRC, "psignn_b200.cu")]
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + proc.stdout + proc.stderr)
+    return path
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile the extension if the sources changed since the last build; returns the .so path."""
     if not force and is_current():

@@ -167,10 +167,11 @@ __global__ void k_and_fin(const float* __restrict__ norm_part, int norm_blocks, 
     }
 }
 
-// lowest_xest = X[slot].clone() when this step improved (solver.py:268-269)
+// lowest_xest = X[slot].clone() when this step improved (solver.py:268-269).  `k` is the step this launch belongs to: launches
+// queued behind the stop see the control block of the LAST executed step (k_and_fin no longer runs) and must not copy anything.
 __global__ void __launch_bounds__(QN_THREADS)
-k_and_keep(const float* __restrict__ xs, float* __restrict__ best, int num_chunks, QnCtrl* __restrict__ ctrl) {
-    if (!ctrl->improved) return;
+k_and_keep(const float* __restrict__ xs, float* __restrict__ best, int num_chunks, QnCtrl* __restrict__ ctrl, int k) {
+    if (!ctrl->improved || ctrl->nstep != k) return;
     for (int chunk = blockIdx.x; chunk < num_chunks; chunk += gridDim.x) {
         const int64_t e0 = (int64_t)chunk * QN_CHUNK + threadIdx.x * 4;
         *reinterpret_cast<float4*>(best + e0) = *reinterpret_cast<const float4*>(xs + e0);

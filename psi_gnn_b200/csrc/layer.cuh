@@ -4,11 +4,10 @@
 //                    concatenation [h_i, h_j, a], so its h_j block is a per-SOURCE quantity: the per-edge work
 //                    drops from 130 to 30 FMAs + 10 adds.
 //   k_layer_forward  one thread owns one destination node (one warp = one 32-node slice of the SELL lists):
-//     1. coalesced 16-byte edge records {j, a0, a1, a2}; the 32 neighbour rows Q[j] of a trip (48-byte padded rows) are gathered
-//        COOPERATIVELY: lane l loads the 16-byte pieces l, l+32, l+64 of the 32·48 B the warp needs (consecutive pieces of
-//        consecutive rows → a few cache lines per load instead of 32), stages them in shared memory and reads its own row back with
-//        two LDS.128 + one LDS.64.  One thread gathering its own row made the kernel L1-wavefront bound (ncu:
-//        profiles/r02_a_operator.md); rows of trip t+1 are in flight while trip t is consumed.
+//     1. coalesced 16-byte edge records {j, a0, a1, a2}; every lane gathers the 48-byte padded row Q[j] of its neighbour with three
+//        16-byte loads (two trips in flight).  The round-1 kernel gathered h[j] with five 8-byte loads per edge and was bound by L1
+//        wavefronts (ncu: profiles/r02_a_operator.md); a cooperative shared-memory staged gather (walk_ring below) halves the
+//        wavefronts again but costs more instructions than it saves once the arithmetic is packed.
 //     The contractions are packed fp32x2 FMAs (FFMA2: two output channels per issue slot, bit-identical to scalar fma chains).
 //     2. z_e = (P_i + Q_j) + W1a·a_e with P_i = b1 + W1i·h_i hoisted per destination; ReLU; summed per destination in CSR order
 //        (deterministic, no atomics); the second edge layer is applied once to the sum:
@@ -237,12 +236,52 @@ __device__ __forceinline__ void walk_ring(const REC* __restrict__ recs, int widt
     }
 }
 
+// The same walk with every lane gathering its own 48-byte row (three 16-byte loads, no staging, no shuffles): more cache lines per
+// load instruction (one per lane) but a third of the instructions around the loads and far fewer live registers.  Two trips per
+// iteration so that both records and both rows are in flight before the arithmetic of either starts.
+__device__ __forceinline__ void row_direct(const float* __restrict__ src, int rowidx, f2 (&q)[PSI_D / 2]) {
+    const float4* p = reinterpret_cast<const float4*>(src + (size_t)(unsigned)rowidx * PSI_QPITCH);
+    const float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+    q[0] = pk(a.x, a.y); q[1] = pk(a.z, a.w); q[2] = pk(b.x, b.y); q[3] = pk(b.z, b.w); q[4] = pk(c.x, c.y);
+}
+template <class REC, class Key, class Body>
+__device__ __forceinline__ void walk_direct(const REC* __restrict__ recs, int width, const float* __restrict__ src, int lane, Key&& key, Body&& body) {
+    const REC* p = recs + lane;
+    int t = 0;
+    for (; t + 1 < width; t += 2) {
+        const REC r0 = ld_rec(p + 32 * t), r1 = ld_rec(p + 32 * (t + 1));
+        f2 q0[PSI_D / 2], q1[PSI_D / 2];
+        row_direct(src, key(r0), q0);
+        row_direct(src, key(r1), q1);
+        body(r0, q0);
+        body(r1, q1);
+    }
+    if (t < width) {
+        const REC r0 = ld_rec(p + 32 * t);
+        f2 q0[PSI_D / 2];
+        row_direct(src, key(r0), q0);
+        body(r0, q0);
+    }
+}
+
+// Measured on B200 (ncu gpu__time_duration, profiles/r02_b_operator_ab.md): k_layer_forward<dirichlet> at C5 (1 M nodes) 106 µs
+// direct vs 148 µs cooperative (196 µs for the round-1 kernel: one thread gathering its row of h with five 8-byte loads and doing
+// the full 23→10 contraction per edge), at C3 (131 k nodes) 19.7 µs vs 30 µs (30.3 µs).  The cooperative walk halves the L1
+// wavefronts per trip but spends ≈ 45 more instructions per trip on shuffles, staging and synchronisation — with the packed FMAs the
+// kernel is issue-bound, so the simpler walk wins.  walk_ring stays as the documented alternative (-DPSI_GATHER_DIRECT=0).
+#ifndef PSI_GATHER_DIRECT
+#define PSI_GATHER_DIRECT 1              // 1: every lane gathers its own row (walk_direct); 0: cooperative staged gather (walk_ring)
+#endif
 template <class RowIdx, class Body>
 __device__ __forceinline__ void walk_list(const SellDev& L, const float* __restrict__ src, int slice, int lane, WarpStage& W, const CoopMap& M,
                                           RowIdx&& rowidx_of, Body&& body) {
     const int64_t base = L.slice_off[slice];
     const int width = (int)((L.slice_off[slice + 1] - base) >> 5);
+#if PSI_GATHER_DIRECT
+    walk_direct(L.recs + base, width, src, lane, [&](const int4& r) { return r.x >= 0 ? rowidx_of(r.x) : 0; }, body);
+#else
     walk_ring(L.recs + base, width, src, lane, W, M, [&](const int4& r) { return r.x >= 0 ? rowidx_of(r.x) : 0; }, body);
+#endif
 }
 
 __device__ __forceinline__ float sigmoidf_acc(float s) { return 1.0f / (1.0f + expf(-s)); }

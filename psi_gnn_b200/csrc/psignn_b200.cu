@@ -13,6 +13,7 @@
 #include "anderson.cuh"
 #include "qn_tma.cuh"
 #include "comm.cuh"
+#include "pgrad.cuh"
 
 #include <algorithm>
 #include <cstring>
@@ -471,15 +472,15 @@ extern "C" int psi_vjp_prepare(psi_graph_t* g, int kind, const float* dev_hstar,
 }
 
 template <bool EPI>
-static int launch_vjp(psi_graph* g, int kind, const float* y, const float* grad, float* out, SolverEpi E, cudaStream_t st) {
+static int launch_vjp(psi_graph* g, int kind, const float* y, const float* grad, float* out, SolverEpi E, cudaStream_t st, float* acc_out = nullptr) {
     if (g->dev.n_compute == 0) return 0;
     const unsigned grid = node_grid(g->dev.n_compute);
     if (kind == PSI_KIND_DIRICHLET) k_vjp_phase_a<KIND_DIRICHLET><<<grid, PSI_NODE_BLOCK, 0, st>>>(g->dev, g->vjp, y, E.done);
     else k_vjp_phase_a<KIND_MIXED><<<grid, PSI_NODE_BLOCK, 0, st>>>(g->dev, g->vjp, y, E.done);
     // mesh partition: S̄ of the ghost rows comes from their owners between the two phases (y itself is needed on owned rows only)
     if (g->part != nullptr && halo_refresh(g, g->vjp.Sb, 1, E.done, st)) return -1;
-    if (kind == PSI_KIND_DIRICHLET) k_vjp_phase_b<KIND_DIRICHLET, EPI><<<grid, PSI_NODE_BLOCK, 0, st>>>(g->dev, g->vjp, y, grad, out, E);
-    else k_vjp_phase_b<KIND_MIXED, EPI><<<grid, PSI_NODE_BLOCK, 0, st>>>(g->dev, g->vjp, y, grad, out, E);
+    if (kind == PSI_KIND_DIRICHLET) k_vjp_phase_b<KIND_DIRICHLET, EPI><<<grid, PSI_NODE_BLOCK, 0, st>>>(g->dev, g->vjp, y, grad, out, E, acc_out);
+    else k_vjp_phase_b<KIND_MIXED, EPI><<<grid, PSI_NODE_BLOCK, 0, st>>>(g->dev, g->vjp, y, grad, out, E, acc_out);
     PSI_CK_LAUNCH();
     return 0;
 }
@@ -489,6 +490,57 @@ extern "C" int psi_vjp_apply(psi_graph_t* g, int kind, const float* dev_y, const
     if (!g->vjp_ready || g->vjp_kind != kind) PSI_FAIL("psi_vjp_apply: call psi_vjp_prepare first");
     if (g->N > 0 && (dev_y == nullptr || dev_out == nullptr)) PSI_FAIL("psi_vjp_apply: null pointer");
     return launch_vjp<false>(g, kind, dev_y, dev_grad, dev_out, SolverEpi{nullptr, nullptr, nullptr, nullptr}, as_stream(stream));
+}
+
+// θ̄ = (∂f/∂θ at the prepared point)ᵀ ȳ as a flat vector in the layout of the packed weight block (psi_weights_floats() floats, only
+// the LayerWeights part is written); also returns Jᵀȳ (dev_jty, may be NULL).  tab_*: the table of psi_gnn_b200/weights.py.
+extern "C" int psi_param_grad(psi_graph_t* g, int kind, const float* dev_hstar, const float* dev_ybar, const int32_t* dev_tab_dst,
+                              const int32_t* dev_tab_y, const int32_t* dev_tab_x, int n_tab, float* dev_out, float* dev_jty, void* stream) {
+    if (check_kind(g, kind)) return -1;
+    if (kind != PSI_KIND_DIRICHLET && kind != PSI_KIND_MIXED) PSI_FAIL("psi_param_grad: implemented for the PSI-GNN layers");
+    if (!g->vjp_ready || g->vjp_kind != kind) PSI_FAIL("psi_param_grad: call psi_vjp_prepare (at the same H*) first");
+    if (n_tab < 1 || n_tab > PG_NODES * PG_MAX_PER_THREAD) PSI_FAIL("psi_param_grad: table size out of range");
+    if (dev_out == nullptr || dev_tab_dst == nullptr || dev_tab_y == nullptr || dev_tab_x == nullptr) PSI_FAIL("psi_param_grad: null pointer");
+    cudaStream_t st = as_stream(stream);
+    PSI_CK(cudaMemsetAsync(dev_out, 0, sizeof(LayerWeights), st));
+    if (g->N == 0) return 0;
+    if (dev_hstar == nullptr || dev_ybar == nullptr) PSI_FAIL("psi_param_grad: null pointer");
+    const float* hs = (g->part != nullptr && g->p_hstar != nullptr) ? g->p_hstar : dev_hstar;
+    float *acc = nullptr, *partial = nullptr, *jty = dev_jty;
+    PSI_CK(psi_malloc_async((void**)&acc, (size_t)g->N * 30 * sizeof(float), st));
+    if (jty == nullptr) PSI_CK(psi_malloc_async((void**)&jty, (size_t)g->N * PSI_D * sizeof(float), st));
+    const SolverEpi noE{nullptr, nullptr, nullptr, nullptr};
+    int rc = launch_vjp<false>(g, kind, dev_ybar, nullptr, jty, noE, st, acc);
+    const int num_batches = (int)((g->dev.n_compute + PG_NODES - 1) / PG_NODES);
+    const int grid = std::max(1, std::min(num_batches, PSI_NUM_SMS_B200 * 2));
+    if (!rc && psi_malloc_async((void**)&partial, (size_t)grid * n_tab * sizeof(float), st) != cudaSuccess) { g_psi_err = "psi_param_grad: out of device memory"; rc = -1; }
+    if (!rc) {
+        const size_t smem = (size_t)PG_NODES * PG_PITCH * sizeof(float);
+        static bool attr_done = false;
+        if (!attr_done) {
+            cudaFuncSetAttribute(k_pgrad<KIND_DIRICHLET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaFuncSetAttribute(k_pgrad<KIND_MIXED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            attr_done = true;
+        }
+        if (kind == PSI_KIND_DIRICHLET)
+            k_pgrad<KIND_DIRICHLET><<<grid, PG_NODES, smem, st>>>(g->dev, g->vjp, hs, dev_ybar, acc, dev_tab_y, dev_tab_x, n_tab, partial, num_batches);
+        else
+            k_pgrad<KIND_MIXED><<<grid, PG_NODES, smem, st>>>(g->dev, g->vjp, hs, dev_ybar, acc, dev_tab_y, dev_tab_x, n_tab, partial, num_batches);
+        k_pgrad_reduce<<<(n_tab + 127) / 128, 128, 0, st>>>(partial, grid, n_tab, dev_tab_dst, dev_out);
+        if (cudaGetLastError() != cudaSuccess) { g_psi_err = "psi_param_grad: kernel launch failed"; rc = -1; }
+    }
+    psi_free_async(acc, st);
+    psi_free_async(partial, st);
+    if (dev_jty == nullptr) psi_free_async(jty, st);
+    return rc;
+}
+
+// record layout of pgrad.cuh for the table builder: {PG_ONE, PG_DEG, PG_C, PG_CN, PG_YB, PG_RHAT, PG_MB, PG_HID, PG_TB, PG_SB, PG_EDGE,
+// PG_ACC, PG_MBN, PG_HIDN, PG_TBN, PG_REC}
+extern "C" int psi_pgrad_layout(int32_t out[16]) {
+    const int32_t v[16] = {PG_ONE, PG_DEG, PG_C, PG_CN, PG_YB, PG_RHAT, PG_MB, PG_HID, PG_TB, PG_SB, PG_EDGE, PG_ACC, PG_MBN, PG_HIDN, PG_TBN, PG_REC};
+    for (int i = 0; i < 16; ++i) out[i] = v[i];
+    return 0;
 }
 
 extern "C" int psi_residual(const psi_graph_t* g, const float* dev_u, const float* dev_y, float* dev_r, float* dev_mean_sq, void* stream) {
@@ -1154,7 +1206,7 @@ static int and_advance(psi_solver* s, cudaStream_t st) {
     } else if (e >= 2) {
         k_and_post<<<s->num_chunks, QN_THREADS, 0, st>>>(xs, fs, s->best, s->norm_part, s->num_chunks, &s->ctrl->done);
         k_and_fin<<<1, 32, 0, st>>>(s->norm_part, s->num_chunks, s->ctrl, s->rel_trace, s->abs_trace, e, s->eps);
-        k_and_keep<<<s->axpy_ctas, QN_THREADS, 0, st>>>(xs, s->best, s->num_chunks, s->ctrl);
+        k_and_keep<<<s->axpy_ctas, QN_THREADS, 0, st>>>(xs, s->best, s->num_chunks, s->ctrl, e);
         PSI_CK_LAUNCH();
         s->launches += 3;
         if (s->xtrace != nullptr)                                                          // xest_trace.append(lowest_xest) (:273)
@@ -1223,6 +1275,34 @@ extern "C" int psi_solver_anderson(psi_solver_t* s, psi_graph_t* g, int kind, co
         }
     }
     return and_finish(s, dev_result, stats, rel_trace, abs_trace, st);
+}
+
+// ---- teacher-forced single Anderson update (parity tests): window (X, F) of n vectors in, X[slot] = β·Σα_iF_i + (1−β)·Σα_iX_i and α out
+extern "C" int psi_anderson_forced_step(psi_solver_t* s, int m, int n, int slot, double lam, double beta, const float* dev_X, const float* dev_F,
+                                        float* dev_xnew, float* dev_alpha, void* stream) {
+    if (s == nullptr) PSI_FAIL("psi_anderson_forced_step: null solver");
+    if (m < 2 || m > AND_MAX_M || n < 1 || n > m || slot < 0 || slot >= m) PSI_FAIL("psi_anderson_forced_step: bad window");
+    if (s->numel == 0) return 0;
+    cudaStream_t st = as_stream(stream);
+    if (and_ensure(s, m)) return -1;
+    const size_t vb = s->stride * sizeof(float);
+    PSI_CK(cudaMemsetAsync(s->and_X, 0, (size_t)m * vb, st));
+    PSI_CK(cudaMemsetAsync(s->and_F, 0, (size_t)m * vb, st));
+    for (int i = 0; i < n; ++i) {
+        PSI_CK(cudaMemcpyAsync(s->and_X + (size_t)i * s->stride, dev_X + (size_t)i * s->numel, s->numel * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        PSI_CK(cudaMemcpyAsync(s->and_F + (size_t)i * s->stride, dev_F + (size_t)i * s->numel, s->numel * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    }
+    k_qn_ctrl_init<<<1, 1, 0, st>>>(s->ctrl, nullptr);
+    float* part = s->and_small;
+    float* alpha = s->and_small + (size_t)AND_MAX_M * AND_MAX_M * s->num_chunks;
+    k_and_gram<<<s->num_chunks, QN_THREADS, 0, st>>>(s->and_X, s->and_F, s->stride, n, part, s->num_chunks, &s->ctrl->done);
+    k_and_solve<<<1, 32, 0, st>>>(part, s->num_chunks, n, (float)lam, alpha, &s->ctrl->done);
+    k_and_mix<<<s->axpy_ctas, QN_THREADS, 0, st>>>(s->and_X, s->and_F, s->stride, n, slot, alpha, (float)beta, s->num_chunks, &s->ctrl->done);
+    PSI_CK_LAUNCH();
+    if (dev_xnew) PSI_CK(cudaMemcpyAsync(dev_xnew, s->and_X + (size_t)slot * s->stride, s->numel * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (dev_alpha) PSI_CK(cudaMemcpyAsync(dev_alpha, alpha, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    s->last_act = -1;
+    return 0;
 }
 
 // ---- step API (arbitrary operator): begin ; loop { fx = f(psi_anderson_x()) ; psi_anderson_feed(fx) -> done? } ; finish ----------

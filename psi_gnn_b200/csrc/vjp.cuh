@@ -277,10 +277,21 @@ k_vjp_phase_a(GraphDev G, VjpCacheDev C, const float* __restrict__ y, const int*
     store_row12(C.Sb, (int64_t)G.N + node, SbF);
 }
 
+// phase B's per-record work is ten selects and adds: the staged cooperative gather costs more instructions than it saves cache
+// wavefronts there (measured: 22.0 µs vs 17.8 µs at C3, 108 µs vs 102 µs at C5), so its rows are gathered directly
+#ifndef PSI_VJP_GATHER_DIRECT
+#define PSI_VJP_GATHER_DIRECT 1
+#endif
+#if PSI_VJP_GATHER_DIRECT
+#define PSI_WALK_B(recs, width, src, lane, W, M, key, body) walk_direct(recs, width, src, lane, key, body)
+#else
+#define PSI_WALK_B(recs, width, src, lane, W, M, key, body) walk_ring(recs, width, src, lane, W, M, key, body)
+#endif
+
 template <int KIND, bool EPI>
 __global__ void __launch_bounds__(PSI_NODE_BLOCK, PSI_OP_MIN_CTAS)
 k_vjp_phase_b(GraphDev G, VjpCacheDev C, const float* __restrict__ y, const float* __restrict__ grad,
-              float* __restrict__ out, SolverEpi E) {
+              float* __restrict__ out, SolverEpi E, float* __restrict__ acc_out /* optional [N][30]: the gathered sums themselves (pgrad.cuh) */) {
     __shared__ WarpStage stage[PSI_NODE_BLOCK / 32];
     __shared__ float smem[2 * PSI_NODE_BLOCK / 32];
     if (EPI && *E.done) return;
@@ -305,7 +316,7 @@ k_vjp_phase_b(GraphDev G, VjpCacheDev C, const float* __restrict__ y, const floa
         {
             const int64_t base = G.F.slice_off[slice];
             const int width = (int)((G.F.slice_off[slice + 1] - base) >> 5);
-            walk_ring(reinterpret_cast<const int2*>(G.F.xmask) + base, width, C.Sb, lane, W, M,
+            PSI_WALK_B(reinterpret_cast<const int2*>(G.F.xmask) + base, width, C.Sb, lane, W, M,
                       [&](const int2& jm) { return jm.y ? jm.x : 0; },
                       [&](const int2& jm, const f2 (&q2)[PSI_D / 2]) {
                           float sb[PSI_D];
@@ -319,7 +330,7 @@ k_vjp_phase_b(GraphDev G, VjpCacheDev C, const float* __restrict__ y, const floa
         {
             const int64_t base = G.T.slice_off[slice];
             const int width = (int)((G.T.slice_off[slice + 1] - base) >> 5);
-            walk_ring(reinterpret_cast<const int2*>(G.T.xmask) + base, width, C.Sb, lane, W, M,
+            PSI_WALK_B(reinterpret_cast<const int2*>(G.T.xmask) + base, width, C.Sb, lane, W, M,
                       [&](const int2& jm) { return jm.y ? N + jm.x : 0; },
                       [&](const int2& jm, const f2 (&q2)[PSI_D / 2]) {
                           float sb[PSI_D];
@@ -338,6 +349,11 @@ k_vjp_phase_b(GraphDev G, VjpCacheDev C, const float* __restrict__ y, const floa
                               for (int o = 0; o < PSI_D; ++o) accF[o] += ((xm >> o) & 1u) ? sb[o] : 0.f;
                           }
                       });
+        }
+        if (valid && acc_out != nullptr) {
+            store_row(acc_out, (int64_t)node * 3 + 0, accT);
+            store_row(acc_out, (int64_t)node * 3 + 1, accF);
+            store_row(acc_out, (int64_t)node * 3 + 2, accN);
         }
         if (valid) {
             load_row_rw(C.Dloc, node, res);

@@ -4,3 +4,5 @@ from ...model import (MLP, Phi_to, Phi_from, Encoder, Decoder, Autoencoder, Deep
                       initialize_weights_xavier, jac_loss_estimate, power_method)
 from ...model import FunctionDirichlet as Function              # noqa: F401
 from ...model import ModelDEQDSSDirichlet as ModelDEQDSS        # noqa: F401
+# evaluation-form variants of the reference's tests/model_psignn.py (solver dict out of the DEQ wrapper, `nsteps` in the loss dict)
+from ...model import ModelPSIGNN, ModelPSIGNNIterative          # noqa: F401,E402

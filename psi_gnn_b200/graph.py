@@ -78,6 +78,19 @@ class NativeGraph:
             N.check(N.load().psi_vjp_apply(self.handle, kind, N.ptr(y), N.ptr(g), N.ptr(out), N.stream_ptr()), "psi_vjp_apply")
         return out
 
+    def param_grad(self, kind: int, hstar: torch.Tensor, ybar: torch.Tensor, want_jty: bool = False):
+        """θ̄ = (∂f/∂θ)ᵀ ȳ at the prepared point as a flat vector in packed-block layout (weights.unpack_psignn_grads turns it into
+        per-parameter gradients) — native, deterministic; optionally also Jᵀȳ"""
+        from . import weights as W
+        hs, yb = N.f32(hstar), N.f32(ybar)
+        dst, ty, tx = W.grad_table_device(kind == N.KIND_MIXED, self.device)
+        out = torch.zeros(W.TOTAL_FLOATS, dtype=torch.float32, device=self.device)
+        jty = torch.empty_like(yb) if want_jty else None
+        with torch.cuda.device(self.device):
+            N.check(N.load().psi_param_grad(self.handle, kind, N.ptr(hs), N.ptr(yb), N.ptr(dst), N.ptr(ty), N.ptr(tx), int(dst.numel()),
+                                            N.ptr(out), N.ptr(jty), N.stream_ptr()), "psi_param_grad")
+        return (out, jty) if want_jty else out
+
     def residual(self, u: torch.Tensor, y: torch.Tensor, want_vector: bool = False):
         """(mean((A u − y)²), residual vector or None)  — dirichlet/psignn/model.py:157-167."""
         u = N.f32(u.reshape(-1))

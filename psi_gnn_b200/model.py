@@ -6,9 +6,10 @@ boundary-condition family.  What runs where:
 
 * forward fixed-point solve, backward implicit-adjoint solve, ``inference``, residual, encoder/decoder in
   inference, spectral-radius power iteration: CUDA kernels behind the C ABI (include/psignn_b200.h);
-* the *single* differentiable re-application ``f(H*)`` per training step (reference model.py:204-207), whose
-  autograd graph carries the parameter gradients and the Jacobian regulariser's double backward: torch ops on
-  the same device (≈1 of ≈660 evaluations of a step).
+* the differentiable re-application ``f(H*)`` of a training step (reference model.py:204-205) and everything its backward needs — the
+  implicit-adjoint solve and the parameter gradients — run on the extension too (``_ImplicitLayer`` / ``psi_param_grad``);
+* only the Hutchinson Jacobian regulariser (model.py:207, ``create_graph=True``) keeps a torch-op evaluation of the layer, for its
+  double backward (1 of ≈ 560 operator evaluations of a step).
 CPU tensors raise ``RuntimeError`` everywhere — there is no CPU path.
 """
 from __future__ import annotations
@@ -261,6 +262,47 @@ def power_method(f0, z0, n_iters=200, operator: Optional[_solver.VjpOperator] = 
 
 
 # ---------------------------------------------------------------------------------------------------------
+# the differentiable application f(H*) of a training step: native forward, native implicit backward, native parameter gradients
+# ---------------------------------------------------------------------------------------------------------
+class _ImplicitLayer(autograd.Function):
+    """``new_H_star = f(H_star, H_init, batch)`` of reference model.py:204-205 together with its backward hook (:210-223).
+
+    forward : one launch of the fused layer kernels.
+    backward: (1) the implicit-adjoint solve y = Jᵀy + grad (what the reference's hook does), (2) the parameter gradients
+    (∂f/∂θ)ᵀy with ``psi_param_grad`` — per-node products reduced in a fixed order, no atomics, so a training step is
+    deterministic — and (3) the gradient to ``H_init`` (f copies the Dirichlet rows of it)."""
+
+    @staticmethod
+    def forward(ctx, deq, batch, H_star, H_init, *params):
+        f = deq.f
+        g = f.native_graph(batch)
+        f.upload_weights(H_star.device)
+        ctx.deq, ctx.batch = deq, batch
+        ctx.save_for_backward(H_star, H_init)
+        return g.layer_forward(f.kind, H_star.detach(), H_init.detach())
+
+    @staticmethod
+    def backward(ctx, grad):
+        deq, batch = ctx.deq, ctx.batch
+        H_star, H_init = ctx.saved_tensors
+        f = deq.f
+        op = _solver.VjpOperator(f, H_star, batch, grad.contiguous())
+        out_bw = deq._solve(op, torch.zeros_like(grad), "bw_thres", "bw_tol")
+        deq.last_backward = out_bw
+        deq._log("backward_iteration.csv", '\n{} \t {}'.format(out_bw['lowest'], out_bw['nstep']))
+        y = out_bw['result'].contiguous()
+        mixed = f.kind == N.KIND_MIXED
+        op.upload()
+        flat = op.graph.param_grad(f.kind, H_star, y)
+        names = ["deqdss.f." + n for n, _ in f.named_parameters()]
+        grads = W.unpack_psignn_grads(flat, names, mixed)
+        t = batch.tags
+        dmask = ((t[:, 1] if mixed else t.reshape(-1)) == 1)[:, None]
+        g_init = torch.where(dmask, y, torch.zeros_like(y)) if ctx.needs_input_grad[3] else None
+        return (None, None, None, g_init) + tuple(grads[n].clone() if n in grads else None for n in names)
+
+
+# ---------------------------------------------------------------------------------------------------------
 # DEQ wrapper
 # ---------------------------------------------------------------------------------------------------------
 class DeepEquilibrium(nn.Module):
@@ -293,21 +335,12 @@ class DeepEquilibrium(nn.Module):
 
         if torch.is_grad_enabled():
             self._log("forward_iteration.csv", '\n{} \t {}'.format(out_fw['lowest'], out_fw['nstep']))
-            H_star.requires_grad_()
-            new_H_star = self.f(H_star, H_init, batch)
-            jac_loss = jac_loss_estimate(new_H_star, H_star, vecs=1)
-
-            def backward_hook(grad):
-                if self.hook is not None:
-                    self.hook.remove()
-                    torch.cuda.synchronize()
-                op = _solver.VjpOperator(self.f, H_star, batch, grad)
-                out_bw = self._solve(op, torch.zeros_like(grad), "bw_thres", "bw_tol")
-                self.last_backward = out_bw
-                self._log("backward_iteration.csv", '\n{} \t {}'.format(out_bw['lowest'], out_bw['nstep']))
-                return out_bw['result']
-
-            self.hook = new_H_star.register_hook(backward_hook)
+            # new_H_star = f(H*) with the reference's backward hook folded into its backward: native solve + native parameter gradients
+            new_H_star = _ImplicitLayer.apply(self, batch, H_star, H_init, *list(self.f.parameters()))
+            # Hutchinson Jacobian regulariser ‖Jᵀv‖²/numel with create_graph=True (reference model.py:207, :416-435): its double
+            # backward runs through the torch form of the layer (one evaluation per step)
+            Hs = H_star.detach().requires_grad_()
+            jac_loss = jac_loss_estimate(self.f._forward_torch(Hs, H_init.detach(), batch), Hs, vecs=1)
         else:
             with torch.enable_grad():
                 H_star.requires_grad_()
@@ -464,3 +497,55 @@ class ModelDEQDSSDirichlet(_ModelBase):
 class ModelDEQDSSMixed(_ModelBase):
     _function_cls = FunctionMixed
     _second_member_dim = 3
+
+
+# ---------------------------------------------------------------------------------------------------------
+# evaluation-form variants (reference tests/model_psignn.py): the DEQ wrapper returns the raw solver dict
+# ---------------------------------------------------------------------------------------------------------
+class DeepEquilibriumEval(DeepEquilibrium):
+    """``DeepEquilibrium`` of tests/model_psignn.py:216-250: ``forward`` is the forward solve only and returns the solver dict."""
+
+    def forward(self, H_init, batch, keep_trace=None):
+        return self.inference(H_init, batch, keep_trace=keep_trace)
+
+
+class _ModelEvalBase(_ModelBase):
+    def __init__(self, config):
+        super().__init__(config)
+        f = self.deqdss.f
+        self.deqdss = DeepEquilibriumEval(function=f, config_deq=self.config_deq)
+
+
+class ModelPSIGNN(_ModelEvalBase):
+    """tests/model_psignn.py:28-112: ``forward(batch) -> (u_final, loss_dic)`` with ``loss_dic['nsteps']``, no Jacobian term, forward
+    solve only (evaluation form; runs entirely on the native kernels — nothing here is differentiated)."""
+
+    def forward(self, batch):
+        if not batch.x.is_cuda:
+            raise RuntimeError("psi_gnn_b200: CUDA tensors required — there is no CPU path")
+        loss_dic = {}
+        with torch.no_grad():
+            h_initial = self._encode_native(batch.x)
+            out = self.deqdss(h_initial, batch)
+            h_final, nsteps = out["result"], out["nstep"]
+            u_final = self._decode_native(h_final)
+            residual_loss = self.residual_loss(u_final, batch)
+            encoder_loss = self.mse_loss(self._encode_native(u_final), h_final)
+            autoencoder_loss = self.mse_loss(self._decode_native(self._encode_native(u_final)), u_final)
+            mse = self.mse_loss(u_final, batch.sol)
+            index_dirichlet = self._dirichlet_index(batch)
+            mse_dirichlet = self.mse_loss(u_final[index_dirichlet, :], batch.x[index_dirichlet, :])
+        loss_dic["residual_loss"] = residual_loss
+        loss_dic["encoder_loss"] = encoder_loss
+        loss_dic["autoencoder_loss"] = autoencoder_loss
+        loss_dic["mse_loss"] = mse
+        loss_dic["mse_dirichlet_loss"] = mse_dirichlet
+        loss_dic["nsteps"] = nsteps
+        return u_final, loss_dic
+
+
+class ModelPSIGNNIterative(_ModelEvalBase):
+    """tests/model_psignn.py:114-214: decodes every Broyden iterate (``forward(batch) -> out_dic``)."""
+
+    def forward(self, batch):
+        return self.iterative_inference(batch)

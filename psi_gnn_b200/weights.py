@@ -161,6 +161,109 @@ def pack_dsgps(P: Mapping[str, torch.Tensor], device) -> torch.Tensor:
 _EPOCH = [0]        # bumped by invalidate(); part of every module's pack-cache key
 
 
+# ---- parameter gradients (csrc/pgrad.cuh) -----------------------------------------------------------------------------------
+# record layout of one node, mirrored from the enum of pgrad.cuh (checked against psi_pgrad_layout() when the table is built)
+PG = dict(ONE=0, DEG=1, C=4, CN=37, YB=62, RHAT=72, MB=82, HID=92, TB=102, SB=112, EDGE=113, ACC=323, MBN=353, HIDN=363, TBN=373, REC=383)
+_PG_ORDER = ("ONE", "DEG", "C", "CN", "YB", "RHAT", "MB", "HID", "TB", "SB", "EDGE", "ACC", "MBN", "HIDN", "TBN", "REC")
+
+
+def grad_table(mixed: bool):
+    """(dst, ty, tx) int32 lists: gradient of the float at offset dst of the packed block = Σ_nodes record[ty]·record[tx].
+    Derivation: csrc/pgrad.cuh (per-node cotangents of vjp.cuh phase A times forward intermediates; the W1j blocks regrouped by
+    source node).  Only the fields a layer kind owns are listed."""
+    dst, ty, tx = [], [], []
+
+    def add(d, y, x):
+        dst.append(d); ty.append(y); tx.append(x)
+
+    for w, name in enumerate(("to", "from", "neu")[: 3 if mixed else 2]):
+        eb = PG["EDGE"] + 70 * w
+        for o in range(D):
+            for i in range(D):
+                add(OFFSETS[name + ".W1i"] + o * D + i, eb + 20 + o, PG["C"] + i)              # zs_X ⊗ h_dst
+                add(OFFSETS[name + ".W1j"] + o * D + i, PG["ACC"] + 10 * w + o, PG["C"] + i)    # acc_X ⊗ h_src (node as source)
+                add(OFFSETS[name + ".W2"] + o * D + i, eb + o, eb + 10 + i)                     # m̄X ⊗ S_X
+            for c in range(3):
+                add(OFFSETS[name + ".W1a"] + o * 3 + c, eb + 30 + o, eb + 40 + 3 * o + c)       # S̄X[o]·Σ_e mask_e[o] a_e[c]
+            add(OFFSETS[name + ".b1"] + o, eb + 20 + o, PG["ONE"])
+            add(OFFSETS[name + ".b2"] + o, eb + o, PG["DEG"] + w)
+    width = 33 if mixed else 32
+    for i in range(width):
+        add(OFFSETS["gate_w"] + i, PG["SB"], PG["C"] + i)
+    add(OFFSETS["gate_b"], PG["SB"], PG["ONE"])
+    for o in range(D):
+        for i in range(width):
+            add(OFFSETS["up_W1"] + o * 33 + i, PG["TB"] + o, PG["C"] + i)
+        add(OFFSETS["up_b1"] + o, PG["TB"] + o, PG["ONE"])
+        for i in range(D):
+            add(OFFSETS["up_W2"] + o * D + i, PG["MB"] + o, PG["HID"] + i)
+        add(OFFSETS["up_b2"] + o, PG["MB"] + o, PG["ONE"])
+        add(OFFSETS["ln_g"] + o, PG["YB"] + o, PG["RHAT"] + o)
+        add(OFFSETS["ln_b"] + o, PG["YB"] + o, PG["ONE"])
+        if mixed:
+            for i in range(25):
+                add(OFFSETS["un_W1"] + o * 25 + i, PG["TBN"] + o, PG["CN"] + i)
+            add(OFFSETS["un_b1"] + o, PG["TBN"] + o, PG["ONE"])
+            for i in range(D):
+                add(OFFSETS["un_W2"] + o * D + i, PG["MBN"] + o, PG["HIDN"] + i)
+            add(OFFSETS["un_b2"] + o, PG["MBN"] + o, PG["ONE"])
+    return dst, ty, tx
+
+
+_TABLES = {}
+
+
+def grad_table_device(mixed: bool, device):
+    """the table as three int32 device tensors (cached per device); verifies the record layout against the extension once"""
+    key = (bool(mixed), str(device))
+    if key not in _TABLES:
+        import ctypes
+        from . import _native as N
+        lay = (ctypes.c_int32 * 16)()
+        N.check(N.load().psi_pgrad_layout(lay), "psi_pgrad_layout")
+        if [int(v) for v in lay] != [PG[k] for k in _PG_ORDER]:
+            raise RuntimeError("psi_gnn_b200: weights.py parameter-gradient record layout does not match the extension")
+        _TABLES[key] = tuple(torch.tensor(t, dtype=torch.int32, device=device) for t in grad_table(mixed))
+    return _TABLES[key]
+
+
+def unpack_psignn_grads(flat: torch.Tensor, names, mixed: bool, f_prefix: str = "deqdss.f", layer: int = 0) -> Dict[str, torch.Tensor]:
+    """inverse of :func:`pack_psignn` for a gradient in block layout: ``{state_dict key: gradient tensor}`` for the keys in ``names``"""
+    f = f_prefix
+    out: Dict[str, torch.Tensor] = {}
+
+    def field(name, rows=None, width=None, cols=None):
+        off = OFFSETS[name]
+        if rows is None:
+            return flat[off:off + (cols or 1)]
+        return flat[off:off + rows * width].view(rows, width)[:, :cols if cols is not None else width]
+
+    def edge(slot, prefix):
+        out[prefix + ".0.weight"] = torch.cat([field(slot + ".W1i", D, D), field(slot + ".W1j", D, D), field(slot + ".W1a", D, 3)], dim=1)
+        out[prefix + ".0.bias"] = field(slot + ".b1", cols=D)
+        out[prefix + ".2.weight"] = field(slot + ".W2", D, D)
+        out[prefix + ".2.bias"] = field(slot + ".b2", cols=D)
+
+    width = 33 if mixed else 32
+    edge("to", f"{f}.phi_to_list.{layer}.mlp.mlp")
+    edge("from", f"{f}.phi_from_list.{layer}.mlp.mlp")
+    out[f"{f}.alpha.0.weight"] = field("gate_w", cols=width).reshape(1, width)
+    out[f"{f}.alpha.0.bias"] = field("gate_b", cols=1)
+    out[f"{f}.update_list.{layer}.mlp.0.weight"] = field("up_W1", D, 33, width)
+    out[f"{f}.update_list.{layer}.mlp.0.bias"] = field("up_b1", cols=D)
+    out[f"{f}.update_list.{layer}.mlp.2.weight"] = field("up_W2", D, D)
+    out[f"{f}.update_list.{layer}.mlp.2.bias"] = field("up_b2", cols=D)
+    out[f"{f}.laynorm.weight"] = field("ln_g", cols=D)
+    out[f"{f}.laynorm.bias"] = field("ln_b", cols=D)
+    if mixed:
+        edge("neu", f"{f}.phi_neumann.mlp.mlp")
+        out[f"{f}.update_neumann.mlp.0.weight"] = field("un_W1", D, 25)
+        out[f"{f}.update_neumann.mlp.0.bias"] = field("un_b1", cols=D)
+        out[f"{f}.update_neumann.mlp.2.weight"] = field("un_W2", D, D)
+        out[f"{f}.update_neumann.mlp.2.bias"] = field("un_b2", cols=D)
+    return {k: out[k] for k in names if k in out}
+
+
 def named_tensors(module: torch.nn.Module, prefix: str = "") -> Dict[str, torch.Tensor]:
     """parameters of ``module`` keyed like its ``state_dict`` (optionally under ``prefix``)."""
     return {(prefix + k): v for k, v in module.named_parameters()}

@@ -49,7 +49,7 @@ class Golden:
             if k.startswith("batch.") and k != "batch.num_nodes":
                 setattr(b, k[6:], self.t(k, device))
         b.num_nodes = int(self.z["batch.num_nodes"])
-        b.num_graphs = int(b.ptr.numel() - 1)
+        b.num_graphs = int(b.ptr.numel() - 1) if getattr(b, "ptr", None) is not None else 1
         return b
 
     def params(self, device="cpu"):

@@ -158,6 +158,63 @@ def test_forced_quasi_newton_steps(golden_small):
         ws.close()
 
 
+def test_param_grad_matches_autograd(golden):
+    """psi_param_grad — θ̄ = (∂f/∂θ at H)ᵀ ȳ — against torch autograd on the differentiable form of the same layer evaluated in fp64
+    (every parameter tensor of the layer, both families, checkpoint and random-init weights); and bit-identical on a second run"""
+    from psi_gnn_b200 import weights as W
+    from psi_gnn_b200.solver import VjpOperator
+    m = golden.model(DEV)
+    b = golden.batch(DEV)
+    f = m.deqdss.f
+    H, y, h0 = golden.t("f2", DEV), golden.t("vjp_y", DEV), golden.t("h0", DEV)
+    op = VjpOperator(f, H, b, torch.zeros_like(y))
+    flat, jty = op.graph.param_grad(f.kind, H, y, want_jty=True)
+    flat2 = op.graph.param_grad(f.kind, H, y)
+    assert torch.equal(flat, flat2)                      # fixed reduction order, no atomics
+    assert rel_err(jty, golden.t("vjp_out")) <= TOL
+    names = ["deqdss.f." + n for n, _ in f.named_parameters()]
+    got = W.unpack_psignn_grads(flat, names, golden.mixed)
+    assert set(got) == set(names)
+    m64 = golden.model(DEV).double()
+    b64 = b.double()
+    Hr = H.double().requires_grad_()
+    out = m64.deqdss.f._forward_torch(Hr, h0.double(), b64)
+    ref = torch.autograd.grad(out, list(m64.deqdss.f.parameters()), y.double(), allow_unused=True)
+    tot_e, tot_n = 0.0, 0.0
+    for (n, p), r in zip(m64.deqdss.f.named_parameters(), ref):
+        r = torch.zeros_like(p) if r is None else r
+        g_ = got["deqdss.f." + n].double()
+        assert g_.shape == r.shape, n
+        tot_e += float((g_ - r).norm() ** 2); tot_n += float(r.norm() ** 2)
+        assert float((g_ - r).norm()) <= 2e-5 * float(r.norm()) + 1e-7 * (tot_n ** 0.5 + 1e-30), (n, float((g_ - r).norm()), float(r.norm()))
+    assert (tot_e / tot_n) ** 0.5 <= TOL
+
+
+def test_forced_anderson_steps(golden_small):
+    """Teacher-forced Anderson updates (Gram matrix, bordered solve, mixing) with the production kernels vs the reference's formulas
+    (solver.py:250-255) evaluated in fp64 on the same fp32 window: rel L2 ≤ 1e-5 (the reference's own fp32 evaluation is at 2e-8 … 6e-8)"""
+    from psi_gnn_b200 import _native as N
+    from psi_gnn_b200.solver import SolverWorkspace
+    g = golden_small
+    lib = N.load()
+    m, lam, beta = int(g["andf_m"]), float(g["andf_lam"]), float(g["andf_beta"])
+    for k in [int(s) for s in g["andf_steps"]]:
+        pre = "andf%d_" % k
+        X, F = g.t(pre + "X", DEV).contiguous(), g.t(pre + "F", DEV).contiguous()
+        n, numel = X.shape[0], X.shape[1]
+        ws = SolverWorkspace(numel, 64, torch.device(DEV))
+        xn = torch.empty(numel, device=DEV)
+        al = torch.empty(n, device=DEV)
+        N.check(lib.psi_anderson_forced_step(ws.handle, m, n, int(g[pre + "slot"]), lam, beta, N.ptr(X), N.ptr(F), N.ptr(xn), N.ptr(al),
+                                             N.stream_ptr()), "forced anderson")
+        torch.cuda.synchronize()
+        floor = rel_err(g.t(pre + "x32"), g.t(pre + "x64"))
+        e = rel_err(xn, g.t(pre + "x64"))
+        assert e <= max(TOL, 2 * floor), (k, e, floor)
+        assert rel_err(al, g.t(pre + "alpha64")) <= 1e-4, (k, al, g[pre + "alpha64"])     # α solves a 4×4 system with cond ~ 1e4
+        ws.close()
+
+
 def test_forward_solve_free_running(golden):
     m = golden.model(DEV)
     b = golden.batch(DEV)
@@ -244,10 +301,13 @@ def test_anderson_matches_reference(golden):
     ref = golden["anderson_rel_trace"]
     got = np.asarray(out["rel_trace"])
     assert got.shape == ref.shape
+    # Anderson(2) is far less chaotic than Broyden: the first 8 residuals follow the reference to 1e-3; the result is an eps = 1e-4
+    # accurate fixed point like the reference's (two such points differ by ~ eps / (1 − ρ))
     k = 8
-    assert np.all(np.abs(got[:k] - ref[:k]) <= 2e-2 * ref[:k] + 1e-9)
+    assert np.all(np.abs(got[:k] - ref[:k]) <= 1e-3 * ref[:k] + 1e-9)
     assert out["lowest"] < 1e-4 or float(golden["anderson_lowest"]) >= 1e-4
-    assert rel_err(out["result"], golden.t("anderson_result")) <= 1e-2
+    assert rel_err(out["result"], golden.t("anderson_result")) <= 3e-3
+    assert abs(out["nstep"] - int(golden["anderson_nstep"])) <= max(3, 0.15 * int(golden["anderson_nstep"]))
 
 
 def _train_step(m, b, v, monkeypatch):
@@ -446,10 +506,13 @@ def test_large_mesh_properties():
 def _baseline(name):
     g = Golden(name)
     z = g.z
-    cfg = dict(latent_dim=10, k=int(z["cfg.k"]), alpha=float(z["cfg.alpha"]), gamma=0.9)
+    cfg = dict(latent_dim=10, k=int(z["cfg.k"]), alpha=float(z["cfg.alpha"]), gamma=float(z["cfg.gamma"]) if "cfg.gamma" in z.files else 0.9)
     if name.startswith("dss"):
         from psi_gnn_b200.dirichlet.dss import model as M
         m = M.DeepStatisticalSolver(cfg)
+    elif "mixed" in name:
+        from psi_gnn_b200.mixed.dsgps import model as M
+        m = M.ModelDSGPS(cfg)
     else:
         from psi_gnn_b200.dirichlet.dsgps import model as M
         m = M.ModelDSGPS(cfg)
@@ -497,6 +560,158 @@ def test_dsgps_single_layer_matches_reference():
     W.upload(W.pack_dsgps(g.params(DEV), DEV), W.next_serial())
     out = graph_of(b, N.KIND_DSGPS).layer_forward(N.KIND_DSGPS, g.t("layer_in", DEV), g.t("layer_h0", DEV))
     assert rel_err(out, g.t("layer_out")) <= TOL
+
+
+def test_dsgps_mixed_inference_and_layer_match_reference():
+    """mixed/dsgps (reference mixed/dsgps/model.py:76-97): native layer kind 4 — Neumann rows overwritten by update_neumann, Dirichlet
+    rows clamped — one layer and the 30-step unrolled inference against the unmodified reference"""
+    from psi_gnn_b200 import _native as N, weights as W
+    from psi_gnn_b200.graph import graph_of
+    g, m, b = _baseline("dsgps_mixed_ckpt")
+    u = m.inference(b)
+    assert rel_err(u, g.t("u")) <= 5 * TOL          # 30 recurrent steps
+    W.upload(W.pack_dsgps(g.params(DEV), DEV), W.next_serial())
+    out = graph_of(b, N.KIND_DSGPS_MIXED).layer_forward(N.KIND_DSGPS_MIXED, g.t("layer_in", DEV), g.t("layer_h0", DEV))
+    assert rel_err(out, g.t("layer_out")) <= TOL
+    t = b.tags
+    assert torch.equal(out[t[:, 1] == 1], g.t("layer_h0", DEV)[t[:, 1] == 1])       # Dirichlet rows are copied
+
+
+@pytest.mark.parametrize("name", ["dss_ckpt", "dsgps_ckpt", "dsgps_mixed_ckpt"])
+def test_baseline_training_step_and_checkpoint_roundtrip(name, tmp_path):
+    """unrolled training forward + backward of the baselines (reference dirichlet/dss/model.py:59-104, */dsgps/model.py:48-131): total
+    loss, last state and every parameter gradient against the unmodified reference; then a checkpoint in the reference's layout
+    (training_class.py:297-307: epoch, hyperparameters, state_dict, …) survives torch.save / torch.load / load_state_dict and the
+    reloaded model reproduces the native inference bit for bit"""
+    g, m, b = _baseline(name)
+    m.train()
+    m.zero_grad()
+    U, ld = m(b)
+    ld["train_loss"].backward()
+    k = str(m.config["k"])
+    ref = float(g["train_loss"])
+    assert abs(ld["train_loss"].item() - ref) <= 2e-5 * abs(ref)
+    assert rel_err(U[k].detach(), g.t("train_u_last")) <= 5 * TOL
+    assert abs(ld["residual_loss"][k].item() - float(g["train_res_last"])) <= 1e-4 * abs(float(g["train_res_last"]))
+    gs = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1).double().cpu() for _, p in m.named_parameters()])
+    rs = torch.cat([g.t("train_grad." + n).reshape(-1).double() for n, _ in m.named_parameters()])
+    assert float((gs - rs).norm() / rs.norm()) <= 1e-4, float((gs - rs).norm() / rs.norm())
+    # checkpoint round-trip
+    path = tmp_path / "best_model.pt"
+    torch.save({"epoch": 3, "hyperparameters": dict(m.config), "state_dict": m.state_dict(), "hist_train": {}, "hist_val": {}, "training_time": 1.0}, path)
+    ck = torch.load(path, map_location=DEV, weights_only=False)
+    m2 = type(m)(ck["hyperparameters"]).to(DEV)
+    m2.load_state_dict(ck["state_dict"])
+    assert set(ck["state_dict"].keys()) == set(g.params().keys())
+    m.eval(); m2.eval()
+    assert torch.equal(m2.inference(b), m.inference(b))
+
+
+def test_evaluation_form_models():
+    """ModelPSIGNN / ModelPSIGNNIterative (reference tests/model_psignn.py:28-214): the evaluation-form wrappers around the same solve"""
+    from psi_gnn_b200.dirichlet.psignn import model as M
+    from psi_gnn_b200.dirichlet.psignn.utilities import solver as S
+    g = Golden("dirichlet_ckpt")
+    cfg = g.cfg()
+    cfg["solver"] = S.broyden
+    b = g.batch(DEV)
+    m = M.ModelPSIGNN(cfg)
+    m.load_state_dict(g.params())
+    m = m.to(DEV)
+    u, ld = m(b)
+    assert rel_err(u, g.t("u")) <= band_u(g)
+    assert ld["nsteps"] == m.deqdss.last_forward["nstep"] and abs(ld["nsteps"] - int(g["fw_nstep"])) <= 0.25 * int(g["fw_nstep"])
+    assert abs(ld["residual_loss"].item() - float(g["residual"])) <= 0.05 * float(g["residual"])
+    assert set(ld) == {"residual_loss", "encoder_loss", "autoencoder_loss", "mse_loss", "mse_dirichlet_loss", "nsteps"}
+    mi = M.ModelPSIGNNIterative(cfg)
+    mi.load_state_dict(g.params())
+    out = mi.to(DEV)(b)
+    assert len(out["sol_dic"]) == mi.deqdss.last_forward["steps_run"] + 2 and out["nstep"] == mi.deqdss.last_forward["nstep"]
+
+
+def test_training_loop_on_the_dropin_modules(tmp_path):
+    """the reference's TrainModel step recipe (dirichlet/psignn/training_class.py:147-166) driven through the PyG stand-ins
+    (DataListLoader → DataParallel.collate → ModelDEQDSS): two epochs over 3 batches of 4 meshes; the collated device batches and
+    their native re-layouts are built once (cache hits on the second epoch), the parameters move, the checkpoint round-trips"""
+    from psi_gnn_b200 import synthetic, training as T
+    from psi_gnn_b200.dirichlet.psignn import model as M
+    from psi_gnn_b200.dirichlet.psignn.utilities import solver as S
+    g = Golden("dirichlet_ckpt")
+    cfg = g.cfg()
+    cfg["solver"] = S.broyden
+    net = M.ModelDEQDSS(cfg)
+    net.load_state_dict(g.params())
+    model = T.DataParallel(net.to(DEV), device=DEV)
+    dataset = [synthetic.make_mesh(200 + i, h=0.11) for i in range(12)]
+    loader = T.DataListLoader(dataset, batch_size=4, shuffle=False)
+    tm = T.TrainModel({"loader_train": loader, "loader_val": None, "model": model, "config_model": cfg, "lr_deq": 1e-4, "lr_ae": 1e-4,
+                       "sched_step_deq": 0.5, "sched_step_ae": 0.5, "path_ckpt": str(tmp_path), "max_epochs": 2, "gradient_clip": 0.1,
+                       "jac_weight": 1.0, "sup_weight": 0.0, "min_loss_save": 1e9})
+    before = torch.cat([p.detach().reshape(-1).clone() for p in net.parameters()])
+    hist_train, _ = tm.train_model()
+    after = torch.cat([p.detach().reshape(-1) for p in net.parameters()])
+    assert len(hist_train["loss"]) == 2 and all(np.isfinite(v) for v in hist_train["loss"])
+    assert float((after - before).abs().max()) > 0
+    assert model.cache_hits == 3                                   # second epoch: collation, H2D copy and SELL build all skipped
+    ck = torch.load(tmp_path / "final_model.pt", map_location=DEV, weights_only=False)
+    assert set(ck) >= {"epoch", "hyperparameters", "state_dict", "hist_train", "hist_val", "opt_deq", "opt_ae", "sched_deq", "sched_ae", "training_time"}
+    net2 = M.ModelDEQDSS(cfg)
+    net2.load_state_dict(ck["state_dict"])
+    b = T.Batch.from_data_list(dataset[:2]).to(DEV)
+    assert torch.equal(net2.to(DEV).inference(b), net.inference(b))
+
+
+def test_stale_graph_cache_is_rebuilt():
+    """the native handle snapshots tags / prb_data / a_ij / edge_attr: reassigning or modifying them in place on the same batch (new
+    right-hand side on the same mesh) must rebuild it — otherwise the solves and the autograd path would see different functions"""
+    from psi_gnn_b200.graph import graph_of, invalidate
+    g = Golden("dirichlet_seed0")
+    m = g.model(DEV)
+    b = g.batch(DEV)
+    h0 = g.t("h0", DEV)
+    with torch.no_grad():
+        a = m.deqdss.f(h0, h0, b)
+        g1 = graph_of(b, 0)
+        b.prb_data.mul_(2.0)                                         # in place: same storage, new version
+        c = m.deqdss.f(h0, h0, b)
+        assert graph_of(b, 0) is not g1 and not torch.equal(a, c)
+        b.prb_data = b.prb_data / 2.0                                # reassigned
+        d = m.deqdss.f(h0, h0, b)
+    assert rel_err(d, a) <= 1e-6
+    g2 = graph_of(b, 0)
+    b.prb_data.data.mul_(3.0)                                        # .data writes carry no version: explicit invalidation
+    assert graph_of(b, 0) is g2
+    invalidate(b)
+    assert graph_of(b, 0) is not g2
+
+
+def test_edge_index_out_of_range_fails_loudly():
+    from psi_gnn_b200.graph import graph_of
+    g = Golden("dirichlet_seed0")
+    b = g.batch(DEV)
+    b.edge_index = b.edge_index.clone()
+    b.edge_index[1, 5] = b.num_nodes + 3
+    with pytest.raises(RuntimeError, match="out of range"):
+        graph_of(b, 0)
+
+
+def test_keep_trace_on_every_solver():
+    """the reference's solvers always return the iterates; here keep_trace=True asks for them (iterative_inference does) on Broyden,
+    Picard and Anderson alike, fused and callable paths"""
+    from psi_gnn_b200 import solver as S
+    g = Golden("dirichlet_seed0")
+    m = g.model(DEV)
+    b = g.batch(DEV)
+    h0 = g.t("h0", DEV)
+    op = S.LayerOperator(m.deqdss.f, h0, b)
+    p = S.forward_iteration(op, h0, eps=1e-4, threshold=40, keep_trace=True)
+    assert len(p["xest_trace"]) == p["nstep"] + 2 and torch.equal(p["xest_trace"][0], h0) and torch.equal(p["xest_trace"][-1], p["result"])
+    pc = S.forward_iteration(lambda H: op(H), h0, eps=1e-4, threshold=40, keep_trace=True)
+    assert len(pc["xest_trace"]) == len(p["xest_trace"]) and rel_err(pc["xest_trace"][3], p["xest_trace"][3]) < 1e-6
+    a = S.anderson(op, h0, m=2, threshold=30, eps=1e-4, keep_trace=True)
+    assert len(a["xest_trace"]) == a["steps_run"] + 1 and torch.equal(a["xest_trace"][0], h0)
+    assert torch.equal(a["xest_trace"][-1], a["result"])            # the trace holds the best iterate so far (solver.py:273)
+    assert S.anderson(op, h0, m=2, threshold=30, eps=1e-4)["xest_trace"] == []
 
 
 @pytest.mark.timeout(600)

@@ -152,8 +152,8 @@ def test_baseline_state_dict_keys():
     assert set(m.state_dict().keys()) == set(gd.params().keys())          # 480 tensors of the shipped DSS checkpoint
     m2 = DSGPS.ModelDSGPS(dict(latent_dim=10, k=30, alpha=1e-3, gamma=0.9))
     assert set(m2.state_dict().keys()) == set(gg.params().keys())
-    with pytest.raises(NotImplementedError):
-        m.forward(None)
+    with pytest.raises(RuntimeError):                                     # the training forward exists, but there is no CPU path
+        m.forward(gd.batch("cpu"))
 
 
 def test_shard_batch_balanced_and_complete():
@@ -187,3 +187,32 @@ def test_bench_reference_arm_prints_one_json_line():
     assert d["impl"] == "reference" and d["vs_baseline"] is None and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "workload" in d["config"]
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_loader_and_batch_standins():
+    """DataListLoader / Batch.from_data_list (PyG stand-ins of psi_gnn_b200/training.py): list batches, rank shares, offsets"""
+    from psi_gnn_b200 import synthetic, training as T
+    data = [synthetic.make_mesh(300 + i, h=0.2) for i in range(7)]
+    loader = T.DataListLoader(data, batch_size=3)
+    batches = list(loader)
+    assert [len(b) for b in batches] == [3, 3, 1] and len(loader) == 3
+    b = T.Batch.from_data_list(batches[0])
+    assert b.num_graphs == 3 and b.num_nodes == sum(d.num_nodes for d in batches[0]) and int(b.ptr[-1]) == b.num_nodes
+    assert int(b.edge_index.max()) < b.num_nodes and int(b.edge_index[:, int(b.edge_ptr[1]):].min()) >= int(b.ptr[1])
+    r0 = list(T.DataListLoader(data, batch_size=4, rank=0, world=2))
+    r1 = list(T.DataListLoader(data, batch_size=4, rank=1, world=2))
+    assert [len(x) for x in r0] == [2, 2] and [len(x) for x in r1] == [2, 1]
+    assert [d._psi_item_id for d in r0[0]] == [0, 1] and [d._psi_item_id for d in r1[0]] == [2, 3]
+    sh = T.DataListLoader(data, batch_size=7, shuffle=True, seed=1)
+    e1 = [d._psi_item_id for d in next(iter(sh))]
+    e2 = [d._psi_item_id for d in next(iter(sh))]
+    assert sorted(e1) == list(range(7)) and e1 != e2
+
+
+def test_mixed_dsgps_state_dict_keys():
+    from conftest import Golden
+    from psi_gnn_b200.mixed.dsgps import model as M
+    g = Golden("dsgps_mixed_ckpt")
+    m = M.ModelDSGPS(dict(latent_dim=10, k=30, alpha=1e-3, gamma=0.9))
+    assert set(m.state_dict().keys()) == set(g.params().keys())
+    m.load_state_dict(g.params())
