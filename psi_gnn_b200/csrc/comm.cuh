@@ -82,9 +82,11 @@ struct psi_comm {
 #define PSI_MAIL_RED_OFF 4096
 #define PSI_SPIN_TIMEOUT_NS 4000000000ull   // 4 s
 struct MailHeader {
-    unsigned long long halo_seq[PSI_MAX_WORLD];
+    unsigned long long halo_seq[PSI_MAX_WORLD];      // written by the producer: its rows of exchange `seq` have landed here
     unsigned long long sb_seq[PSI_MAX_WORLD];
     unsigned long long red_seq[2][PSI_MAX_WORLD];
+    unsigned long long halo_ack[PSI_MAX_WORLD];      // written by the consumer into the PRODUCER's header: rows of exchange `seq` consumed
+    unsigned long long sb_ack[PSI_MAX_WORLD];
 };
 static inline size_t mail_xg_off(int world) { return PSI_MAIL_RED_OFF + (size_t)2 * world * PSI_RED_MAX * sizeof(double); }
 static inline size_t mail_sg_off(int world, int64_t total_recv) { return mail_xg_off(world) + (size_t)total_recv * PSI_QPITCH * sizeof(float); }
@@ -95,6 +97,8 @@ struct PeerDev {                            // one neighbour of the halo exchang
     float* sg0; float* sg1;                 // … and in the two planes of its S̄ ghost area
     unsigned long long* halo_flag;          // &peer_header->halo_seq[my_rank]
     unsigned long long* sb_flag;            // &peer_header->sb_seq[my_rank]
+    unsigned long long* halo_ack;           // &peer_header->halo_ack[my_rank]: where I acknowledge the rows the peer sent me
+    unsigned long long* sb_ack;
     int send_off, send_count;               // my rows for this peer: send_index[send_off .. send_off + send_count)
     int rank, recv_off, recv_count;         // the peer's rank; its rows in MY ghost order
 };
@@ -140,9 +144,21 @@ __device__ __forceinline__ bool spin_until(const unsigned long long* flag, unsig
 // the LAST block to finish publishes the sequence number at every neighbour.  plane_src: one [rows, pitch_src] array (the iterate:
 // pitch 10) or the two S̄ planes (pitch PSI_QPITCH, second plane at + N·PSI_QPITCH).
 template <int WHICH /*0 iterate rows → xg, 1 S̄ rows → sg*/>
-__global__ void __launch_bounds__(128) k_halo_put(PartDev P, const float* __restrict__ src, unsigned long long seq, const int* __restrict__ done) {
+__global__ void __launch_bounds__(128) k_halo_put(PartDev P, const float* __restrict__ src, unsigned long long seq, unsigned long long prev_seq,
+                                                   int* done) {
     if (done != nullptr && *done) return;
-    __shared__ int s_last;
+    __shared__ int s_last, s_ok;
+    // flow control: a neighbour's landing zone may be overwritten only after it has consumed the previous exchange (it says so in MY
+    // header).  Inside a solve the all-reduce of every step already orders this; the first evaluations of a solve and stand-alone
+    // exchanges have no such barrier.
+    if (threadIdx.x == 0) s_ok = 1;
+    __syncthreads();
+    if (prev_seq != 0 && threadIdx.x < P.n_peers) {
+        const unsigned long long* a = (WHICH == 0 ? P.hdr->halo_ack : P.hdr->sb_ack) + P.peers[threadIdx.x].rank;
+        if (!spin_until(a, prev_seq)) { s_ok = 0; *P.error = 1; if (done != nullptr) *done = 1; }
+    }
+    __syncthreads();
+    if (!s_ok) return;
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i < P.total_send) {
         int pi = 0;
@@ -192,20 +208,31 @@ __global__ void __launch_bounds__(128) k_halo_get(PartDev P, float* __restrict__
     __syncthreads();
     if (!s_ok) return;
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i >= P.total_recv) return;
-    if (WHICH == 0) {
-        const float4* s4 = reinterpret_cast<const float4*>(P.xg + i * PSI_QPITCH);
-        const float4 a = __ldcg(s4), b = __ldcg(s4 + 1), c = __ldcg(s4 + 2);
-        float2* d2 = reinterpret_cast<float2*>(dst + (P.n_owned + i) * PSI_D);
-        d2[0] = make_float2(a.x, a.y); d2[1] = make_float2(a.z, a.w); d2[2] = make_float2(b.x, b.y); d2[3] = make_float2(b.z, b.w);
-        d2[4] = make_float2(c.x, c.y);
-    } else {
+    if (i < P.total_recv) {
+        if (WHICH == 0) {
+            const float4* s4 = reinterpret_cast<const float4*>(P.xg + i * PSI_QPITCH);
+            const float4 a = __ldcg(s4), b = __ldcg(s4 + 1), c = __ldcg(s4 + 2);
+            float2* d2 = reinterpret_cast<float2*>(dst + (P.n_owned + i) * PSI_D);
+            d2[0] = make_float2(a.x, a.y); d2[1] = make_float2(a.z, a.w); d2[2] = make_float2(b.x, b.y); d2[3] = make_float2(b.z, b.w);
+            d2[4] = make_float2(c.x, c.y);
+        } else {
 #pragma unroll
-        for (int w = 0; w < 2; ++w) {
-            const float4* s4 = reinterpret_cast<const float4*>(P.sg + ((int64_t)w * P.total_recv + i) * PSI_QPITCH);
-            float4* d4 = reinterpret_cast<float4*>(dst + ((int64_t)w * P.N + P.n_owned + i) * PSI_QPITCH);
-            d4[0] = __ldcg(s4); d4[1] = __ldcg(s4 + 1); d4[2] = __ldcg(s4 + 2);
+            for (int w = 0; w < 2; ++w) {
+                const float4* s4 = reinterpret_cast<const float4*>(P.sg + ((int64_t)w * P.total_recv + i) * PSI_QPITCH);
+                float4* d4 = reinterpret_cast<float4*>(dst + ((int64_t)w * P.N + P.n_owned + i) * PSI_QPITCH);
+                d4[0] = __ldcg(s4); d4[1] = __ldcg(s4 + 1); d4[2] = __ldcg(s4 + 2);
+            }
         }
+    }
+    // the last block to finish tells every producer that its rows have been consumed
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&P.counter[3 + WHICH], 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (s_last) {
+        if (threadIdx.x < P.n_peers) st_release_sys(WHICH == 0 ? P.peers[threadIdx.x].halo_ack : P.peers[threadIdx.x].sb_ack, seq);
+        if (threadIdx.x == 0) P.counter[3 + WHICH] = 0;
     }
 }
 
@@ -295,6 +322,7 @@ struct Partition {
     // numbers depend only on the (rank-independent) position of an exchange inside its solve — never on how many no-op steps a
     // rank's host happened to queue behind the stop.
     unsigned long long epoch = 0, cnt_halo = 0, cnt_sb = 0, cnt_red = 0;
+    unsigned long long last_halo = 0, last_sb = 0;      // sequence numbers of the previous exchanges (what the peers must have acknowledged)
     void new_epoch() { ++epoch; cnt_halo = cnt_sb = cnt_red = 0; }
     unsigned long long next(unsigned long long& cnt) { return (epoch << 24) + (++cnt); }
 };

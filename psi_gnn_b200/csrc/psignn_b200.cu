@@ -33,8 +33,8 @@ extern "C" int psi_weights_floats(void) { return (int)((sizeof(LayerWeights) + s
 
 // one packed block = LayerWeights followed by LayerWeightsT (the transposed copies for the packed-FMA kernels)
 static int upload_block(const float* dev_blob, cudaStream_t st) {
-    PSI_CK(cudaMemcpyToSymbolAsync(cW, dev_blob, sizeof(LayerWeights), 0, cudaMemcpyDeviceToDevice, st));
-    PSI_CK(cudaMemcpyToSymbolAsync(cWT, dev_blob + sizeof(LayerWeights) / sizeof(float), sizeof(LayerWeightsT), 0, cudaMemcpyDeviceToDevice, st));
+    static_assert(sizeof(LayerBlock) == sizeof(LayerWeights) + sizeof(LayerWeightsT), "LayerBlock is the packed blob");
+    PSI_CK(cudaMemcpyToSymbolAsync(cB, dev_blob, sizeof(LayerBlock), 0, cudaMemcpyDeviceToDevice, st));
     return 0;
 }
 
@@ -271,6 +271,8 @@ extern "C" int psi_part_mail_open(psi_graph_t* g, const char* handles, const int
         pd[i].sg1 = sg + (total_recvs[q] + remote_off[i]) * PSI_QPITCH;
         pd[i].halo_flag = &hq->halo_seq[rank];
         pd[i].sb_flag = &hq->sb_seq[rank];
+        pd[i].halo_ack = &hq->halo_ack[rank];
+        pd[i].sb_ack = &hq->sb_ack[rank];
         pd[i].send_off = (int)P->send_off[i]; pd[i].send_count = (int)P->send_count[i];
         pd[i].rank = q; pd[i].recv_off = (int)P->recv_off[i]; pd[i].recv_count = (int)P->recv_count[i];
     }
@@ -309,16 +311,19 @@ static int halo_refresh(psi_graph* g, float* vec, int which, const int* done, cu
     if (P->p2p) {
         PartDev D = P->dev;
         D.N = g->N;
+        int* dn = const_cast<int*>(done);
+        const unsigned pgrid = (unsigned)std::max<int64_t>(1, (P->total_send + 127) / 128);
+        const unsigned ggrid = (unsigned)std::max<int64_t>(1, (P->total_recv + 127) / 128);
         if (which == 0) {
             const unsigned long long seq = P->next(P->cnt_halo);
-            if (P->total_send > 0) k_halo_put<0><<<(unsigned)((P->total_send + 127) / 128), 128, 0, st>>>(D, vec, seq, done);
-            else k_halo_put<0><<<1, 128, 0, st>>>(D, vec, seq, done);
-            k_halo_get<0><<<(unsigned)std::max<int64_t>(1, (P->total_recv + 127) / 128), 128, 0, st>>>(D, vec, seq, const_cast<int*>(done));
+            k_halo_put<0><<<pgrid, 128, 0, st>>>(D, vec, seq, P->last_halo, dn);
+            k_halo_get<0><<<ggrid, 128, 0, st>>>(D, vec, seq, dn);
+            P->last_halo = seq;
         } else {
             const unsigned long long seq = P->next(P->cnt_sb);
-            if (P->total_send > 0) k_halo_put<1><<<(unsigned)((P->total_send + 127) / 128), 128, 0, st>>>(D, vec, seq, done);
-            else k_halo_put<1><<<1, 128, 0, st>>>(D, vec, seq, done);
-            k_halo_get<1><<<(unsigned)std::max<int64_t>(1, (P->total_recv + 127) / 128), 128, 0, st>>>(D, vec, seq, const_cast<int*>(done));
+            k_halo_put<1><<<pgrid, 128, 0, st>>>(D, vec, seq, P->last_sb, dn);
+            k_halo_get<1><<<ggrid, 128, 0, st>>>(D, vec, seq, dn);
+            P->last_sb = seq;
         }
         PSI_CK_LAUNCH();
         return 0;
@@ -843,8 +848,14 @@ static int qn_update(psi_solver* s, int n, int norm_blocks, cudaStream_t st) {
     const double vec = (double)s->act_numel * 4.0;
     // pass 1 (also at nhist = 0: it carries ⟨δx,δg⟩ and ⟨δx,g⟩, from which s and p of this step follow)
     prof_begin(s, n, 1, (2.0 * nhist + 3.0) * vec, st);
-    int kr = DOTS_KR;                       // finest of {32, 16, 8} history vectors per work item that still gives every SM an item
-    while (kr > 8 && (int64_t)s->act_dchunks * ((nhist + kr - 1) / kr) < 2 * (int64_t)s->tma_ctas) kr >>= 1;
+    // history vectors per work item: 32, or — for small problems — the finest of {16, 8} whose items still fit ONE wave of CTAs
+    // (more SMs busy; a second wave of single-batch items is avoided: repeated long solves at 7 … 15 chunks were not bitwise
+    // repeatable in that regime, see NOTES.md)
+    int kr = DOTS_KR;
+#ifndef PSI_FIXED_KR
+    for (int cand = 16; cand >= 8; cand >>= 1)
+        if ((int64_t)s->act_dchunks * ((nhist + cand - 1) / cand) <= (int64_t)s->tma_ctas) kr = cand;
+#endif
     k_qn_dots_tma<<<s->tma_ctas, TMA_THREADS, dots_tma_smem(), st>>>(s->hist, nhist, s->dx, s->dg, s->g, s->partial, s->act_dchunks,
                                                                      &s->ctrl->done, kr);
     prof_end(s, n, 1, st);
@@ -891,6 +902,11 @@ static int qn_poll(psi_solver* s, cudaStream_t st) {
 
 static int qn_finish(psi_solver* s, float* result, psi_solve_stats_t* stats, double* rel_trace, double* abs_trace, cudaStream_t st) {
     if (qn_poll(s, st)) return -1;
+    if (s->part != nullptr) {
+        // the exchanges queued behind the stop were no-ops and acknowledged nothing; the all-reduce of the last executed step has
+        // ordered every real one — the next exchange needs no acknowledgement
+        s->part->last_halo = 0; s->part->last_sb = 0;
+    }
     const QnCtrl& c = *s->h_ctrl;
     const int ran = c.nstep;
     // the last executed step stopped before its rank-one update unless it ran out of steps: its axpy/fin2 pairs are no-ops

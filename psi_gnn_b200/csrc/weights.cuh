@@ -70,8 +70,14 @@ struct __align__(16) LayerWeightsT {
 static_assert(sizeof(EdgeMLPT) == 330 * 4, "EdgeMLPT layout");
 static_assert(sizeof(LayerWeightsT) == 2760 * 4, "LayerWeightsT layout");
 
-__constant__ LayerWeights cW;   // single translation unit (psignn_b200.cu)
-__constant__ LayerWeightsT cWT;
+// one contiguous constant block (a weight upload — per layer for the unrolled DSS baseline — is a single 23.8 KB copy)
+struct __align__(16) LayerBlock {
+    LayerWeights w;
+    LayerWeightsT t;
+};
+__constant__ LayerBlock cB;     // single translation unit (psignn_b200.cu)
+#define cW (cB.w)
+#define cWT (cB.t)
 
 template <int WHICH> __device__ __forceinline__ const EdgeMLPT& edge_mlp_t();
 template <> __device__ __forceinline__ const EdgeMLPT& edge_mlp_t<0>() { return cWT.to; }

@@ -38,9 +38,37 @@ def main():
     N.check(N.load().psi_halo_exchange(gr.handle, N.ptr(test), 10, N.stream_ptr()), "halo")
     torch.cuda.synchronize()
     assert torch.equal(test, vec), "halo exchange mismatch on rank %d" % rank
+    if os.environ.get("PSI_PART_P2P") == "0":
+        partition.USE_P2P = False
     # partitioned solve
     u_loc = model.inference(loc)
     out = model.deqdss.last_forward
+    repeats = int(os.environ.get("PSI_PART_REPEAT", "2"))
+    if repeats:
+        # the partitioned solve must be bitwise repeatable (no timing dependence in the exchange)
+        runs = [(out["steps_run"], out["lowest"])]
+        for _ in range(repeats):
+            model.inference(loc)
+            runs.append((model.deqdss.last_forward["steps_run"], model.deqdss.last_forward["lowest"]))
+        if rank == 0:
+            print("repeatability of the partitioned solve (p2p=%s):" % partition.USE_P2P, runs)
+        from psi_gnn_b200 import solver as S_
+        h0_ = model._encode_native(loc.x)
+        op_ = S_.LayerOperator(model.deqdss.f, h0_, loc)
+        traces = []
+        for _ in range(3):
+            o_ = S_.broyden(op_, h0_, threshold=200, eps=1e-30)
+            traces.append(o_["rel_trace"][:200])
+        base = traces[0]
+        firsts = [next((i for i, (a_, b_) in enumerate(zip(t_, base)) if a_ != b_), -1) for t_ in traces]
+        if rank == 0:
+            print("first step whose rel differs from run 0 (−1 = identical over 200 steps):", firsts)
+        if any(r_ != runs[0] for r_ in runs) or any(f_ != -1 for f_ in firsts):
+            raise SystemExit("the partitioned solve is not repeatable: %s %s" % (runs, firsts))
+        # single pieces, bitwise: layer (with ghost refresh) and one Broyden step repeated
+        outs = [op_(h0_.clone()) for _ in range(6)]
+        if rank == 0:
+            print("layer application with halo refresh repeatable:", [bool(torch.equal(outs[0][:part.n_owned], o[:part.n_owned])) for o in outs])
     # gather the owned rows on rank 0
     sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
     dist.all_gather(sizes, torch.tensor([part.n_owned], dtype=torch.int64, device=dev))

@@ -861,6 +861,22 @@ def test_solve_is_deterministic():
     assert torch.equal(a["result"], c["result"])
 
 
+def test_long_small_solves_are_bitwise_repeatable():
+    """long Broyden solves (250 steps, no stop) of small meshes — 7 and 14 reduction chunks, where the dot pass packs its work items
+    differently from the large configurations — repeated: identical residual traces to the last bit (fixed summation orders, no
+    atomics, no timing dependence)"""
+    from psi_gnn_b200 import solver as S, synthetic
+    g = Golden("dirichlet_ckpt")
+    m = g.model(DEV)
+    for nodes in (3000, 6000):
+        mesh = synthetic.make_large_mesh(nodes, seed=3).to(DEV)
+        h0 = m._encode_native(mesh.x)
+        op = S.LayerOperator(m.deqdss.f, h0, mesh)
+        runs = [S.broyden(op, h0, threshold=250, eps=1e-30) for _ in range(5)]
+        assert all(r["rel_trace"] == runs[0]["rel_trace"] for r in runs[1:]), nodes
+        assert all(torch.equal(r["result"], runs[0]["result"]) for r in runs[1:]), nodes
+
+
 def test_anderson_generic_callable():
     from psi_gnn_b200 import solver as S
     g = Golden("dirichlet_seed0")
