@@ -134,6 +134,12 @@ int psi_vjp_apply(psi_graph_t* g, int kind, const float* dev_y, const float* dev
  * record[tab_y] * record[tab_x], record layout from psi_pgrad_layout).  Deterministic (no atomics). */
 int psi_param_grad(psi_graph_t* g, int kind, const float* dev_hstar, const float* dev_ybar, const int32_t* dev_tab_dst,
                    const int32_t* dev_tab_y, const int32_t* dev_tab_x, int n_tab, float* dev_out, float* dev_jty, void* stream);
+/* Tangent of psi_param_grad along a direction dev_hdot of the frozen point: d/d eps theta_bar(H* + eps*hdot; y_bar) at eps = 0.  With
+ * y_bar = v (Hutchinson probe) and hdot = J^T v it equals 1/2 grad_theta ||J^T v||^2, the double backward that the reference's
+ * jac_loss_estimate(create_graph=True) + loss.backward() performs (dirichlet/psignn/model.py:207, :416-435; mixed :149, :355-374). */
+int psi_param_grad_tangent(psi_graph_t* g, int kind, const float* dev_hstar, const float* dev_ybar, const float* dev_hdot,
+                           const int32_t* dev_tab_dst, const int32_t* dev_tab_y, const int32_t* dev_tab_x, int n_tab, float* dev_out,
+                           void* stream);
 int psi_pgrad_layout(int32_t out[16]);
 
 /* ---- physics residual, encoder, decoder ------------------------------------------------------- */

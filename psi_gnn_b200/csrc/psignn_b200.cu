@@ -540,6 +540,59 @@ extern "C" int psi_param_grad(psi_graph_t* g, int kind, const float* dev_hstar, 
     return rc;
 }
 
+// θ̄' = d/dε θ̄(H* + ε ḣ; ȳ) at ε = 0: the tangent of psi_param_grad along a direction of the frozen point (pgrad.cuh, second half).
+// With ȳ = v (the Hutchinson probe) and ḣ = Jᵀv this is ½ ∇θ ‖Jᵀv‖² — the double backward of jac_loss_estimate
+// (dirichlet/psignn/model.py:207, :416-435).  Same table, same output layout, deterministic.
+extern "C" int psi_param_grad_tangent(psi_graph_t* g, int kind, const float* dev_hstar, const float* dev_ybar, const float* dev_hdot,
+                                      const int32_t* dev_tab_dst, const int32_t* dev_tab_y, const int32_t* dev_tab_x, int n_tab,
+                                      float* dev_out, void* stream) {
+    if (check_kind(g, kind)) return -1;
+    if (kind != PSI_KIND_DIRICHLET && kind != PSI_KIND_MIXED) PSI_FAIL("psi_param_grad_tangent: implemented for the PSI-GNN layers");
+    if (!g->vjp_ready || g->vjp_kind != kind) PSI_FAIL("psi_param_grad_tangent: call psi_vjp_prepare (at the same H*) first");
+    if (g->part != nullptr) PSI_FAIL("psi_param_grad_tangent: not available on a mesh partition (training shards whole graphs)");
+    if (n_tab < 1 || n_tab > PG_NODES * PG_MAX_PER_THREAD) PSI_FAIL("psi_param_grad_tangent: table size out of range");
+    if (dev_out == nullptr || dev_tab_dst == nullptr || dev_tab_y == nullptr || dev_tab_x == nullptr) PSI_FAIL("psi_param_grad_tangent: null pointer");
+    cudaStream_t st = as_stream(stream);
+    PSI_CK(cudaMemsetAsync(dev_out, 0, sizeof(LayerWeights), st));
+    if (g->N == 0) return 0;
+    if (dev_hstar == nullptr || dev_ybar == nullptr || dev_hdot == nullptr) PSI_FAIL("psi_param_grad_tangent: null pointer");
+    const int num_batches = (int)((g->dev.n_compute + PG_NODES - 1) / PG_NODES);
+    const int grid = std::max(1, std::min(num_batches, PSI_NUM_SMS_B200));
+    const size_t n30 = (size_t)g->N * 30, nsb = (size_t)2 * g->N * PSI_QPITCH, nrow = (size_t)g->N * PSI_D;
+    float* buf = nullptr;     // acc | acc' | S̄' | scratch row output of phase B | per-CTA partials
+    PSI_CK(psi_malloc_async((void**)&buf, (2 * n30 + nsb + nrow + (size_t)grid * n_tab) * sizeof(float), st));
+    float *acc = buf, *acc_t = acc + n30, *sb_t = acc_t + n30, *scratch = sb_t + nsb, *partial = scratch + nrow;
+    const SolverEpi noE{nullptr, nullptr, nullptr, nullptr};
+    int rc = launch_vjp<false>(g, kind, dev_ybar, nullptr, scratch, noE, st, acc);            // acc of the primal cotangents
+    if (!rc) {
+        const size_t smem = (size_t)2 * PG_NODES * PG_PITCH * sizeof(float);
+        static bool attr_done = false;
+        if (!attr_done) {
+            cudaFuncSetAttribute(k_pgrad_tan<KIND_DIRICHLET, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaFuncSetAttribute(k_pgrad_tan<KIND_DIRICHLET, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaFuncSetAttribute(k_pgrad_tan<KIND_MIXED, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaFuncSetAttribute(k_pgrad_tan<KIND_MIXED, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            attr_done = true;
+        }
+        VjpCacheDev Ct = g->vjp;                   // same masks and statistics; the gathered array is S̄' instead of S̄
+        Ct.Sb = sb_t;
+        const unsigned ngrid = node_grid(g->dev.n_compute);
+        if (kind == PSI_KIND_DIRICHLET) {
+            k_pgrad_tan<KIND_DIRICHLET, 0><<<grid, PG_NODES, smem, st>>>(g->dev, g->vjp, dev_hstar, dev_hdot, dev_ybar, acc, nullptr, dev_tab_y, dev_tab_x, n_tab, partial, num_batches, sb_t);
+            k_vjp_phase_b<KIND_DIRICHLET, false><<<ngrid, PSI_NODE_BLOCK, 0, st>>>(g->dev, Ct, dev_ybar, nullptr, scratch, noE, acc_t);
+            k_pgrad_tan<KIND_DIRICHLET, 1><<<grid, PG_NODES, smem, st>>>(g->dev, g->vjp, dev_hstar, dev_hdot, dev_ybar, acc, acc_t, dev_tab_y, dev_tab_x, n_tab, partial, num_batches, nullptr);
+        } else {
+            k_pgrad_tan<KIND_MIXED, 0><<<grid, PG_NODES, smem, st>>>(g->dev, g->vjp, dev_hstar, dev_hdot, dev_ybar, acc, nullptr, dev_tab_y, dev_tab_x, n_tab, partial, num_batches, sb_t);
+            k_vjp_phase_b<KIND_MIXED, false><<<ngrid, PSI_NODE_BLOCK, 0, st>>>(g->dev, Ct, dev_ybar, nullptr, scratch, noE, acc_t);
+            k_pgrad_tan<KIND_MIXED, 1><<<grid, PG_NODES, smem, st>>>(g->dev, g->vjp, dev_hstar, dev_hdot, dev_ybar, acc, acc_t, dev_tab_y, dev_tab_x, n_tab, partial, num_batches, nullptr);
+        }
+        k_pgrad_reduce<<<(n_tab + 127) / 128, 128, 0, st>>>(partial, grid, n_tab, dev_tab_dst, dev_out);
+        if (cudaGetLastError() != cudaSuccess) { g_psi_err = "psi_param_grad_tangent: kernel launch failed"; rc = -1; }
+    }
+    psi_free_async(buf, st);
+    return rc;
+}
+
 // record layout of pgrad.cuh for the table builder: {PG_ONE, PG_DEG, PG_C, PG_CN, PG_YB, PG_RHAT, PG_MB, PG_HID, PG_TB, PG_SB, PG_EDGE,
 // PG_ACC, PG_MBN, PG_HIDN, PG_TBN, PG_REC}
 extern "C" int psi_pgrad_layout(int32_t out[16]) {

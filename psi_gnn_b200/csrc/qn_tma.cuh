@@ -17,9 +17,15 @@
 #define DOTS_CH 4096                         // elements per chunk (16 KB per vector), four float4 per consumer thread
 #define DOTS_STAGES 6                        // 6 × (16 KB U + 16 KB V) = 192 KB
 #define DOTS_KR 32                           // history vectors per work item (upper bound; the launch picks 8, 16 or 32)
+#ifndef DOTS_PRODUCER_LANES
+#define DOTS_PRODUCER_LANES 4                // producer lanes issuing fills in parallel (< DOTS_STAGES)
+#endif
 #define DOTS_KB 8                            // ks per cross-warp reduction batch
 #define AXPY_TILE 2048                       // max elements per tile (8 KB per vector), two float4 per consumer thread
 #define AXPY_STAGES 11                       // 11 × (8 KB U + 8 KB V) = 176 KB
+#ifndef AXPY_PRODUCER_LANES
+#define AXPY_PRODUCER_LANES 8                // producer lanes issuing fills in parallel (< AXPY_STAGES)
+#endif
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -79,13 +85,19 @@ k_qn_dots_tma(QnHistory H, int nhist, const float* __restrict__ dx, const float*
     const int items = num_chunks * kranges;
     if (warp == TMA_CONSUMERS / 32) {
         // ---- producer ----
-        if (lane == 0) {
-            uint32_t fill = 0;
-            for (int item = blockIdx.x; item < items; item += gridDim.x) {
-                const int c = item % num_chunks, r = item / num_chunks;
-                const int k0 = r * kr, k1 = min(nhist, k0 + kr);
-                const int64_t e0 = (int64_t)c * DOTS_CH;
-                for (int k = k0; k < k1; ++k, ++fill) {
+        // DOTS_PRODUCER_LANES lanes (fewer than stages) take consecutive fills, so that their wait → expect → copy chains overlap.
+        // Rounds are warp-synchronous: every fill of a round is issued before the next round starts, hence when a lane waits for the
+        // slot of fill f, fill f − STAGES has been issued and the parity it waits on is that of the slot's CURRENT phase (a lane running
+        // two phases ahead would see a stale parity as "free").
+        uint32_t fill0 = 0;
+        for (int item = blockIdx.x; item < items; item += gridDim.x) {
+            const int c = item % num_chunks, r = item / num_chunks;
+            const int k0 = r * kr, k1 = min(nhist, k0 + kr);
+            const int64_t e0 = (int64_t)c * DOTS_CH;
+            for (int kk = k0; kk < k1; kk += DOTS_PRODUCER_LANES) {
+                const int k = kk + lane;
+                if (lane < DOTS_PRODUCER_LANES && k < k1) {
+                    const uint32_t fill = fill0 + (uint32_t)(k - k0);
                     const uint32_t s = fill % DOTS_STAGES, use = fill / DOTS_STAGES;
                     if (use > 0) mbar_wait(&empty[s], (use - 1) & 1);
                     mbar_expect_tx(&full[s], 2 * DOTS_CH * sizeof(float));
@@ -93,7 +105,9 @@ k_qn_dots_tma(QnHistory H, int nhist, const float* __restrict__ dx, const float*
                     bulk_g2s(dst, hist_u(H, k) + e0, DOTS_CH * sizeof(float), &full[s]);
                     bulk_g2s(dst + DOTS_CH, hist_v(H, k) + e0, DOTS_CH * sizeof(float), &full[s]);
                 }
+                __syncwarp();
             }
+            fill0 += (uint32_t)(k1 - k0);
         }
         return;
     }
@@ -226,21 +240,26 @@ k_qn_axpy_tma(QnHistory H, int nhist, int n, const float* __restrict__ coef, int
     const int ntiles = (int)((len4 * 4 + AXPY_TILE - 1) / AXPY_TILE);
     const int tile4 = ntiles > 0 ? (int)((len4 + ntiles - 1) / ntiles) : 0;            // ≤ AXPY_TILE/4 float4 per tile
     if (warp == TMA_CONSUMERS / 32) {
-        if (lane == 0) {
-            uint32_t fill = 0;
-            for (int t = 0; t < ntiles; ++t) {
+        // Producer: AXPY_PRODUCER_LANES lanes take consecutive fills (fewer lanes than stages: the fills of one round land in distinct
+        // stages).  One lane's wait → expect → copy → copy chain costs ≈ 0.3 µs; with a single producer lane that chain caps the SM at
+        // one fill per 0.3 µs, which is below the HBM rate once a fill is < 16 KB (small batches: 4.4 KB per vector at 16 k nodes).
+        const uint32_t total = (uint32_t)ntiles * (uint32_t)nhist;
+        for (uint32_t f0 = 0; f0 < total; f0 += AXPY_PRODUCER_LANES) {
+            const uint32_t fill = f0 + lane;
+            if (lane < AXPY_PRODUCER_LANES && fill < total) {
+                const uint32_t t = fill / (uint32_t)nhist;
+                const int k = nhist - 1 - (int)(fill - t * (uint32_t)nhist);   // descending: pass 1 just streamed the newest vectors
+                                                                               // last, the tail of the history is what L2 still holds
                 const int64_t t0 = q0 + (int64_t)t * tile4;
                 const uint32_t bytes = (uint32_t)(min((int64_t)tile4, q1 - t0) * 16);
-                for (int k = nhist - 1; k >= 0; --k, ++fill) {   // descending: pass 1 just streamed the newest vectors last, the
-                                                                 // tail of the history is what the 126 MB L2 still holds
-                    const uint32_t st = fill % AXPY_STAGES, use = fill / AXPY_STAGES;
-                    if (use > 0) mbar_wait(&empty[st], (use - 1) & 1);
-                    mbar_expect_tx(&full[st], 2 * bytes);
-                    float* dst = ring + (size_t)st * 2 * AXPY_TILE;
-                    bulk_g2s(dst, hist_u(H, k) + t0 * 4, bytes, &full[st]);
-                    bulk_g2s(dst + AXPY_TILE, hist_v(H, k) + t0 * 4, bytes, &full[st]);
-                }
+                const uint32_t st = fill % AXPY_STAGES, use = fill / AXPY_STAGES;
+                if (use > 0) mbar_wait(&empty[st], (use - 1) & 1);
+                mbar_expect_tx(&full[st], 2 * bytes);
+                float* dst = ring + (size_t)st * 2 * AXPY_TILE;
+                bulk_g2s(dst, hist_u(H, k) + t0 * 4, bytes, &full[st]);
+                bulk_g2s(dst + AXPY_TILE, hist_v(H, k) + t0 * 4, bytes, &full[st]);
             }
+            __syncwarp();
         }
         return;
     }

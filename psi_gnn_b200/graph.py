@@ -91,6 +91,18 @@ class NativeGraph:
                                             N.ptr(out), N.ptr(jty), N.stream_ptr()), "psi_param_grad")
         return (out, jty) if want_jty else out
 
+    def param_grad_tangent(self, kind: int, hstar: torch.Tensor, ybar: torch.Tensor, hdot: torch.Tensor) -> torch.Tensor:
+        """d/dε θ̄(H* + ε ḣ; ȳ) at ε = 0 (flat, packed-block layout): with ȳ = v and ḣ = Jᵀv it is ½ ∇θ ‖Jᵀv‖², the double backward of
+        the Hutchinson regulariser (model.py:207, :416-435) — native, deterministic"""
+        from . import weights as W
+        hs, yb, hd = N.f32(hstar), N.f32(ybar), N.f32(hdot)
+        dst, ty, tx = W.grad_table_device(kind == N.KIND_MIXED, self.device)
+        out = torch.zeros(W.TOTAL_FLOATS, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            N.check(N.load().psi_param_grad_tangent(self.handle, kind, N.ptr(hs), N.ptr(yb), N.ptr(hd), N.ptr(dst), N.ptr(ty), N.ptr(tx),
+                                                    int(dst.numel()), N.ptr(out), N.stream_ptr()), "psi_param_grad_tangent")
+        return out
+
     def residual(self, u: torch.Tensor, y: torch.Tensor, want_vector: bool = False):
         """(mean((A u − y)²), residual vector or None)  — dirichlet/psignn/model.py:157-167."""
         u = N.f32(u.reshape(-1))

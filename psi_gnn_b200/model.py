@@ -8,8 +8,9 @@ boundary-condition family.  What runs where:
   inference, spectral-radius power iteration: CUDA kernels behind the C ABI (include/psignn_b200.h);
 * the differentiable re-application ``f(H*)`` of a training step (reference model.py:204-205) and everything its backward needs — the
   implicit-adjoint solve and the parameter gradients — run on the extension too (``_ImplicitLayer`` / ``psi_param_grad``);
-* only the Hutchinson Jacobian regulariser (model.py:207, ``create_graph=True``) keeps a torch-op evaluation of the layer, for its
-  double backward (1 of ≈ 560 operator evaluations of a step).
+* the Hutchinson Jacobian regulariser (model.py:207, ``create_graph=True``): value = one native VJP, double backward = the tangent of
+  the native parameter gradient (``_JacobianLoss`` / ``psi_param_grad_tangent``).  A training step evaluates the layer with torch ops
+  nowhere; ``_forward_torch`` remains as the differentiable form for user code that asks autograd for a graph through ``f`` directly.
 CPU tensors raise ``RuntimeError`` everywhere — there is no CPU path.
 """
 from __future__ import annotations
@@ -302,6 +303,40 @@ class _ImplicitLayer(autograd.Function):
         return (None, None, None, g_init) + tuple(grads[n].clone() if n in grads else None for n in names)
 
 
+class _JacobianLoss(autograd.Function):
+    """Hutchinson estimate ``‖Jᵀv‖² / numel`` of reference model.py:416-435 (``vecs=1``, as :207 calls it) and its double backward.
+
+    forward : one native VJP at the frozen point.
+    backward: ``∇θ ‖Jᵀv‖² = 2 d/dε ∂θ[vᵀ f_θ(H* + ε w)]`` with ``w = Jᵀv`` held fixed — the tangent of the native parameter gradient
+    along ``w`` (``psi_param_grad_tangent``, forward-over-reverse; csrc/pgrad.cuh).  The reference reaches the same numbers with
+    ``autograd.grad(..., create_graph=True)`` and a second autograd walk; ``H*`` is a detached leaf there, so θ is the only
+    destination of this gradient."""
+
+    @staticmethod
+    def forward(ctx, deq, batch, H_star, v, *params):
+        f = deq.f
+        g = f.native_graph(batch)
+        f.upload_weights(H_star.device)
+        g.vjp_prepare(f.kind, H_star.detach())
+        w = g.vjp_apply(f.kind, v, None)
+        ctx.deq, ctx.batch = deq, batch
+        ctx.save_for_backward(H_star, v, w)
+        return w.norm() ** 2 / w.numel()
+
+    @staticmethod
+    def backward(ctx, gout):
+        deq, batch = ctx.deq, ctx.batch
+        H_star, v, w = ctx.saved_tensors
+        f = deq.f
+        g = f.native_graph(batch)
+        f.upload_weights(H_star.device)
+        g.vjp_prepare(f.kind, H_star.detach())
+        flat = g.param_grad_tangent(f.kind, H_star, v, w) * (gout * (2.0 / w.numel()))
+        names = ["deqdss.f." + n for n, _ in f.named_parameters()]
+        grads = W.unpack_psignn_grads(flat, names, f.kind == N.KIND_MIXED)
+        return (None, None, None, None) + tuple(grads[n].clone() if n in grads else None for n in names)
+
+
 # ---------------------------------------------------------------------------------------------------------
 # DEQ wrapper
 # ---------------------------------------------------------------------------------------------------------
@@ -337,16 +372,16 @@ class DeepEquilibrium(nn.Module):
             self._log("forward_iteration.csv", '\n{} \t {}'.format(out_fw['lowest'], out_fw['nstep']))
             # new_H_star = f(H*) with the reference's backward hook folded into its backward: native solve + native parameter gradients
             new_H_star = _ImplicitLayer.apply(self, batch, H_star, H_init, *list(self.f.parameters()))
-            # Hutchinson Jacobian regulariser ‖Jᵀv‖²/numel with create_graph=True (reference model.py:207, :416-435): its double
-            # backward runs through the torch form of the layer (one evaluation per step)
-            Hs = H_star.detach().requires_grad_()
-            jac_loss = jac_loss_estimate(self.f._forward_torch(Hs, H_init.detach(), batch), Hs, vecs=1)
+            # Hutchinson Jacobian regulariser ‖Jᵀv‖²/numel (reference model.py:207, :416-435, create_graph=True): value and double
+            # backward native (same probe draw as the reference: torch.randn of the latent shape)
+            v = torch.randn(*H_star.shape, device=H_star.device)
+            jac_loss = _JacobianLoss.apply(self, batch, H_star, v, *list(self.f.parameters()))
         else:
-            with torch.enable_grad():
-                H_star.requires_grad_()
-                new_H_star = self.f(H_star, H_init, batch)
-            jac_loss = jac_loss_estimate(new_H_star, H_star, vecs=1)
+            new_H_star = self.f(H_star, H_init, batch)                 # native layer (no graph under no_grad)
             op = _solver.VjpOperator(self.f, H_star, batch, torch.zeros_like(H_star))
+            v = torch.randn(*H_star.shape, device=H_star.device)
+            w = op.graph.vjp_apply(op.kind, v, None)                   # jac_loss_estimate(new_H_star, H_star, vecs=1), native VJP
+            jac_loss = w.norm() ** 2 / w.numel()
             _, sradius = power_method(new_H_star, H_star, n_iters=150, operator=op)
             self._log("spectral_radius.csv", '\n{}'.format(sradius.item()))
         return new_H_star, jac_loss

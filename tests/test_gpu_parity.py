@@ -190,6 +190,46 @@ def test_param_grad_matches_autograd(golden):
     assert (tot_e / tot_n) ** 0.5 <= TOL
 
 
+def test_jacobian_loss_double_backward_matches_autograd(golden):
+    """psi_param_grad_tangent — the double backward of the Hutchinson regulariser ‖Jᵀv‖²/numel (model.py:207, :416-435) — against torch
+    autograd (``create_graph=True`` + backward) on the differentiable form of the same layer in fp64, same probe v: the loss value and
+    every parameter gradient, both families, checkpoint and random-init weights; bit-identical on a second run"""
+    from psi_gnn_b200 import model as PM
+    m = golden.model(DEV)
+    b = golden.batch(DEV)
+    f = m.deqdss.f
+    H, v, h0 = golden.t("f2", DEV), golden.t("vjp_y", DEV), golden.t("h0", DEV)
+    params = list(f.parameters())
+
+    def native():
+        for p_ in params:
+            p_.grad = None
+        loss = PM._JacobianLoss.apply(m.deqdss, b, H, v, *params)
+        loss.backward()
+        return float(loss), {n: (p_.grad.clone() if p_.grad is not None else torch.zeros_like(p_)) for n, p_ in f.named_parameters()}
+
+    l1, g1 = native()
+    l2, g2 = native()
+    assert l1 == l2 and all(torch.equal(g1[n], g2[n]) for n in g1)
+    m64 = golden.model(DEV).double()
+    b64 = b.double()
+    Hr = H.double().requires_grad_()
+    out = m64.deqdss.f._forward_torch(Hr, h0.double(), b64)
+    vJ = torch.autograd.grad(out, Hr, v.double(), create_graph=True)[0]
+    lref = vJ.norm() ** 2 / vJ.numel()
+    ref = torch.autograd.grad(lref, list(m64.deqdss.f.parameters()), allow_unused=True)
+    assert abs(l1 - float(lref)) <= 1e-5 * abs(float(lref))
+    tot_e, tot_n = 0.0, 0.0
+    for (n, p_), r in zip(m64.deqdss.f.named_parameters(), ref):
+        r = torch.zeros_like(p_) if r is None else r
+        tot_e += float((g1[n].double() - r).norm() ** 2); tot_n += float(r.norm() ** 2)
+    for (n, p_), r in zip(m64.deqdss.f.named_parameters(), ref):
+        r = torch.zeros_like(p_) if r is None else r
+        e = float((g1[n].double() - r).norm())
+        assert e <= 5e-5 * float(r.norm()) + 2e-6 * tot_n ** 0.5, (n, e, float(r.norm()), tot_n ** 0.5)
+    assert (tot_e / tot_n) ** 0.5 <= 2e-5, (tot_e / tot_n) ** 0.5
+
+
 def test_forced_anderson_steps(golden_small):
     """Teacher-forced Anderson updates (Gram matrix, bordered solve, mixing) with the production kernels vs the reference's formulas
     (solver.py:250-255) evaluated in fp64 on the same fp32 window: rel L2 ≤ 1e-5 (the reference's own fp32 evaluation is at 2e-8 … 6e-8)"""
