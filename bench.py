@@ -36,7 +36,7 @@ WORKLOADS = {
     "c1": ("dirichlet", 32, 0.075, "C1: PSI-GNN dirichlet training step, batch of 32 synthetic ~500-node 2D triangle Poisson meshes"),
     "c3": ("dirichlet", 256, 0.075, "C3: PSI-GNN dirichlet training step (Broyden forward + implicit-adjoint backward), batch 256 synthetic ~500-node meshes per GPU"),
     "c5": ("dirichlet", 1, 0.075, "C5: PSI-GNN dirichlet forward Broyden solve (500-step cap) of ONE synthetic 1M-node mesh, node-range partitioned "
-                                   "over the GPUs (NCCL halo exchange + all-reduced inner products)"),
+                                   "over the GPUs (halo rows and inner products exchanged through peer-mapped memory over NVLink)"),
     "c4": ("mixed", 256, 0.037, "C4: PSI-GNN mixed Dirichlet/Neumann training step, batch 256 synthetic ~2k-node meshes per GPU"),
 }
 C5_NODES = 1_000_000

@@ -326,7 +326,7 @@ __device__ __forceinline__ void ln_tan(const float (&rhat)[PSI_D], float rstd, c
 
 // fills rt[0 .. PG_REC) = tangent of rec (rec already filled by pgrad_node for the same node)
 template <int KIND>
-__device__ __forceinline__ void pgrad_node_tan(const GraphDev& G, const VjpCacheDev& C, const float* __restrict__ h, const float* __restrict__ hdot,
+__device__ __noinline__ void pgrad_node_tan(const GraphDev& G, const VjpCacheDev& C, const float* __restrict__ h, const float* __restrict__ hdot,
                                                const float* __restrict__ acc_t, int node, const float* rec, float* rt) {
     constexpr int PRB = (KIND == KIND_MIXED) ? 3 : 2;
     for (int i = 0; i < PG_REC; ++i) rt[i] = 0.f;
@@ -529,12 +529,18 @@ __device__ __forceinline__ void pgrad_node_tan(const GraphDev& G, const VjpCache
     }
 }
 
+template <int KIND>
+__device__ __noinline__ void pgrad_node_outline(const GraphDev& G, const VjpCacheDev& C, const float* __restrict__ h, const float* __restrict__ y,
+                                                const float* __restrict__ acc, int node, float* rec) {
+    pgrad_node<KIND>(G, C, h, y, acc, node, rec);
+}
+
 // PASS 0: S̄' of every node into Sb_t (the planar padded [2][N][12] layout of VjpCacheDev::Sb).  PASS 1: accumulate.
-template <int KIND, int PASS>
+template <int KIND>
 __global__ void __launch_bounds__(PG_NODES)
 k_pgrad_tan(GraphDev G, VjpCacheDev C, const float* __restrict__ h, const float* __restrict__ hdot, const float* __restrict__ y,
             const float* __restrict__ acc, const float* __restrict__ acc_t, const int* __restrict__ tab_y, const int* __restrict__ tab_x,
-            int n_tab, float* __restrict__ partial, int num_batches, float* __restrict__ Sb_t) {
+            int n_tab, float* __restrict__ partial, int num_batches, float* __restrict__ Sb_t, const int PASS) {
     extern __shared__ float rec[];                         // [PG_NODES][PG_PITCH] record, then [PG_NODES][PG_PITCH] tangent
     float* rect = rec + PG_NODES * PG_PITCH;
     float a[PG_MAX_PER_THREAD];
@@ -552,7 +558,7 @@ k_pgrad_tan(GraphDev G, VjpCacheDev C, const float* __restrict__ h, const float*
         const int node = batch * PG_NODES + threadIdx.x;
         float* r = rec + threadIdx.x * PG_PITCH;
         float* rt = rect + threadIdx.x * PG_PITCH;
-        pgrad_node<KIND>(G, C, h, y, acc, node, r);
+        pgrad_node_outline<KIND>(G, C, h, y, acc, node, r);
         pgrad_node_tan<KIND>(G, C, h, hdot, PASS == 1 ? acc_t : nullptr, node, r, rt);
         if (PASS == 0) {
             if (node < G.n_compute) {

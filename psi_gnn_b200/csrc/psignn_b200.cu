@@ -568,23 +568,21 @@ extern "C" int psi_param_grad_tangent(psi_graph_t* g, int kind, const float* dev
         const size_t smem = (size_t)2 * PG_NODES * PG_PITCH * sizeof(float);
         static bool attr_done = false;
         if (!attr_done) {
-            cudaFuncSetAttribute(k_pgrad_tan<KIND_DIRICHLET, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            cudaFuncSetAttribute(k_pgrad_tan<KIND_DIRICHLET, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            cudaFuncSetAttribute(k_pgrad_tan<KIND_MIXED, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            cudaFuncSetAttribute(k_pgrad_tan<KIND_MIXED, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaFuncSetAttribute(k_pgrad_tan<KIND_DIRICHLET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaFuncSetAttribute(k_pgrad_tan<KIND_MIXED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             attr_done = true;
         }
         VjpCacheDev Ct = g->vjp;                   // same masks and statistics; the gathered array is S̄' instead of S̄
         Ct.Sb = sb_t;
         const unsigned ngrid = node_grid(g->dev.n_compute);
         if (kind == PSI_KIND_DIRICHLET) {
-            k_pgrad_tan<KIND_DIRICHLET, 0><<<grid, PG_NODES, smem, st>>>(g->dev, g->vjp, dev_hstar, dev_hdot, dev_ybar, acc, nullptr, dev_tab_y, dev_tab_x, n_tab, partial, num_batches, sb_t);
+            k_pgrad_tan<KIND_DIRICHLET><<<grid, PG_NODES, smem, st>>>(g->dev, g->vjp, dev_hstar, dev_hdot, dev_ybar, acc, nullptr, dev_tab_y, dev_tab_x, n_tab, partial, num_batches, sb_t, 0);
             k_vjp_phase_b<KIND_DIRICHLET, false><<<ngrid, PSI_NODE_BLOCK, 0, st>>>(g->dev, Ct, dev_ybar, nullptr, scratch, noE, acc_t);
-            k_pgrad_tan<KIND_DIRICHLET, 1><<<grid, PG_NODES, smem, st>>>(g->dev, g->vjp, dev_hstar, dev_hdot, dev_ybar, acc, acc_t, dev_tab_y, dev_tab_x, n_tab, partial, num_batches, nullptr);
+            k_pgrad_tan<KIND_DIRICHLET><<<grid, PG_NODES, smem, st>>>(g->dev, g->vjp, dev_hstar, dev_hdot, dev_ybar, acc, acc_t, dev_tab_y, dev_tab_x, n_tab, partial, num_batches, nullptr, 1);
         } else {
-            k_pgrad_tan<KIND_MIXED, 0><<<grid, PG_NODES, smem, st>>>(g->dev, g->vjp, dev_hstar, dev_hdot, dev_ybar, acc, nullptr, dev_tab_y, dev_tab_x, n_tab, partial, num_batches, sb_t);
+            k_pgrad_tan<KIND_MIXED><<<grid, PG_NODES, smem, st>>>(g->dev, g->vjp, dev_hstar, dev_hdot, dev_ybar, acc, nullptr, dev_tab_y, dev_tab_x, n_tab, partial, num_batches, sb_t, 0);
             k_vjp_phase_b<KIND_MIXED, false><<<ngrid, PSI_NODE_BLOCK, 0, st>>>(g->dev, Ct, dev_ybar, nullptr, scratch, noE, acc_t);
-            k_pgrad_tan<KIND_MIXED, 1><<<grid, PG_NODES, smem, st>>>(g->dev, g->vjp, dev_hstar, dev_hdot, dev_ybar, acc, acc_t, dev_tab_y, dev_tab_x, n_tab, partial, num_batches, nullptr);
+            k_pgrad_tan<KIND_MIXED><<<grid, PG_NODES, smem, st>>>(g->dev, g->vjp, dev_hstar, dev_hdot, dev_ybar, acc, acc_t, dev_tab_y, dev_tab_x, n_tab, partial, num_batches, nullptr, 1);
         }
         k_pgrad_reduce<<<(n_tab + 127) / 128, 128, 0, st>>>(partial, grid, n_tab, dev_tab_dst, dev_out);
         if (cudaGetLastError() != cudaSuccess) { g_psi_err = "psi_param_grad_tangent: kernel launch failed"; rc = -1; }
@@ -895,6 +893,21 @@ static int qn_first(psi_solver* s, cudaStream_t st) {
 }
 
 // bookkeeping of step n (1-based) after the operator epilogue produced g_n, δg and the norm partials
+#ifdef PSI_DOTS_SELFCHECK
+static inline float __int_as_float_host(int v) { float f; memcpy(&f, &v, 4); return f; }
+__global__ void k_dots_selfcheck(const float* a, const float* b, int count, int chunks, int step, int kr, int* dbg, const int* done) {
+    if (*done) return;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+        if (__float_as_int(a[i]) != __float_as_int(b[i])) {
+            if (atomicAdd(&dbg[0], 1) == 0) {
+                dbg[1] = step; dbg[2] = i / chunks; dbg[3] = i % chunks; dbg[4] = kr; dbg[5] = __float_as_int(a[i]); dbg[6] = __float_as_int(b[i]);
+                dbg[7] = (count / chunks - 2) / 3;
+            }
+        }
+    }
+}
+#endif
+
 static int qn_update(psi_solver* s, int n, int norm_blocks, cudaStream_t st) {
     const int nhist = n - 1;
     if (hist_ensure(s, n - 1, st)) return -1;
@@ -909,10 +922,33 @@ static int qn_update(psi_solver* s, int n, int norm_blocks, cudaStream_t st) {
     for (int cand = 16; cand >= 8; cand >>= 1)
         if ((int64_t)s->act_dchunks * ((nhist + cand - 1) / cand) <= (int64_t)s->tma_ctas) kr = cand;
 #endif
+#ifdef PSI_FORCE_KR
+    kr = PSI_FORCE_KR;
+#endif
     k_qn_dots_tma<<<s->tma_ctas, TMA_THREADS, dots_tma_smem(), st>>>(s->hist, nhist, s->dx, s->dg, s->g, s->partial, s->act_dchunks,
                                                                      &s->ctrl->done, kr);
     prof_end(s, n, 1, st);
     PSI_CK_LAUNCH();
+#ifdef PSI_DOTS_SELFCHECK
+    {   // diagnosis: the same pass with 32-vector items into a second buffer; the partial sums must agree bit for bit
+        static float* p2 = nullptr;
+        static int* dbg = nullptr;
+        static size_t p2_floats = 0;
+        const size_t need = (size_t)(3 * s->cap + 2) * (size_t)s->num_chunks;
+        if (p2 == nullptr || p2_floats < need) { cudaMalloc(&p2, need * sizeof(float)); p2_floats = need; }
+        if (dbg == nullptr) { cudaMallocManaged(&dbg, 64 * sizeof(int)); memset(dbg, 0, 64 * sizeof(int)); }
+        k_qn_dots_tma<<<s->tma_ctas, TMA_THREADS, dots_tma_smem(), st>>>(s->hist, nhist, s->dx, s->dg, s->g, p2, s->act_dchunks, &s->ctrl->done, DOTS_KR);
+        k_dots_selfcheck<<<64, 256, 0, st>>>(s->partial, p2, (3 * nhist + 2) * s->act_dchunks, s->act_dchunks, n, kr, dbg, &s->ctrl->done);
+        if (n == s->threshold || n % 50 == 0) {
+            cudaStreamSynchronize(st);
+            if (dbg[0] > 0 && dbg[8] == 0) {
+                dbg[8] = 1;
+                fprintf(stderr, "[selfcheck] %d mismatching partials so far; first at step %d: row %d (k %d q %d) chunk %d kr %d: %.9g vs %.9g (nhist %d chunks %d)\n",
+                        dbg[0], dbg[1], dbg[2], dbg[2] / 3, dbg[2] % 3, dbg[3], dbg[4], __int_as_float_host(dbg[5]), __int_as_float_host(dbg[6]), dbg[7], s->act_dchunks);
+            }
+        }
+    }
+#endif
     const int fin_blocks = std::max(1, std::min(2 * s->tma_ctas, (nhist * 3 + 2 + 7) / 8));   // one warp per row of the partial matrix
     if (s->comm == nullptr) {
         k_qn_fin1<<<fin_blocks, 256, 0, st>>>(nhist, s->partial, s->act_dchunks, s->coef, s->cap, s->dbuf, s->norm_part, norm_blocks, s->ctrl,

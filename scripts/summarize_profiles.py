@@ -55,6 +55,22 @@ def full(path, out):
         for k in KEYS:
             if k in hdr:
                 out.write("| %s | %s %s |\n" % (k, r[hdr.index(k)], units[hdr.index(k)]))
+        # warp-state: the largest stall reasons (cycles a warp waits per issued instruction) and the busiest pipes
+        def top(pattern, n):
+            vals = []
+            for i, h_ in enumerate(hdr):
+                if re.search(pattern, h_):
+                    try:
+                        vals.append((float(r[i]), h_, units[i]))
+                    except ValueError:
+                        pass
+            return sorted(vals, reverse=True)[:n]
+        for v_, h_, u_ in top(r"issue_stalled_.*_per_warp_active|average_warps_issue_stalled_.*ratio|average_warp_latency_issue_stalled", 6):
+            out.write("| stall: %s | %.3f %s |\n" % (h_, v_, u_))
+        for v_, h_, u_ in top(r"inst_executed_pipe_.*pct_of_peak|pipe_.*cycles_active.avg.pct_of_peak_sustained_active", 6):
+            out.write("| pipe: %s | %.2f %s |\n" % (h_, v_, u_))
+        for v_, h_, u_ in top(r"^l1tex__data_pipe_lsu_wavefronts.sum$|^l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum$|^l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum$|^smsp__inst_executed_pipe_fma.sum$|^sm__inst_executed_pipe_fma.sum$|^smsp__inst_executed_pipe_fmaheavy.sum$|^smsp__inst_executed_pipe_fmalite.sum$", 8):
+            out.write("| count: %s | %.0f %s |\n" % (h_, v_, u_))
         scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
 
         def in_bytes(key):
@@ -71,7 +87,8 @@ def main():
     tag = sys.argv[1]
     os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
     with open(os.path.join(ROOT, "profiles", tag + ".md"), "w") as out:
-        out.write("# ncu summary %s\n\nCommand: `python bench.py --steps 1 --warmup 1 --no-cpu-baseline` (C3, 1 × B200).\n\n" % tag)
+        out.write("# ncu summary %s\n\nCommands: `scripts/ncu_round2.sh` (1 × B200; operator kernels via `scripts/prof_operator.py`, launch list and history "
+                  "kernels via `python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-extra-blocks`).\n\n" % tag)
         for a in sys.argv[2:]:
             if a.endswith(".csv"):
                 launches(a, out)
