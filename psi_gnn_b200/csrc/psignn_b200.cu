@@ -918,7 +918,9 @@ static int qn_update(psi_solver* s, int n, int norm_blocks, cudaStream_t st) {
     // (more SMs busy; a second wave of single-batch items is avoided: repeated long solves at 7 … 15 chunks were not bitwise
     // repeatable in that regime, see NOTES.md)
     int kr = DOTS_KR;
-#ifndef PSI_FIXED_KR
+#if defined(PSI_KR_FINE)
+    while (kr > 8 && (int64_t)s->act_dchunks * ((nhist + kr - 1) / kr) < 2 * (int64_t)s->tma_ctas) kr >>= 1;
+#elif !defined(PSI_FIXED_KR)
     for (int cand = 16; cand >= 8; cand >>= 1)
         if ((int64_t)s->act_dchunks * ((nhist + cand - 1) / cand) <= (int64_t)s->tma_ctas) kr = cand;
 #endif

@@ -157,8 +157,10 @@ k_qn_dots_tma(QnHistory H, int nhist, const float* __restrict__ dx, const float*
                 float4 u[R], v[R];
 #pragma unroll
                 for (int j = 0; j < R; ++j) { u[j] = su[tid + j * TMA_CONSUMERS]; v[j] = sv[tid + j * TMA_CONSUMERS]; }
+#ifdef PSI_EARLY_RELEASE          // diagnosis only: the round-1 order (release right behind the loads)
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty[s]);
+#endif
                 float a = 0.f, cc = 0.f, e = 0.f;
 #pragma unroll
                 for (int j = 0; j < R; ++j) {
@@ -167,6 +169,12 @@ k_qn_dots_tma(QnHistory H, int nhist, const float* __restrict__ dx, const float*
                     e = dot4(v[j], rg[j], e);
                 }
                 a = warp_sum(a); cc = warp_sum(cc); e = warp_sum(e);
+                // Release the slot only now: the shuffles above consumed every lane's loaded values, so all shared-memory reads of the
+                // warp have completed.  (An arrive issued right behind the loads runs in another pipe and can overtake loads still in
+                // flight; the refill — fastest when the history sits in L2 — would then overwrite data not yet read.)
+#ifndef PSI_EARLY_RELEASE
+                if (lane == 0) mbar_arrive(&empty[s]);
+#endif
                 if (lane == 0) {
                     float* rp = red + ((buf * DOTS_KB + kk) * 3) * 8 + warp;
                     rp[0] = a; rp[8] = cc; rp[16] = e;
@@ -282,14 +290,21 @@ k_qn_axpy_tma(QnHistory H, int nhist, int n, const float* __restrict__ coef, int
             // rows beyond cnt4 hold stale ring data: they are read (harmless) but never stored
             u[0] = su[tid]; u[1] = su[tid + TMA_CONSUMERS];
             v[0] = su[AXPY_TILE / 4 + tid]; v[1] = su[AXPY_TILE / 4 + tid + TMA_CONSUMERS];
+#ifdef PSI_EARLY_RELEASE
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[st]);
+#endif
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
                 av[j].x = fmaf(a, v[j].x, av[j].x); av[j].y = fmaf(a, v[j].y, av[j].y); av[j].z = fmaf(a, v[j].z, av[j].z); av[j].w = fmaf(a, v[j].w, av[j].w);
                 aw[j].x = fmaf(c, u[j].x, aw[j].x); aw[j].y = fmaf(c, u[j].y, aw[j].y); aw[j].z = fmaf(c, u[j].z, aw[j].z); aw[j].w = fmaf(c, u[j].w, aw[j].w);
                 at[j].x = fmaf(e, u[j].x, at[j].x); at[j].y = fmaf(e, u[j].y, at[j].y); at[j].z = fmaf(e, u[j].z, at[j].z); at[j].w = fmaf(e, u[j].w, at[j].w);
             }
+            // release the slot after the FMAs have consumed the loaded values (see pass 1): no shared-memory read of the warp is in flight
+#ifndef PSI_EARLY_RELEASE
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[st]);
+#endif
         }
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
