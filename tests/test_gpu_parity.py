@@ -542,6 +542,75 @@ def test_large_mesh_properties():
     assert abs(lhs - rhs) <= 1e-4 * abs(rhs) + 1e-5
 
 
+def test_c5_size_mesh_layer_vs_oracle_and_properties():
+    """BASELINE configs[4] at FULL size — one 1 005 496-node mesh (7 M matrix entries), reordered as bench.py does:
+      * one layer application through the C ABI vs the CPU oracle (fp32) on the same inputs: rel L2 ≤ 1e-5;
+      * bit-equal re-run, Dirichlet rows bit-equal to h0, LayerNorm statistics of the free rows;
+      * one VJP application vs the oracle's autograd VJP (≤ 1e-5) and bit-equal on a second run;
+      * a 25-step Broyden solve: bit-equal on a second run, residual decreasing, rel trace of the first 5 steps vs the oracle's solve."""
+    from oracle import psignn_oracle as O
+    from psi_gnn_b200 import partition, solver as S, synthetic
+    g = Golden("dirichlet_ckpt")
+    m = g.model(DEV)
+    host = partition.reorder_mesh(synthetic.make_large_mesh(1_000_000, seed=0))
+    assert host.num_nodes > 1_000_000
+    b = host.to(DEV)
+    P = g.params()
+    with torch.no_grad():
+        h0 = m._encode_native(b.x)
+        f1 = m.deqdss.f(h0, h0, b)
+        f1b = m.deqdss.f(h0, h0, b)
+        f2 = m.deqdss.f(f1, h0, b)
+    assert torch.equal(f1, f1b)
+    h0_ref = O.encoder(P, host.x)
+    assert rel_err(h0, h0_ref) <= TOL
+    Hc = f1.cpu().requires_grad_()
+    ref2 = O.f_dirichlet(P, Hc, h0.cpu(), host)                       # second application, on the CUDA path's own f1
+    assert rel_err(f2, ref2.detach()) <= TOL, rel_err(f2, ref2.detach())
+    d = b.tags.reshape(-1) == 1
+    assert torch.equal(f1[d], h0[d]) and int(d.sum()) > 1000
+    z = (f1[~d] - m.deqdss.f.laynorm.bias) / m.deqdss.f.laynorm.weight
+    assert float(z.mean(1).abs().max()) < 1e-4
+    # VJP at the same point.  Among the 1.2e8 ReLUs of a 1 M-node mesh a few pre-activations sit within fp32 rounding of zero, so ANY
+    # fp32 evaluation flips a few masks against the fp64 one (a derivative discontinuity): the oracle's own fp32 VJP is 9e-5 away from
+    # its fp64 VJP here.  Band: our distance to the fp64 VJP ≤ 3 × the fp32 oracle's, and the error sits in a handful of rows.
+    y = torch.randn(f1.shape, generator=torch.Generator().manual_seed(7))
+    v32 = torch.autograd.grad(ref2, Hc, y)[0]
+    P64 = {k_: v_.double() for k_, v_ in P.items()}
+    H64 = f1.cpu().double().requires_grad_()
+    v64 = torch.autograd.grad(O.f_dirichlet(P64, H64, h0.cpu().double(), host.double()), H64, y.double())[0]
+    op = S.VjpOperator(m.deqdss.f, f1, b, torch.zeros_like(f1))
+    v1, v2 = op(y.to(DEV)), op(y.to(DEV))
+    assert torch.equal(v1, v2)
+    e_ours, e_ref = rel_err(v1, v64), rel_err(v32, v64)
+    row_err = (v1.cpu().double() - v64).norm(dim=1) / (v64.norm(dim=1) + 1e-12)
+    bad_rows = int((row_err > 1e-4).sum())
+    print("C5-size VJP vs fp64 oracle: ours %.2e, fp32 oracle %.2e; rows off by > 1e-4: %d of %d" % (e_ours, e_ref, bad_rows, v64.shape[0]))
+    assert e_ours <= 3.0 * e_ref + TOL, (e_ours, e_ref)
+    assert bad_rows <= 1e-4 * v64.shape[0], bad_rows
+    assert float(torch.median(row_err)) <= TOL
+    lop = S.LayerOperator(m.deqdss.f, h0, b)
+    r1 = S.broyden(lop, h0, threshold=25, eps=1e-30)
+    r2 = S.broyden(lop, h0, threshold=25, eps=1e-30)
+    assert r1["rel_trace"] == r2["rel_trace"] and torch.equal(r1["result"], r2["result"])
+    assert r1["rel_trace"][-1] < 0.2 * r1["rel_trace"][0]
+    # the oracle's solve (reference algorithm, fp32, CPU).  Its own rel values come from fp32 norms over 1e7 elements, which torch's
+    # CPU reduction gets right only to ≈ 1e-3 (0.0025252 vs 0.0025284 with fp64 accumulation, thread-count dependent), so the residuals
+    # of ITS iterates are re-measured with fp64 norms; the CUDA path (fp64 sums of per-block fp32 partials) must match those.
+    rec = []
+
+    def f_oracle(H):
+        Y = O.f_dirichlet(P, H, h0_ref, host)
+        rec.append(float((Y - H).double().norm() / Y.double().norm()))
+        return Y
+
+    ref = O.broyden(f_oracle, h0_ref, 5, 1e-30)
+    want = np.asarray(rec[1:6])                      # rel_trace[j] belongs to the (j+1)-th evaluation
+    got = np.asarray(r1["rel_trace"][:len(want)])
+    assert np.all(np.abs(np.asarray(ref["rel_trace"][:len(want)]) - want) <= 5e-3 * want)
+    assert np.all(np.abs(got - want) <= 1e-3 * want), (got, want)
+
+
 # ---- DSS / DSGPS baselines on the shared layer kernel (config 2) ------------------------------------------------------
 def _baseline(name):
     g = Golden(name)
