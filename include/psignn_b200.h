@@ -141,6 +141,14 @@ int psi_param_grad_tangent(psi_graph_t* g, int kind, const float* dev_hstar, con
                            const int32_t* dev_tab_dst, const int32_t* dev_tab_y, const int32_t* dev_tab_x, int n_tab, float* dev_out,
                            void* stream);
 int psi_pgrad_layout(int32_t out[16]);
+/* Backward of ONE unrolled layer of the DSS / DSGPS baselines at the layer's own input h — what autograd does for one step of the
+ * reference's unrolled training forward (dirichlet/dss/model.py:83-91, dirichlet/dsgps/model.py:143-163, mixed/dsgps/model.py:76-97):
+ * dev_hbar = (d f / d h)^T y_bar, dev_out = (d f / d theta)^T y_bar in packed-block layout (as psi_param_grad).  kind = PSI_KIND_DSS,
+ * PSI_KIND_DSGPS or PSI_KIND_DSGPS_MIXED; the layer's weight block must be resident (psi_weights_upload); the table comes from
+ * psi_gnn_b200/weights.py (baseline_grad_table; record layout = psi_pgrad_layout).  The gradient to h0 (the clamped Dirichlet rows
+ * copy it) is y_bar on those rows and is left to the caller.  Deterministic (no atomics). */
+int psi_layer_backward(psi_graph_t* g, int kind, const float* dev_h, const float* dev_ybar, const int32_t* dev_tab_dst,
+                       const int32_t* dev_tab_y, const int32_t* dev_tab_x, int n_tab, float* dev_hbar, float* dev_out, void* stream);
 
 /* ---- physics residual, encoder, decoder ------------------------------------------------------- */
 /* r = A u - y (all nnz incl. diagonal); *dev_mean_sq = mean(r^2); dev_r may be NULL */

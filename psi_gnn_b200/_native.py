@@ -49,6 +49,7 @@ SIGNATURES = {
     "psi_param_grad": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "psi_param_grad_tangent": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "psi_pgrad_layout": (c_int, [POINTER(c_int32)]),
+    "psi_layer_backward": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "psi_residual": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "psi_spmv_t": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "psi_encode": (c_int, [c_int64, c_void_p, c_void_p, c_void_p]),

@@ -6,14 +6,17 @@
 
 Class names, constructor signatures and ``state_dict`` keys are the reference's, so its checkpoints load; ``inference`` runs
 entirely on the extension (one weight-block upload + one layer launch per unrolled step).  ``forward`` (the unrolled training
-forward with the per-layer losses of the reference, differentiable) evaluates every layer through the differentiable torch form of
-the same layer (``_Phi`` + ``nn.Linear``): the baselines' unrolled backward has no native kernel ("layer kernel reuse
-only"); the residuals use the native SpMV.  ``ModelDSGPSMixed`` is the mixed-boundary variant (reference mixed/dsgps/model.py).
+forward with the per-layer losses of the reference) evaluates every layer with the same native kernel and differentiates it with
+``psi_layer_backward`` (``_UnrolledLayer``: h̄ and the parameter gradients of one step, deterministic, no atomics); the decoders /
+encoder are ``nn.Linear`` under autograd, the residuals use the native SpMV.  ``_step_torch`` keeps the differentiable torch form of a
+DSGPS step for user code that needs a graph through the layer (double backward).  ``ModelDSGPSMixed`` is the mixed-boundary variant
+(reference mixed/dsgps/model.py).
 """
 from __future__ import annotations
 
 import torch
 import torch.nn as nn
+from torch import autograd
 
 from . import _native as N
 from . import weights as W
@@ -57,6 +60,33 @@ def _decode(h):
     return u
 
 
+class _UnrolledLayer(autograd.Function):
+    """one unrolled step ``H_{k+1} = layer_k(H_k)`` of a baseline: forward = the fused layer kernel with the step's weight block,
+    backward = ``psi_layer_backward`` (Jᵀȳ and (∂f/∂θ)ᵀȳ in one call) + the gradient to ``h0`` (the clamped Dirichlet rows copy it).
+    ``owner`` is the model (``_layer_kind``, ``_layer_block``, ``_layer_names``, ``_layer_unpack``), ``params`` the step's parameters
+    in the order of ``owner._layer_names(step)``.  The weight block is looked up again in backward because another step's block may
+    occupy the constant bank by then."""
+
+    @staticmethod
+    def forward(ctx, owner, batch, step, dmask, h, h0, *params):
+        g = graph_of(batch, owner._layer_kind)
+        W.upload(*owner._layer_block(step, h.device))
+        ctx.owner, ctx.g, ctx.step, ctx.dmask = owner, g, step, dmask
+        ctx.save_for_backward(h)
+        return g.layer_forward(owner._layer_kind, h.detach(), h0.detach() if h0 is not None else None)
+
+    @staticmethod
+    def backward(ctx, ybar):
+        (h,) = ctx.saved_tensors
+        owner = ctx.owner
+        W.upload(*owner._layer_block(ctx.step, h.device))
+        ybar = ybar.contiguous()
+        hbar, flat = ctx.g.layer_backward(owner._layer_kind, h.detach(), ybar)
+        grads = owner._layer_unpack(flat, ctx.step)
+        h0bar = torch.where(ctx.dmask, ybar, torch.zeros_like(ybar)) if (ctx.dmask is not None and ctx.needs_input_grad[5]) else None
+        return (None, None, None, None, hbar, h0bar) + tuple(grads[n].clone() for n in owner._layer_names(ctx.step))
+
+
 class DeepStatisticalSolver(nn.Module):
     """config keys: latent_dim, k, alpha, gamma (reference dirichlet/dss/main.py)."""
 
@@ -79,6 +109,26 @@ class DeepStatisticalSolver(nn.Module):
                 self._blobs = (key, torch.stack([W.pack_dss(P, k, self.config["alpha"], device) for k in range(self.config["k"])]).contiguous(),
                                W.next_serial())
         return self._blobs[2], self._blobs[1]
+
+    _layer_kind = N.KIND_DSS
+
+    def _layer_block(self, k, device):
+        """(packed block of layer k, constant-bank key)"""
+        serial, blobs = self._packed(device)
+        return blobs[k], (serial, k)
+
+    def _layer_names(self, k):
+        return [f"{m}.{k}.mlp.mlp.{i}.{w}" for m in ("phi_to_list", "phi_from_list", "psi_list") for i in (0, 2) for w in ("weight", "bias")]
+
+    def _layer_unpack(self, flat, k):
+        return W.unpack_dss_grads(flat, k)
+
+    def _step_torch(self, k, h, h0, batch):
+        """layer k in differentiable torch form (dirichlet/dss/model.py:83-91) — not used by ``forward`` (which runs ``_UnrolledLayer``);
+        kept for user code that needs an autograd graph through the layer"""
+        mess_to = self.phi_to_list[k](h, batch.edge_index, batch.a_ij_norm)
+        mess_from = self.phi_from_list[k](h, batch.edge_index, batch.a_ij_norm)
+        return h + self.config["alpha"] * self.psi_list[k](torch.cat([h, mess_to, mess_from, batch.b_prime_norm], dim=1))
 
     def inference(self, batch):
         if not batch.edge_index.is_cuda:
@@ -109,12 +159,12 @@ class DeepStatisticalSolver(nn.Module):
         U['0'] = self.decoder_list[0](H['0']) + batch.x * 0
         cumul_res['0'] = self.residual_loss(U['0'], batch.edge_index, batch.a_ij, batch.b_prime)
         cumul_mse['0'] = self.mse_loss(U['0'], batch.x)
+        if cfg["latent_dim"] != W.D:
+            raise NotImplementedError("psi_gnn_b200: the fused kernel is built for latent_dim=10")
+        P = dict(self.named_parameters())
         for update in range(cfg["k"]):
             h = H[str(update)]
-            mess_to = self.phi_to_list[update](h, batch.edge_index, batch.a_ij_norm)
-            mess_from = self.phi_from_list[update](h, batch.edge_index, batch.a_ij_norm)
-            correction = self.psi_list[update](torch.cat([h, mess_to, mess_from, batch.b_prime_norm], dim=1))
-            H[str(update + 1)] = h + cfg["alpha"] * correction
+            H[str(update + 1)] = _UnrolledLayer.apply(self, batch, update, None, h, None, *[P[n] for n in self._layer_names(update)])
             U[str(update + 1)] = self.decoder_list[update](H[str(update + 1)])
             cumul_res[str(update + 1)] = self.residual_loss(U[str(update + 1)], batch.edge_index, batch.a_ij, batch.b_prime)
             cumul_mse[str(update + 1)] = self.mse_loss(U[str(update + 1)], batch.x)
@@ -149,6 +199,25 @@ class ModelDSGPS(nn.Module):
         self.mse_loss = nn.MSELoss()
         self._blob = (None, None, None)
 
+    def _layer_block(self, step, dev):
+        """(packed block of the recurrent step, constant-bank key) — the same block at every step"""
+        P = W.named_tensors(self)
+        key = (W.version_key(P), str(dev))
+        if self._blob[0] != key:
+            with torch.no_grad():
+                self._blob = (key, W.pack_dsgps(P, dev), W.next_serial())
+        return self._blob[1], self._blob[2]
+
+    @property
+    def _layer_kind(self):
+        return self.KIND
+
+    def _layer_names(self, step):
+        return list(W.unpack_dsgps_grads(torch.zeros(W.TOTAL_FLOATS), self.KIND == N.KIND_DSGPS_MIXED))
+
+    def _layer_unpack(self, flat, step):
+        return W.unpack_dsgps_grads(flat, self.KIND == N.KIND_DSGPS_MIXED)
+
     def inference(self, batch, k=None):
         if not batch.edge_index.is_cuda:
             raise RuntimeError("psi_gnn_b200: CUDA tensors required — there is no CPU path")
@@ -156,12 +225,7 @@ class ModelDSGPS(nn.Module):
             raise NotImplementedError("psi_gnn_b200: the fused kernel is built for latent_dim=10")
         g = graph_of(batch, self.KIND)
         dev = batch.edge_index.device
-        P = W.named_tensors(self)
-        key = (W.version_key(P), str(dev))
-        if self._blob[0] != key:
-            with torch.no_grad():
-                self._blob = (key, W.pack_dsgps(P, dev), W.next_serial())
-        W.upload(self._blob[1], self._blob[2])
+        W.upload(*self._layer_block(0, dev))
         x = N.f32(batch.x.reshape(-1))
         H0 = torch.empty(x.numel(), W.D, dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
@@ -175,8 +239,10 @@ class ModelDSGPS(nn.Module):
                                                  N.ptr(out), N.stream_ptr()), "psi_layers_unrolled")
         return _decode(out)
 
-    def _step(self, h, h0, batch, dmask, nmask):
-        """one recurrent step in differentiable torch form (dirichlet/dsgps/model.py:64-78, mixed/dsgps/model.py:76-97)"""
+    def _step_torch(self, step, h, h0, batch):
+        """one recurrent step in differentiable torch form (dirichlet/dsgps/model.py:64-78, mixed/dsgps/model.py:76-97) — not used by
+        ``forward`` (which runs ``_UnrolledLayer``); kept for user code that needs an autograd graph through the step"""
+        dmask, nmask = self._masks(batch)
         mess_to = self.phi_to(h, batch.edge_index, batch.edge_attr)
         mess_from = self.phi_from(h, batch.edge_index, batch.edge_attr)
         c = torch.cat([h, mess_to, mess_from, batch.prb_data], dim=1)
@@ -188,6 +254,12 @@ class ModelDSGPS(nn.Module):
             upd = self.update_neumann(torch.cat([h, mp_neu, batch.prb_data, batch.unit_normal_vector], dim=1))
             nxt = torch.where(nmask, upd, nxt)
         return torch.where(dmask, h0, nxt)
+
+    def _masks(self, batch):
+        """(Dirichlet rows, Neumann rows or None) as [N, 1] boolean masks"""
+        t = batch.tags
+        mixed = self.KIND == N.KIND_DSGPS_MIXED
+        return ((t[:, 1] if mixed else t.reshape(-1)) == 1)[:, None], ((t[:, 2] == 1)[:, None] if mixed else None)
 
     def residual_loss(self, u, batch):
         """mean((A u − y)²) on the native SpMV kernels (forward and backward), reference dirichlet/dsgps/model.py:165-176"""
@@ -201,9 +273,7 @@ class ModelDSGPS(nn.Module):
             raise RuntimeError("psi_gnn_b200: CUDA tensors required — there is no CPU path")
         cfg = self.config
         mixed = self.KIND == N.KIND_DSGPS_MIXED
-        t = batch.tags
-        dmask = ((t[:, 1] if mixed else t.reshape(-1)) == 1)[:, None]
-        nmask = (t[:, 2] == 1)[:, None] if mixed else None
+        dmask, nmask = self._masks(batch)
         index_dirichlet = torch.where(dmask[:, 0])[0]
         H, U = {}, {}
         cumul_res, cumul_mse, cumul_enc, cumul_autoenc, cumul_mse_dirichlet = {}, {}, {}, {}, {}
@@ -213,9 +283,13 @@ class ModelDSGPS(nn.Module):
         cumul_mse['0'] = self.mse_loss(U['0'], batch.sol)
         H['0'] = self.autoencoder.encoder(U['0'])
         enc, dec = self.autoencoder.encoder, self.autoencoder.decoder
+        if cfg["latent_dim"] != W.D:
+            raise NotImplementedError("psi_gnn_b200: the fused kernel is built for latent_dim=10")
+        P = dict(self.named_parameters())
+        names = self._layer_names(0)
         for update in range(cfg["k"]):
             key = str(update + 1)
-            H[key] = self._step(H[str(update)], H['0'], batch, dmask, nmask)
+            H[key] = _UnrolledLayer.apply(self, batch, update, dmask, H[str(update)], H['0'], *[P[n] for n in names])
             U[key] = dec(H[key])
             cumul_res[key] = self.residual_loss(U[key], batch)
             cumul_mse[key] = self.mse_loss(U[key], batch.sol)

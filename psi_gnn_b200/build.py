@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libpsignn_b200.so")
 STAMP = os.path.join(LIB_DIR, "libpsignn_b200.stamp")
-SOURCES = ["psignn_b200.cu", "common.cuh", "weights.cuh", "graph.cuh", "layer.cuh", "vjp.cuh", "broyden.cuh", "anderson.cuh", "qn_tma.cuh", "comm.cuh", "pgrad.cuh"]
+SOURCES = ["psignn_b200.cu", "common.cuh", "weights.cuh", "graph.cuh", "layer.cuh", "vjp.cuh", "broyden.cuh", "anderson.cuh", "qn_tma.cuh", "comm.cuh", "pgrad.cuh", "baseline_bwd.cuh"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
               "-Xcompiler", "-fPIC"]
 

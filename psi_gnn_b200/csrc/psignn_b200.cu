@@ -14,6 +14,7 @@
 #include "qn_tma.cuh"
 #include "comm.cuh"
 #include "pgrad.cuh"
+#include "baseline_bwd.cuh"
 
 #include <algorithm>
 #include <cstring>
@@ -589,6 +590,72 @@ extern "C" int psi_param_grad_tangent(psi_graph_t* g, int kind, const float* dev
     }
     psi_free_async(buf, st);
     return rc;
+}
+
+// Backward of ONE unrolled layer of the DSS / DSGPS baselines at its own input h (baseline_bwd.cuh): h̄ = Jᵀȳ and the parameter gradient
+// θ̄ in packed-block layout.  The layer's weight block must be resident (psi_weights_upload).  Deterministic, no atomics.
+template <int KIND>
+static int launch_baseline_backward(psi_graph* g, const float* h, const float* ybar, const int32_t* tab_dst, const int32_t* tab_y,
+                                    const int32_t* tab_x, int n_tab, float* hbar, float* out, cudaStream_t st) {
+    const int64_t N = g->N;
+    float *Dloc = nullptr, *Sb = nullptr, *acc = nullptr, *partial = nullptr;
+    const int num_batches = (int)((g->dev.n_compute + PG_NODES - 1) / PG_NODES);
+    const int grid = std::max(1, std::min(num_batches, PSI_NUM_SMS_B200 * 2));
+    const size_t smem = (size_t)PG_NODES * PG_PITCH * sizeof(float);
+    int rc = 0;
+    if (psi_malloc_async((void**)&Dloc, (size_t)N * PSI_D * sizeof(float), st) != cudaSuccess ||
+        psi_malloc_async((void**)&Sb, (size_t)2 * N * PSI_QPITCH * sizeof(float), st) != cudaSuccess ||
+        psi_malloc_async((void**)&acc, (size_t)N * 30 * sizeof(float), st) != cudaSuccess ||
+        psi_malloc_async((void**)&partial, (size_t)grid * n_tab * sizeof(float), st) != cudaSuccess) {
+        g_psi_err = "psi_layer_backward: out of device memory";
+        rc = -1;
+    }
+    if (!rc) {
+        static bool attr_done = false;
+        if (!attr_done) {
+            cudaFuncSetAttribute(k_bl_pass<KIND_DSS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaFuncSetAttribute(k_bl_pass<KIND_DSGPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaFuncSetAttribute(k_bl_pass<KIND_DSGPS_MIXED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            attr_done = true;
+        }
+        // PSI_BL_DEBUG=1: synchronise behind every kernel and name the one that failed
+        static const bool dbg = getenv("PSI_BL_DEBUG") != nullptr;
+        auto stage = [&](const char* what) {
+            cudaError_t e = cudaGetLastError();
+            if (e == cudaSuccess && dbg) e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess && !rc) { g_psi_err = std::string("psi_layer_backward: ") + what + " -> " + cudaGetErrorString(e); rc = -1; }
+        };
+        k_bl_pass<KIND><<<grid, PG_NODES, smem, st>>>(g->dev, h, ybar, nullptr, Dloc, Sb, tab_y, tab_x, n_tab, partial, num_batches, 0);
+        stage("k_bl_pass(0)");
+        k_bl_gather<KIND><<<node_grid(g->dev.n_compute), PSI_NODE_BLOCK, 0, st>>>(g->dev, h, Dloc, Sb, hbar, acc);
+        stage("k_bl_gather");
+        k_bl_pass<KIND><<<grid, PG_NODES, smem, st>>>(g->dev, h, ybar, acc, Dloc, Sb, tab_y, tab_x, n_tab, partial, num_batches, 1);
+        stage("k_bl_pass(1)");
+        k_pgrad_reduce<<<(n_tab + 127) / 128, 128, 0, st>>>(partial, grid, n_tab, tab_dst, out);
+        stage("k_pgrad_reduce");
+    }
+    psi_free_async(Dloc, st);
+    psi_free_async(Sb, st);
+    psi_free_async(acc, st);
+    psi_free_async(partial, st);
+    return rc;
+}
+
+extern "C" int psi_layer_backward(psi_graph_t* g, int kind, const float* dev_h, const float* dev_ybar, const int32_t* dev_tab_dst,
+                                  const int32_t* dev_tab_y, const int32_t* dev_tab_x, int n_tab, float* dev_hbar, float* dev_out, void* stream) {
+    if (check_kind(g, kind)) return -1;
+    if (kind != PSI_KIND_DSS && kind != PSI_KIND_DSGPS && kind != PSI_KIND_DSGPS_MIXED)
+        PSI_FAIL("psi_layer_backward: for the unrolled baseline layers (the PSI-GNN layers use psi_vjp_apply / psi_param_grad)");
+    if (g->part != nullptr) PSI_FAIL("psi_layer_backward: not available on a mesh partition");
+    if (n_tab < 1 || n_tab > PG_NODES * BL_MAX_PER_THREAD) PSI_FAIL("psi_layer_backward: table size out of range");
+    if (dev_out == nullptr || dev_tab_dst == nullptr || dev_tab_y == nullptr || dev_tab_x == nullptr) PSI_FAIL("psi_layer_backward: null pointer");
+    cudaStream_t st = as_stream(stream);
+    PSI_CK(cudaMemsetAsync(dev_out, 0, sizeof(LayerWeights), st));
+    if (g->N == 0) return 0;
+    if (dev_h == nullptr || dev_ybar == nullptr || dev_hbar == nullptr) PSI_FAIL("psi_layer_backward: null pointer");
+    if (kind == PSI_KIND_DSS) return launch_baseline_backward<KIND_DSS>(g, dev_h, dev_ybar, dev_tab_dst, dev_tab_y, dev_tab_x, n_tab, dev_hbar, dev_out, st);
+    if (kind == PSI_KIND_DSGPS) return launch_baseline_backward<KIND_DSGPS>(g, dev_h, dev_ybar, dev_tab_dst, dev_tab_y, dev_tab_x, n_tab, dev_hbar, dev_out, st);
+    return launch_baseline_backward<KIND_DSGPS_MIXED>(g, dev_h, dev_ybar, dev_tab_dst, dev_tab_y, dev_tab_x, n_tab, dev_hbar, dev_out, st);
 }
 
 // record layout of pgrad.cuh for the table builder: {PG_ONE, PG_DEG, PG_C, PG_CN, PG_YB, PG_RHAT, PG_MB, PG_HID, PG_TB, PG_SB, PG_EDGE,

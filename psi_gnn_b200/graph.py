@@ -103,6 +103,20 @@ class NativeGraph:
                                                     int(dst.numel()), N.ptr(out), N.stream_ptr()), "psi_param_grad_tangent")
         return out
 
+    def layer_backward(self, kind: int, h: torch.Tensor, ybar: torch.Tensor):
+        """(h̄, θ̄) of ONE unrolled baseline layer (kinds DSS / DSGPS / mixed DSGPS) at its own input ``h``: ``h̄ = Jᵀȳ`` and the parameter
+        gradient as a flat vector in packed-block layout (weights.unpack_dss_grads / unpack_dsgps_grads) — native, deterministic.
+        The layer's weight block must be resident."""
+        from . import weights as W
+        hs, yb = N.f32(h), N.f32(ybar)
+        dst, ty, tx = W.baseline_grad_table_device(kind, self.device)
+        out = torch.zeros(W.TOTAL_FLOATS, dtype=torch.float32, device=self.device)
+        hbar = torch.zeros_like(hs)
+        with torch.cuda.device(self.device):
+            N.check(N.load().psi_layer_backward(self.handle, kind, N.ptr(hs), N.ptr(yb), N.ptr(dst), N.ptr(ty), N.ptr(tx), int(dst.numel()),
+                                                N.ptr(hbar), N.ptr(out), N.stream_ptr()), "psi_layer_backward")
+        return hbar, out
+
     def residual(self, u: torch.Tensor, y: torch.Tensor, want_vector: bool = False):
         """(mean((A u − y)²), residual vector or None)  — dirichlet/psignn/model.py:157-167."""
         u = N.f32(u.reshape(-1))

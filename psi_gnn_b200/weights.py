@@ -264,6 +264,108 @@ def unpack_psignn_grads(flat: torch.Tensor, names, mixed: bool, f_prefix: str = 
     return {k: out[k] for k in names if k in out}
 
 
+# ---- baselines (csrc/baseline_bwd.cuh): same record layout, other meanings of the node slots ---------------------------------------
+def baseline_grad_table(kind: int):
+    """(dst, ty, tx) of one unrolled DSS (kind 2) / DSGPS (3) / mixed DSGPS (4) layer; record slots as documented in baseline_bwd.cuh:
+    TB = t̄ (DSS) or ā (z gate), MB = α·ȳ (DSS) or b̄ (r gate), YB = ē (correction), HID = Ψ hidden, RHAT = r ⊙ h."""
+    dss, mixed = kind == 2, kind == 4
+    attr = 1 if dss else 3
+    dst, ty, tx = [], [], []
+
+    def add(d, y, x):
+        dst.append(d); ty.append(y); tx.append(x)
+
+    for w, name in enumerate(("to", "from", "neu")[: 3 if mixed else 2]):
+        eb = PG["EDGE"] + 70 * w
+        for o in range(D):
+            for i in range(D):
+                add(OFFSETS[name + ".W1i"] + o * D + i, eb + 20 + o, PG["C"] + i)
+                add(OFFSETS[name + ".W1j"] + o * D + i, PG["ACC"] + 10 * w + o, PG["C"] + i)
+                add(OFFSETS[name + ".W2"] + o * D + i, eb + o, eb + 10 + i)
+            for c in range(attr):
+                add(OFFSETS[name + ".W1a"] + o * 3 + c, eb + 30 + o, eb + 40 + 3 * o + c)
+            add(OFFSETS[name + ".b1"] + o, eb + 20 + o, PG["ONE"])
+            add(OFFSETS[name + ".b2"] + o, eb + o, PG["DEG"] + w)
+    if dss:
+        for o in range(D):
+            for i in range(33):
+                add(OFFSETS["up_W1"] + o * 33 + i, PG["TB"] + o, PG["C"] + i)
+            add(OFFSETS["up_b1"] + o, PG["TB"] + o, PG["ONE"])
+            for i in range(D):
+                add(OFFSETS["up_W2"] + o * D + i, PG["MB"] + o, PG["HID"] + i)
+            add(OFFSETS["up_b2"] + o, PG["MB"] + o, PG["ONE"])
+        return dst, ty, tx
+    width = 33 if mixed else 32
+    for o in range(D):
+        for i in range(width):
+            add(OFFSETS["gz_W"] + o * 33 + i, PG["TB"] + o, PG["C"] + i)
+            add(OFFSETS["gr_W"] + o * 33 + i, PG["MB"] + o, PG["C"] + i)
+            add(OFFSETS["gc_W"] + o * 33 + i, PG["YB"] + o, (PG["RHAT"] + i) if i < D else (PG["C"] + i))
+        add(OFFSETS["gz_b"] + o, PG["TB"] + o, PG["ONE"])
+        add(OFFSETS["gr_b"] + o, PG["MB"] + o, PG["ONE"])
+        add(OFFSETS["gc_b"] + o, PG["YB"] + o, PG["ONE"])
+        if mixed:
+            for i in range(25):
+                add(OFFSETS["un_W1"] + o * 25 + i, PG["TBN"] + o, PG["CN"] + i)
+            add(OFFSETS["un_b1"] + o, PG["TBN"] + o, PG["ONE"])
+            for i in range(D):
+                add(OFFSETS["un_W2"] + o * D + i, PG["MBN"] + o, PG["HIDN"] + i)
+            add(OFFSETS["un_b2"] + o, PG["MBN"] + o, PG["ONE"])
+    return dst, ty, tx
+
+
+def baseline_grad_table_device(kind: int, device):
+    key = ("baseline", int(kind), str(device))
+    if key not in _TABLES:
+        grad_table_device(False, device)            # verifies the record layout against the extension
+        _TABLES[key] = tuple(torch.tensor(t, dtype=torch.int32, device=device) for t in baseline_grad_table(kind))
+    return _TABLES[key]
+
+
+def _field(flat, name, rows=None, width=None, cols=None):
+    off = OFFSETS[name]
+    if rows is None:
+        return flat[off:off + (cols or 1)]
+    return flat[off:off + rows * width].view(rows, width)[:, :cols if cols is not None else width]
+
+
+def _edge_grads(flat, slot, prefix, attr, out):
+    out[prefix + ".0.weight"] = torch.cat([_field(flat, slot + ".W1i", D, D), _field(flat, slot + ".W1j", D, D), _field(flat, slot + ".W1a", D, 3, attr)], dim=1)
+    out[prefix + ".0.bias"] = _field(flat, slot + ".b1", cols=D)
+    out[prefix + ".2.weight"] = _field(flat, slot + ".W2", D, D)
+    out[prefix + ".2.bias"] = _field(flat, slot + ".b2", cols=D)
+
+
+def unpack_dss_grads(flat: torch.Tensor, k: int) -> Dict[str, torch.Tensor]:
+    """inverse of :func:`pack_dss` for a gradient in block layout (the decoder of the block is not a layer parameter)"""
+    out: Dict[str, torch.Tensor] = {}
+    _edge_grads(flat, "to", f"phi_to_list.{k}.mlp.mlp", 1, out)
+    _edge_grads(flat, "from", f"phi_from_list.{k}.mlp.mlp", 1, out)
+    out[f"psi_list.{k}.mlp.mlp.0.weight"] = _field(flat, "up_W1", D, 33)
+    out[f"psi_list.{k}.mlp.mlp.0.bias"] = _field(flat, "up_b1", cols=D)
+    out[f"psi_list.{k}.mlp.mlp.2.weight"] = _field(flat, "up_W2", D, D)
+    out[f"psi_list.{k}.mlp.mlp.2.bias"] = _field(flat, "up_b2", cols=D)
+    return out
+
+
+def unpack_dsgps_grads(flat: torch.Tensor, mixed: bool) -> Dict[str, torch.Tensor]:
+    """inverse of :func:`pack_dsgps` for the recurrent step's parameters"""
+    out: Dict[str, torch.Tensor] = {}
+    width = 33 if mixed else 32
+    _edge_grads(flat, "to", "phi_to.mlp.mlp", 3, out)
+    _edge_grads(flat, "from", "phi_from.mlp.mlp", 3, out)
+    for slot, key in (("gz", "z_k"), ("gr", "r_k"), ("gc", "correction")):
+        out[f"{key}.mlp.0.weight"] = _field(flat, slot + "_W", D, 33, width)
+        out[f"{key}.mlp.0.bias"] = _field(flat, slot + "_b", cols=D)
+    if mixed:
+        _edge_grads(flat, "neu", "phi_neumann.mlp.mlp", 3, out)
+        out["update_neumann.mlp.0.weight"] = _field(flat, "un_W1", D, 25)
+        out["update_neumann.mlp.0.bias"] = _field(flat, "un_b1", cols=D)
+        out["update_neumann.mlp.2.weight"] = _field(flat, "un_W2", D, D)
+        out["update_neumann.mlp.2.bias"] = _field(flat, "un_b2", cols=D)
+    return out
+
+
 def named_tensors(module: torch.nn.Module, prefix: str = "") -> Dict[str, torch.Tensor]:
     """parameters of ``module`` keyed like its ``state_dict`` (optionally under ``prefix``)."""
     return {(prefix + k): v for k, v in module.named_parameters()}
