@@ -156,6 +156,9 @@ int psi_residual(const psi_graph_t* g, const float* dev_u, const float* dev_y, f
                  float* dev_mean_sq, void* stream);
 /* out = A^T v   (used by the backward of the residual loss) */
 int psi_spmv_t(const psi_graph_t* g, const float* dev_v, float* dev_out, void* stream);
+/* flux form of the DSS residual (dirichlet/dss/model.py:137-145: F_bar = a_ij*(u_j-u_i) scatter_added by source row):
+ * out_i = sum_{e=(i->j)} a_e (v_j - v_i); transpose != 0: its adjoint (the backward of the above).  Deterministic. */
+int psi_flux(const psi_graph_t* g, const float* dev_v, float* dev_out, int transpose, void* stream);
 int psi_encode(int64_t num_nodes, const float* dev_x, float* dev_h, void* stream);   /* MLP 1->d->d */
 int psi_decode(int64_t num_nodes, const float* dev_h, float* dev_u, void* stream);   /* MLP d->d->1 */
 

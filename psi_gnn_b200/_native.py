@@ -52,6 +52,7 @@ SIGNATURES = {
     "psi_layer_backward": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "psi_residual": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "psi_spmv_t": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "psi_flux": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "psi_encode": (c_int, [c_int64, c_void_p, c_void_p, c_void_p]),
     "psi_decode": (c_int, [c_int64, c_void_p, c_void_p, c_void_p]),
     "psi_solver_create": (c_int, [POINTER(c_void_p), c_int64, c_int]),

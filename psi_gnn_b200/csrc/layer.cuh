@@ -690,6 +690,41 @@ __global__ void __launch_bounds__(PSI_NODE_BLOCK) k_spmv_t(GraphDev G, const flo
     out[node] = s;
 }
 
+// flux form of the DSS residual (dirichlet/dss/model.py:137-145): out_i = Σ_{e = (i → j)} a_e (v_j − v_i) in CSR order (the reference
+// scatter_adds the per-edge fluxes: float atomics on CUDA).  TRANSPOSE: the adjoint out_j = Σ_{e = (i → j)} a_e v_i − v_j Σ_{e = (j → ·)} a_e.
+template <bool TRANSPOSE>
+__global__ void __launch_bounds__(PSI_NODE_BLOCK) k_flux(GraphDev G, const float* __restrict__ v, float* __restrict__ out) {
+    const int node = blockIdx.x * PSI_NODE_BLOCK + threadIdx.x;
+    if (node >= G.N) return;
+    const float vi = __ldg(v + node);
+    float s = 0.f, t = 0.f;
+    {
+        const SellDev& L = G.Ar;
+        const int64_t base = L.slice_off[node >> 5];
+        const int width = (int)((L.slice_off[(node >> 5) + 1] - base) >> 5);
+        const int2* p = L.recs2 + base + (node & 31);
+        for (int k = 0; k < width; ++k) {
+            const int2 rec = __ldg(p + (int64_t)k * 32);
+            if (rec.x < 0) continue;
+            if (TRANSPOSE) s += __int_as_float(rec.y);
+            else s = fmaf(__int_as_float(rec.y), __ldg(v + rec.x) - vi, s);
+        }
+    }
+    if (TRANSPOSE) {
+        const SellDev& L = G.Ac;
+        const int64_t base = L.slice_off[node >> 5];
+        const int width = (int)((L.slice_off[(node >> 5) + 1] - base) >> 5);
+        const int2* p = L.recs2 + base + (node & 31);
+        for (int k = 0; k < width; ++k) {
+            const int2 rec = __ldg(p + (int64_t)k * 32);
+            if (rec.x >= 0) t = fmaf(__int_as_float(rec.y), __ldg(v + rec.x), t);
+        }
+        out[node] = fmaf(-s, vi, t);
+    } else {
+        out[node] = s;
+    }
+}
+
 // deterministic final reduction of per-block partial sums: out[0] = scale * Σ part
 __global__ void k_reduce_partials(int n, const float* __restrict__ part, float scale, float* __restrict__ out) {
     __shared__ double sm[32];

@@ -699,6 +699,17 @@ extern "C" int psi_spmv_t(const psi_graph_t* g, const float* dev_v, float* dev_o
     return 0;
 }
 
+extern "C" int psi_flux(const psi_graph_t* g, const float* dev_v, float* dev_out, int transpose, void* stream) {
+    if (g == nullptr) PSI_FAIL("psi_flux: null graph");
+    if (g->p_recs_Ar == nullptr || g->p_recs_Ac == nullptr) PSI_FAIL("psi_flux: graph was created without a_ij");
+    if (g->N == 0) return 0;
+    if (dev_v == nullptr || dev_out == nullptr || dev_v == dev_out) PSI_FAIL("psi_flux: null or aliased pointer");
+    if (transpose) k_flux<true><<<node_grid(g->N), PSI_NODE_BLOCK, 0, as_stream(stream)>>>(g->dev, dev_v, dev_out);
+    else k_flux<false><<<node_grid(g->N), PSI_NODE_BLOCK, 0, as_stream(stream)>>>(g->dev, dev_v, dev_out);
+    PSI_CK_LAUNCH();
+    return 0;
+}
+
 extern "C" int psi_encode(int64_t num_nodes, const float* dev_x, float* dev_h, void* stream) {
     if (num_nodes < 0) PSI_FAIL("psi_encode: negative size");
     if (num_nodes == 0) return 0;

@@ -134,6 +134,14 @@ class NativeGraph:
             N.check(N.load().psi_spmv_t(self.handle, N.ptr(v), N.ptr(out), N.stream_ptr()), "psi_spmv_t")
         return out
 
+    def flux(self, v: torch.Tensor, transpose: bool = False) -> torch.Tensor:
+        """Σ_{e=(i→j)} a_e (v_j − v_i) per source row i (DSS flux-form residual, dirichlet/dss/model.py:137-145), or its adjoint"""
+        v = N.f32(v.reshape(-1))
+        out = torch.empty_like(v)
+        with torch.cuda.device(self.device):
+            N.check(N.load().psi_flux(self.handle, N.ptr(v), N.ptr(out), 1 if transpose else 0, N.stream_ptr()), "psi_flux")
+        return out
+
     def solver(self, threshold: int):
         """the solver workspace for this graph's size, taken from a process-wide pool keyed by (device, numel): batches of
         a data loader have a few distinct sizes, and re-allocating GBs of U/V history per batch would dominate the step"""

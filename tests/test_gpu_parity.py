@@ -747,6 +747,24 @@ def test_baseline_layer_backward_matches_autograd(name):
         assert float((grads[k_].double().cpu() - r).norm()) <= 1e-4 * float(r.norm()) + 1e-6 * float(want.norm()), k_
 
 
+def test_dss_flux_residual_native_matches_torch():
+    """DSS flux-form residual (reference dirichlet/dss/model.py:129-148): the native edge sums (psi_flux, forward and adjoint) against
+    the reference-signature torch form — value and gradient w.r.t. U; bit-equal on a second call (no atomics)"""
+    g, m, b = _baseline("dss_ckpt")
+    gen = torch.Generator().manual_seed(5)
+    U = torch.randn(b.num_nodes, 1, generator=gen).to(DEV).requires_grad_()
+    a = m._residual_native(U, b)
+    (ga,) = torch.autograd.grad(a, U)
+    U2 = U.detach().clone().requires_grad_()
+    r = m.residual_loss(U2.double(), b.edge_index, b.a_ij.double(), b.b_prime.double())
+    (gr,) = torch.autograd.grad(r, U2)
+    assert abs(a.item() - r.item()) <= 1e-6 * abs(r.item())
+    assert rel_err(ga, gr) <= TOL
+    a2 = m._residual_native(U, b)
+    (ga2,) = torch.autograd.grad(a2, U)
+    assert torch.equal(a, a2) and torch.equal(ga, ga2)
+
+
 class _TorchBackwardLayer(torch.autograd.Function):
     """test double of baselines._UnrolledLayer: the same native forward, but the backward is torch autograd through the differentiable
     torch form of the step, recomputed at the saved input — the reference's backward evaluated at the native path's own states"""
