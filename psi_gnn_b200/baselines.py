@@ -63,15 +63,14 @@ def _decode(h):
 class _UnrolledLayer(autograd.Function):
     """one unrolled step ``H_{k+1} = layer_k(H_k)`` of a baseline: forward = the fused layer kernel with the step's weight block,
     backward = ``psi_layer_backward`` (Jᵀȳ and (∂f/∂θ)ᵀȳ in one call) + the gradient to ``h0`` (the clamped Dirichlet rows copy it).
-    ``owner`` is the model (``_layer_kind``, ``_layer_block``, ``_layer_names``, ``_layer_unpack``), ``params`` the step's parameters
-    in the order of ``owner._layer_names(step)``.  The weight block is looked up again in backward because another step's block may
-    occupy the constant bank by then."""
+    ``owner`` is the model (``_layer_kind``, ``_layer_names``, ``_layer_unpack``), ``block`` the step's (packed weight block, bank key)
+    from ``owner._layer_block``, ``params`` the step's parameters in the order of ``owner._layer_names(step)``."""
 
     @staticmethod
-    def forward(ctx, owner, batch, step, dmask, h, h0, *params):
+    def forward(ctx, owner, batch, step, block, dmask, h, h0, *params):
         g = graph_of(batch, owner._layer_kind)
-        W.upload(*owner._layer_block(step, h.device))
-        ctx.owner, ctx.g, ctx.step, ctx.dmask = owner, g, step, dmask
+        W.upload(*block)
+        ctx.owner, ctx.g, ctx.step, ctx.block, ctx.dmask = owner, g, step, block, dmask
         ctx.save_for_backward(h)
         return g.layer_forward(owner._layer_kind, h.detach(), h0.detach() if h0 is not None else None)
 
@@ -79,12 +78,12 @@ class _UnrolledLayer(autograd.Function):
     def backward(ctx, ybar):
         (h,) = ctx.saved_tensors
         owner = ctx.owner
-        W.upload(*owner._layer_block(ctx.step, h.device))
+        W.upload(*ctx.block)                 # the forward's own packed block: another step's block may occupy the constant bank by now
         ybar = ybar.contiguous()
         hbar, flat = ctx.g.layer_backward(owner._layer_kind, h.detach(), ybar)
         grads = owner._layer_unpack(flat, ctx.step)
-        h0bar = torch.where(ctx.dmask, ybar, torch.zeros_like(ybar)) if (ctx.dmask is not None and ctx.needs_input_grad[5]) else None
-        return (None, None, None, None, hbar, h0bar) + tuple(grads[n].clone() for n in owner._layer_names(ctx.step))
+        h0bar = torch.where(ctx.dmask, ybar, torch.zeros_like(ybar)) if (ctx.dmask is not None and ctx.needs_input_grad[6]) else None
+        return (None, None, None, None, None, hbar, h0bar) + tuple(grads[n].clone() for n in owner._layer_names(ctx.step))
 
 
 class _Flux(autograd.Function):
@@ -176,9 +175,11 @@ class DeepStatisticalSolver(nn.Module):
         if cfg["latent_dim"] != W.D:
             raise NotImplementedError("psi_gnn_b200: the fused kernel is built for latent_dim=10")
         P = dict(self.named_parameters())
+        serial, blobs = self._packed(batch.x.device)        # packed once per forward (the pack cache is keyed by every parameter's version)
         for update in range(cfg["k"]):
             h = H[str(update)]
-            H[str(update + 1)] = _UnrolledLayer.apply(self, batch, update, None, h, None, *[P[n] for n in self._layer_names(update)])
+            H[str(update + 1)] = _UnrolledLayer.apply(self, batch, update, (blobs[update], (serial, update)), None, h, None,
+                                                      *[P[n] for n in self._layer_names(update)])
             U[str(update + 1)] = self.decoder_list[update](H[str(update + 1)])
             cumul_res[str(update + 1)] = self._residual_native(U[str(update + 1)], batch)
             cumul_mse[str(update + 1)] = self.mse_loss(U[str(update + 1)], batch.x)
@@ -233,7 +234,9 @@ class ModelDSGPS(nn.Module):
         return self.KIND
 
     def _layer_names(self, step):
-        return list(W.unpack_dsgps_grads(torch.zeros(W.TOTAL_FLOATS), self.KIND == N.KIND_DSGPS_MIXED))
+        if getattr(self, "_names", None) is None:
+            self._names = list(W.unpack_dsgps_grads(torch.zeros(W.TOTAL_FLOATS), self.KIND == N.KIND_DSGPS_MIXED))
+        return self._names
 
     def _layer_unpack(self, flat, step):
         return W.unpack_dsgps_grads(flat, self.KIND == N.KIND_DSGPS_MIXED)
@@ -307,9 +310,10 @@ class ModelDSGPS(nn.Module):
             raise NotImplementedError("psi_gnn_b200: the fused kernel is built for latent_dim=10")
         P = dict(self.named_parameters())
         names = self._layer_names(0)
+        block = self._layer_block(0, batch.edge_index.device)
         for update in range(cfg["k"]):
             key = str(update + 1)
-            H[key] = _UnrolledLayer.apply(self, batch, update, dmask, H[str(update)], H['0'], *[P[n] for n in names])
+            H[key] = _UnrolledLayer.apply(self, batch, update, block, dmask, H[str(update)], H['0'], *[P[n] for n in names])
             U[key] = dec(H[key])
             cumul_res[key] = self.residual_loss(U[key], batch)
             cumul_mse[key] = self.mse_loss(U[key], batch.sol)

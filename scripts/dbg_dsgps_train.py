@@ -44,17 +44,17 @@ Un = grads.U
 class TorchLayer:
     """route _UnrolledLayer through the differentiable torch step"""
     @staticmethod
-    def apply(owner, batch, step, dmask, h, h0, *params):
+    def apply(owner, batch, step, block, dmask, h, h0, *params):
         return TorchLayer.model._step_torch(step, h, h0, TorchLayer.batch)
 
 
 class HybridLayer(torch.autograd.Function):
     """native forward, torch-autograd backward of the same step recomputed at the saved input"""
     @staticmethod
-    def forward(ctx, owner, batch, step, dmask, h, h0, *params):
+    def forward(ctx, owner, batch, step, block, dmask, h, h0, *params):
         from psi_gnn_b200 import weights as W
         from psi_gnn_b200.graph import graph_of
-        W.upload(*owner._layer_block(step, h.device))
+        W.upload(*block)
         ctx.save_for_backward(h, h0)
         ctx.step, ctx.names = step, owner._layer_names(step)
         return graph_of(batch, owner._layer_kind).layer_forward(owner._layer_kind, h.detach(), h0.detach())
@@ -69,7 +69,7 @@ class HybridLayer(torch.autograd.Function):
             h0_ = h0.detach().requires_grad_()
             out = mm._step_torch(ctx.step, h_, h0_, bb)
             gr = torch.autograd.grad(out, [h_, h0_] + [P[n] for n in ctx.names], ybar, allow_unused=True)
-        return (None,) * 4 + tuple(gr)
+        return (None,) * 5 + tuple(gr)
 
 
 orig = B._UnrolledLayer

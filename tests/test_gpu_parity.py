@@ -770,10 +770,10 @@ class _TorchBackwardLayer(torch.autograd.Function):
     torch form of the step, recomputed at the saved input — the reference's backward evaluated at the native path's own states"""
 
     @staticmethod
-    def forward(ctx, owner, batch, step, dmask, h, h0, *params):
+    def forward(ctx, owner, batch, step, block, dmask, h, h0, *params):
         from psi_gnn_b200 import weights as W
         from psi_gnn_b200.graph import graph_of
-        W.upload(*owner._layer_block(step, h.device))
+        W.upload(*block)
         ctx.owner, ctx.batch, ctx.step, ctx.has_h0 = owner, batch, step, h0 is not None
         ctx.save_for_backward(h, h0 if h0 is not None else h)
         return graph_of(batch, owner._layer_kind).layer_forward(owner._layer_kind, h.detach(), h0.detach() if h0 is not None else None)
@@ -787,7 +787,7 @@ class _TorchBackwardLayer(torch.autograd.Function):
             h_, h0_ = h.detach().requires_grad_(), h0.detach().requires_grad_()
             out = owner._step_torch(ctx.step, h_, h0_ if ctx.has_h0 else None, ctx.batch)
             gr = torch.autograd.grad(out, [h_] + ([h0_] if ctx.has_h0 else []) + [P[n] for n in owner._layer_names(ctx.step)], ybar, allow_unused=True)
-        return (None,) * 4 + ((gr[0], gr[1]) + tuple(gr[2:]) if ctx.has_h0 else (gr[0], None) + tuple(gr[1:]))
+        return (None,) * 5 + ((gr[0], gr[1]) + tuple(gr[2:]) if ctx.has_h0 else (gr[0], None) + tuple(gr[1:]))
 
 
 # band of the whole-step gradient against the reference's own fp32 run.  An unrolled baseline takes ~2.4 M ReLU decisions per training
