@@ -686,6 +686,62 @@ def test_dsgps_mixed_inference_and_layer_match_reference():
     assert torch.equal(out[t[:, 1] == 1], g.t("layer_h0", DEV)[t[:, 1] == 1])       # Dirichlet rows are copied
 
 
+def _baseline_step_oracle(name, P, hh, h0, bc, alpha, k=3):
+    """one unrolled step of a baseline in the oracle's torch form (fp64 when its inputs are): DSS layer k, DSGPS step, mixed DSGPS step
+    (reference dirichlet/dss/model.py:83-91, dirichlet/dsgps/model.py:143-163, mixed/dsgps/model.py:76-97)"""
+    from oracle import psignn_oracle as O
+    if name.startswith("dss"):
+        return O.dss_layer(P, k, hh, bc, alpha)
+    if "mixed" not in name:
+        return O.dsgps_layer(P, hh, h0, bc)
+    ei, attr = O.offdiag(bc.edge_index, bc.edge_attr)
+    to, fr, ne = (O.phi(P, p_, hh, ei, attr, t_) for p_, t_ in (("phi_to", True), ("phi_from", False), ("phi_neumann", False)))
+    c = torch.cat([hh, to, fr, bc.prb_data], 1)
+    zg, rg = torch.sigmoid(O._lin(P, "z_k.mlp.0", c)), torch.sigmoid(O._lin(P, "r_k.mlp.0", c))
+    corr = torch.tanh(O._lin(P, "correction.mlp.0", torch.cat([rg * hh, to, fr, bc.prb_data], 1)))
+    upd = O.mlp2(P, "update_neumann.mlp", torch.cat([hh, ne, bc.prb_data, bc.unit_normal_vector], 1))
+    out = torch.where((bc.tags[:, 2] == 1)[:, None], upd, hh + zg * corr)
+    return torch.where((bc.tags[:, 1] == 1)[:, None], h0, out)
+
+
+@pytest.mark.parametrize("name", ["dss_ckpt", "dsgps_ckpt", "dsgps_mixed_ckpt"])
+@pytest.mark.parametrize("seed,n", [(0, 33), (2, 257), (3, 1000)])
+def test_random_ragged_graphs_baseline_backward(name, seed, n):
+    """psi_layer_forward / psi_layer_backward of the baseline kinds on randomised ragged multigraphs (isolated nodes, a hub of degree
+    n/3, self loops, duplicate and asymmetric edges, every boundary class) against the oracle's fp64 step and autograd through it"""
+    from psi_gnn_b200 import _native as N, weights as W
+    from psi_gnn_b200.graph import graph_of
+    g, m, _ = _baseline(name)
+    mixed = "mixed" in name
+    b, h, h0, y = _random_graph(seed, n, mixed, "cpu")
+    if name.startswith("dss"):
+        gen = torch.Generator().manual_seed(100 + seed)
+        b.a_ij_norm = torch.randn(b.edge_index.shape[1], 1, generator=gen)
+        b.b_prime_norm = torch.randn(n, 3, generator=gen)
+        b.b_prime = torch.randn(n, 3, generator=gen)
+        kind, k = N.KIND_DSS, 3
+        block, unpack = m._layer_block(k, DEV), (lambda flat: W.unpack_dss_grads(flat, k))
+    else:
+        kind = N.KIND_DSGPS_MIXED if mixed else N.KIND_DSGPS
+        block, unpack = m._layer_block(0, DEV), (lambda flat: W.unpack_dsgps_grads(flat, mixed))
+    P = {k_: v.double().requires_grad_() for k_, v in g.params().items()}
+    hh = h.double().requires_grad_()
+    out = _baseline_step_oracle(name, P, hh, h0.double(), b.double(), m.config["alpha"])
+    bd = b.to(DEV)
+    gr = graph_of(bd, kind)
+    W.upload(*block)
+    f_native = gr.layer_forward(kind, h.to(DEV), None if kind == N.KIND_DSS else h0.to(DEV))
+    assert rel_err(f_native, out.detach()) <= TOL
+    hbar, flat = gr.layer_backward(kind, h.to(DEV), y.to(DEV))
+    grads = unpack(flat)
+    names = list(grads)
+    ref = torch.autograd.grad(out, [hh] + [P[k_] for k_ in names], y.double(), allow_unused=True)
+    assert rel_err(hbar, ref[0]) <= TOL, rel_err(hbar, ref[0])
+    got = torch.cat([grads[k_].reshape(-1).double().cpu() for k_ in names])
+    want = torch.cat([(r if r is not None else torch.zeros_like(P[k_])).reshape(-1) for k_, r in zip(names, ref[1:])])
+    assert float((got - want).norm() / want.norm()) <= TOL, float((got - want).norm() / want.norm())
+
+
 @pytest.mark.parametrize("name", ["dss_ckpt", "dsgps_ckpt", "dsgps_mixed_ckpt"])
 def test_baseline_layer_backward_matches_autograd(name):
     """psi_layer_backward (one unrolled DSS / DSGPS / mixed DSGPS step: h̄ = Jᵀȳ and every parameter gradient) through the C ABI
