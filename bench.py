@@ -33,6 +33,9 @@ WORKLOADS = {
                                     "synthetic ~500-node 2D triangle Poisson meshes per GPU"),
     "c2": ("dss", 32, 0.075, "C2 (BASELINE configs[1]): DSS baseline inference (30 unrolled layers with per-layer weights on the shared fused layer kernel), "
                               "batch of 32 synthetic ~500-node meshes per GPU, shipped DSS checkpoint"),
+    "c2train": ("dss", 32, 0.075, "C2-train (SURVEY §8 row f-4): DSS baseline TRAINING step (30 unrolled layers with per-layer decoders and flux-residual losses; "
+                                   "every layer = native fused forward + native layer backward psi_layer_backward), batch of 32 synthetic ~500-node meshes "
+                                   "per GPU, shipped DSS checkpoint"),
     "c1": ("dirichlet", 32, 0.075, "C1: PSI-GNN dirichlet training step, batch of 32 synthetic ~500-node 2D triangle Poisson meshes"),
     "c3": ("dirichlet", 256, 0.075, "C3: PSI-GNN dirichlet training step (Broyden forward + implicit-adjoint backward), batch 256 synthetic ~500-node meshes per GPU"),
     "c5": ("dirichlet", 1, 0.075, "C5: PSI-GNN dirichlet forward Broyden solve (500-step cap) of ONE synthetic 1M-node mesh, node-range partitioned "
@@ -162,7 +165,7 @@ def run_native(args):
     family, n_graphs, h, desc = WORKLOADS[args.workload]
     if args.workload in ("c5", "c0"):
         return run_native_inference(args, rank, local, world, dev)
-    if args.workload == "c2":
+    if args.workload in ("c2", "c2train"):
         return run_native_dss(args, rank, local, world, dev)
     if args.graphs:
         n_graphs = args.graphs
@@ -538,6 +541,9 @@ def run_native_inference(args, rank, local, world, dev, emit_line=True, min_warm
         dist.destroy_process_group()
 
 
+DSS_TRAIN_METRIC = "DSS baseline training-step graphs/s (30 unrolled layers with per-layer losses, forward + backward)"
+
+
 def load_dss():
     z = np.load(os.path.join(ROOT, "tests", "golden", "dss_ckpt.npz"))
     P = {k[6:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("param.")}
@@ -558,22 +564,37 @@ def run_native_dss(args, rank, local, world, dev):
     P, cfg = load_dss()
     model = M.DeepStatisticalSolver(cfg)
     model.load_state_dict(P)
-    model = model.to(dev).eval()
+    train = args.workload == "c2train"
+    if train:
+        desc = WORKLOADS["c2train"][3]
+    model = model.to(dev)
+    model = model.train() if train else model.eval()
     host = dss_batch(n_graphs, h, rank * n_graphs).pin_memory()
     dev_batch = host.to(dev)
     flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)
     N, nnz = host.num_nodes, int(host.edge_index.shape[1])
     warm = max(args.warmup, MIN_WARMUP)
+
+    def train_step(batch):
+        # forward (30 native layer launches + per-layer decoders and flux residuals) and backward (30 × psi_layer_backward)
+        model.zero_grad(set_to_none=True)
+        _, ld = model(batch)
+        ld["train_loss"].backward()
+        return ld["train_loss"].detach()
+
+    step_fn = (lambda: train_step(dev_batch)) if train else (lambda: model.inference(dev_batch))
     for _ in range(warm):
-        model.inference(dev_batch)
+        step_fn()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     # per-launch time of the layer kernel: CUDA events around the 30 layer launches of each step (the decode is outside the bracket)
-    ms_total = _timed_steps(lambda: model.inference(dev_batch), args.steps, world, dev, flush)
+    ms_total = _timed_steps(step_fn, args.steps, world, dev, flush)
     clocks = sampler.stop() if rank == 0 else None
 
     def e2e():
+        if train:
+            return train_step(host.to(dev, non_blocking=True)).cpu()
         return model.inference(host.to(dev, non_blocking=True)).cpu()
 
     e2e()
@@ -589,19 +610,22 @@ def run_native_dss(args, rank, local, world, dev):
     per_launch_us = 1e3 * ms_total / args.steps / k                         # upper bound: includes the weight upload and launch gaps
     achieved = alg / (per_launch_us * 1e-6) / 1e9
     sec = ms_total / 1e3
-    out = {"metric": "DSS baseline inference graphs/s (30 layers on the shared fused layer kernel)",
+    out = {"metric": DSS_TRAIN_METRIC if train else "DSS baseline inference graphs/s (30 layers on the shared fused layer kernel)",
            "value": round(world * n_graphs * args.steps / sec, 2), "unit": "graphs/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
            "ms_per_step": round(ms_total / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
            "data": "synthetic P1-FEM Poisson meshes in the DSS reader's layout; weights = reference shipped DSS checkpoint",
            "config": dss_config(desc, n_graphs, host, k),
            "edge_msg_updates_per_s": round(world * k * 2 * nnz * args.steps / sec, 1),
-           "gpu_launches": args.steps * (k + 1),
+           # training: per layer pre-pass + layer (forward), 2 × k_bl_pass + k_bl_gather + k_pgrad_reduce (backward), k_flux forward and adjoint
+           "gpu_launches": args.steps * (k * 8 + 2) if train else args.steps * (k + 1),
            "e2e": {"value": round(world * n_graphs * args.steps / (ms_e2e / 1e3), 2), "unit": "graphs/s", "ms_per_step": round(ms_e2e / args.steps, 3),
-                   "h2d_bytes_per_step": host.nbytes(), "d2h_bytes_per_step": 4 * N},
+                   "h2d_bytes_per_step": host.nbytes(), "d2h_bytes_per_step": 4 if train else 4 * N},
            "roofline": {"bound": "hbm", "kernel": "k_layer_forward<DSS>", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                         "frac": round(achieved / peak, 4), "traffic": None, "avg_launch_us": round(per_launch_us, 2), "alg_bytes_per_launch": alg,
-                        "note": "latency-bound at this size: 16 k nodes are a fraction of one wave; time per launch includes the 12.7 KB weight-block "
-                                "upload and the launch gap"},
+                        "note": ("training step: host-bound (30 unrolled layers x [layer kernels + torch decoder/loss block]); 'avg_launch_us' is the step time "
+                                 "per unrolled layer, not a kernel duration" if train else
+                                 "latency-bound at this size: 16 k nodes are a fraction of one wave; time per launch includes the 12.7 KB weight-block "
+                                 "upload and the launch gap")},
            "clocks": clocks}
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
@@ -658,6 +682,32 @@ def cpu_sample(args):
     """(step function, sample batch, graphs per step, description, config of the FULL workload) of the bounded CPU sample"""
     family, n_graphs, h, desc = WORKLOADS[args.workload]
     n_graphs = args.graphs or n_graphs
+    if args.workload == "c2train":
+        from oracle import psignn_oracle as O
+        P, cfg = load_dss()
+        P = {k_: v.clone().requires_grad_() for k_, v in P.items()}
+        batch = dss_batch(n_graphs, h, 0)
+        frm, to = batch.edge_index
+        y = batch.b_prime
+
+        def step():
+            # the reference's unrolled training forward + backward (dirichlet/dss/model.py:59-104, :129-148) with the oracle's layer
+            for v in P.values():
+                v.grad = None
+            H = torch.zeros(batch.num_nodes, cfg["latent_dim"])
+            total = None
+            for k_ in range(cfg["k"]):
+                H = O.dss_layer(P, k_, H, batch, cfg["alpha"])
+                U = O.mlp2(P, "decoder_list.%d.mlp.mlp" % k_, H)
+                p1 = (1 - y[:, 1:2]) * (-y[:, 0:1]) + y[:, 1:2] * (U - y[:, 2:3])
+                flux = torch.zeros_like(U).index_add(0, frm, batch.a_ij.reshape(-1, 1) * (U[to] - U[frm]))
+                term = torch.mean((p1 + flux) ** 2) * cfg["gamma"] ** (cfg["k"] - k_ - 1)
+                total = term if total is None else total + term
+            total.backward()
+            return cfg["k"], cfg["k"]
+
+        return (step, batch, n_graphs, "one DSS training step (30 unrolled layers, forward + backward) of the full batch of %d meshes (N=%d nodes)"
+                % (n_graphs, batch.num_nodes), dss_config(WORKLOADS["c2train"][3], n_graphs, batch, cfg["k"]))
     if args.workload == "c2":
         from oracle import psignn_oracle as O
         P, cfg = load_dss()
@@ -746,7 +796,7 @@ def run_reference(args):
         one = round(sample / t1[0], 4)
     sample_txt = ("each step = %s; oracle port of the reference (the Python reference needs PyG/torch_sparse and cannot travel to the "
                   "GPU box); %d warm-up + %d timed steps, median step %.3f s" % (what, warm, args.steps, med))
-    metric = {"c2": "DSS baseline inference graphs/s (30 layers on the shared fused layer kernel)",
+    metric = {"c2": "DSS baseline inference graphs/s (30 layers on the shared fused layer kernel)", "c2train": DSS_TRAIN_METRIC,
               "c5": "PSI-GNN solve graphs/s (forward Broyden solve of one large mesh)", "c0": "PSI-GNN solve graphs/s (forward Broyden solve, inference)"}.get(
         args.workload, "PSI-GNN solve graphs/s (training step: Broyden forward solve + implicit-adjoint backward solve)")
     out = {"impl": "reference", "metric": metric,
@@ -754,7 +804,7 @@ def run_reference(args):
            "ms_per_step": round(1e3 * dt / args.steps, 2), "higher_is_better": True,
            "scaling": "strong" if args.workload == "c5" else "weak", "vs_baseline": None, "dtype": "f32",
            "data": ("synthetic P1-FEM Poisson mesh (seeded generator); weights = reference shipped checkpoint" if args.workload in ("c0", "c5") else
-                    "synthetic P1-FEM Poisson meshes in the DSS reader's layout; weights = reference shipped DSS checkpoint" if args.workload == "c2" else
+                    "synthetic P1-FEM Poisson meshes in the DSS reader's layout; weights = reference shipped DSS checkpoint" if args.workload in ("c2", "c2train") else
                     "synthetic P1-FEM Poisson meshes (seeded generator); weights = reference shipped checkpoint"),
            "config": config,
            "iterations_per_s": round(its / dt, 2),

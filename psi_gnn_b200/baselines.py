@@ -83,7 +83,8 @@ class _UnrolledLayer(autograd.Function):
         hbar, flat = ctx.g.layer_backward(owner._layer_kind, h.detach(), ybar)
         grads = owner._layer_unpack(flat, ctx.step)
         h0bar = torch.where(ctx.dmask, ybar, torch.zeros_like(ybar)) if (ctx.dmask is not None and ctx.needs_input_grad[6]) else None
-        return (None, None, None, None, None, hbar, h0bar) + tuple(grads[n].clone() for n in owner._layer_names(ctx.step))
+        # views into `flat` (a fresh tensor per call): AccumulateGrad copies them into the parameters' .grad
+        return (None, None, None, None, None, hbar, h0bar) + tuple(grads[n] for n in owner._layer_names(ctx.step))
 
 
 class _Flux(autograd.Function):
@@ -131,7 +132,10 @@ class DeepStatisticalSolver(nn.Module):
         return blobs[k], (serial, k)
 
     def _layer_names(self, k):
-        return [f"{m}.{k}.mlp.mlp.{i}.{w}" for m in ("phi_to_list", "phi_from_list", "psi_list") for i in (0, 2) for w in ("weight", "bias")]
+        cache = self.__dict__.setdefault("_names", {})
+        if k not in cache:
+            cache[k] = [f"{m}.{k}.mlp.mlp.{i}.{w}" for m in ("phi_to_list", "phi_from_list", "psi_list") for i in (0, 2) for w in ("weight", "bias")]
+        return cache[k]
 
     def _layer_unpack(self, flat, k):
         return W.unpack_dss_grads(flat, k)
