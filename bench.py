@@ -687,22 +687,12 @@ def cpu_sample(args):
         P, cfg = load_dss()
         P = {k_: v.clone().requires_grad_() for k_, v in P.items()}
         batch = dss_batch(n_graphs, h, 0)
-        frm, to = batch.edge_index
-        y = batch.b_prime
 
         def step():
-            # the reference's unrolled training forward + backward (dirichlet/dss/model.py:59-104, :129-148) with the oracle's layer
+            # the reference's unrolled training forward + backward (dirichlet/dss/model.py:59-104, :129-148) as restated by the oracle
             for v in P.values():
                 v.grad = None
-            H = torch.zeros(batch.num_nodes, cfg["latent_dim"])
-            total = None
-            for k_ in range(cfg["k"]):
-                H = O.dss_layer(P, k_, H, batch, cfg["alpha"])
-                U = O.mlp2(P, "decoder_list.%d.mlp.mlp" % k_, H)
-                p1 = (1 - y[:, 1:2]) * (-y[:, 0:1]) + y[:, 1:2] * (U - y[:, 2:3])
-                flux = torch.zeros_like(U).index_add(0, frm, batch.a_ij.reshape(-1, 1) * (U[to] - U[frm]))
-                term = torch.mean((p1 + flux) ** 2) * cfg["gamma"] ** (cfg["k"] - k_ - 1)
-                total = term if total is None else total + term
+            total, _, _ = O.dss_training_forward(P, batch, cfg["k"], cfg["alpha"], cfg["gamma"])
             total.backward()
             return cfg["k"], cfg["k"]
 

@@ -151,6 +151,73 @@ def dsgps_inference(P: Params, batch, k_steps: int) -> Tensor:
     return decoder(P, H)
 
 
+def dsgps_layer_mixed(P: Params, H: Tensor, H0: Tensor, batch) -> Tensor:
+    """One mixed-boundary DSGPS step (mixed/dsgps/model.py:76-97): interior GRU-style update, Neumann rows overwritten by
+    ``update_neumann(cat[H, ΣΦ_neumann, prb, n̂])``, Dirichlet rows (tags[:,1]) copied from ``H0`` — in that order."""
+    ei, attr = offdiag(batch.edge_index, batch.edge_attr)
+    to = phi(P, "phi_to", H, ei, attr, True)
+    fr = phi(P, "phi_from", H, ei, attr, False)
+    ne = phi(P, "phi_neumann", H, ei, attr, False)
+    c = torch.cat([H, to, fr, batch.prb_data], 1)
+    z = torch.sigmoid(_lin(P, "z_k.mlp.0", c))
+    r = torch.sigmoid(_lin(P, "r_k.mlp.0", c))
+    corr = torch.tanh(_lin(P, "correction.mlp.0", torch.cat([r * H, to, fr, batch.prb_data], 1)))
+    upd = mlp2(P, "update_neumann.mlp", torch.cat([H, ne, batch.prb_data, batch.unit_normal_vector], 1))
+    Hn = torch.where((batch.tags[:, 2] == 1)[:, None], upd, H + z * corr)
+    return torch.where((batch.tags[:, 1] == 1)[:, None], H0, Hn)
+
+
+def dss_flux_residual(U: Tensor, batch) -> Tensor:
+    """flux-form residual of DSS (dirichlet/dss/model.py:129-148): mean((p1 + Σ_{e=(i→j)} a_e (u_j − u_i))²)"""
+    frm, to = batch.edge_index[0], batch.edge_index[1]
+    y = batch.b_prime
+    p1 = (1 - y[:, 1:2]) * (-y[:, 0:1]) + y[:, 1:2] * (U - y[:, 2:3])
+    flux = torch.zeros_like(U).index_add(0, frm, batch.a_ij.reshape(-1, 1) * (U[to] - U[frm]))
+    return torch.mean((p1 + flux) ** 2)
+
+
+def dss_training_forward(P: Params, batch, k_layers: int, alpha: float, gamma: float, latent_dim: int = 10):
+    """``DeepStatisticalSolver.forward`` (dirichlet/dss/model.py:59-104): k unrolled layers from H = 0, per-layer decoders, the flux
+    residual of every state weighted by gamma^(k−1−layer).  Returns (train_loss, U_last, residual of the last state)."""
+    H = torch.zeros(batch.num_nodes, latent_dim, dtype=batch.a_ij.dtype)
+    total = None
+    for k in range(k_layers):
+        H = dss_layer(P, k, H, batch, alpha)
+        U = mlp2(P, f"decoder_list.{k}.mlp.mlp", H)
+        res = dss_flux_residual(U, batch)
+        term = res * gamma ** (k_layers - k - 1)
+        total = term if total is None else total + term
+    return total, U, res
+
+
+def dsgps_training_forward(P: Params, batch, k_steps: int, gamma: float, mixed: bool = False):
+    """``ModelDSGPS.forward`` (dirichlet/dsgps/model.py:48-131, mixed/dsgps/model.py:48-131): k recurrent steps from H0 = encoder(x);
+    per step the residual of the decoded state weighted by gamma^(k−1−step) plus an encoder and an autoencoder loss.  The dirichlet
+    reference freezes the decoder (resp. encoder) PARAMETERS for those two losses (the states keep their graph); the mixed reference
+    detaches the STATES instead.  Returns (train_loss, U_last, residual of the last state)."""
+    enc_keys = [k for k in P if k.startswith("autoencoder.encoder.")]
+    dec_keys = [k for k in P if k.startswith("autoencoder.decoder.")]
+    P_dec_frozen = {**P, **{k: P[k].detach() for k in dec_keys}}
+    P_enc_frozen = {**P, **{k: P[k].detach() for k in enc_keys}}
+    H0 = encoder(P, batch.x)
+    H = H0
+    total = None
+    for step in range(k_steps):
+        H = dsgps_layer_mixed(P, H, H0, batch) if mixed else dsgps_layer(P, H, H0, batch)
+        U = decoder(P, H)
+        res = residual_loss(U, batch)
+        if mixed:
+            u_d, h_d = U.detach(), H.detach()
+            l_enc = F.mse_loss(encoder(P, u_d), h_d)
+            l_auto = F.mse_loss(decoder(P, encoder(P, u_d).detach()), u_d)
+        else:
+            l_enc = F.mse_loss(encoder(P_dec_frozen, decoder(P_dec_frozen, H)), H)          # autoencoder(H, sens="latent")
+            l_auto = F.mse_loss(decoder(P_enc_frozen, encoder(P_enc_frozen, U)), U)         # autoencoder(U, sens="physics")
+        term = res * gamma ** (k_steps - step - 1) + l_enc + l_auto
+        total = term if total is None else total + term
+    return total, U, res
+
+
 def encoder(P: Params, x: Tensor) -> Tensor:
     """MLP 1→d→d (model.py:370-378)."""
     return mlp2(P, "autoencoder.encoder.mlp.mlp", x)
