@@ -284,6 +284,35 @@ __device__ __forceinline__ void walk_list(const SellDev& L, const float* __restr
 #endif
 }
 
+// Sub-wave grids (a few hundred CTAs: C0/C1/C2-size batches): the separate pre-pass launch costs more (≈ 4–6 µs of launch + latency)
+// than recomputing Q_j = W1j·h_j per edge in a kernel that has one warp per scheduler and nothing to hide latency with.  Same record
+// walk, but every lane gathers the neighbour's 40-byte row of h itself and forms Q with the canonical chain edge_q2 — the values, and
+// therefore the results, are bit-identical to the pre-pass path.  `want` = false: the lane does not aggregate over this list (row 0).
+template <int WHICH, class Body>
+__device__ __forceinline__ void walk_direct_h(const int4* __restrict__ recs, int width, const float* __restrict__ h, int lane, bool want, Body&& body) {
+    const int4* p = recs + lane;
+    int t = 0;
+    for (; t + 1 < width; t += 2) {
+        const int4 r0 = __ldg(p + 32 * t), r1 = __ldg(p + 32 * (t + 1));
+        float h0[PSI_D], h1[PSI_D];
+        load_row(h, (want && r0.x >= 0) ? r0.x : 0, h0);
+        load_row(h, (want && r1.x >= 0) ? r1.x : 0, h1);
+        f2 q0[PSI_D / 2], q1[PSI_D / 2];
+        edge_q2<WHICH>(h0, q0);
+        edge_q2<WHICH>(h1, q1);
+        body(r0, q0);
+        body(r1, q1);
+    }
+    if (t < width) {
+        const int4 r0 = __ldg(p + 32 * t);
+        float h0[PSI_D];
+        load_row(h, (want && r0.x >= 0) ? r0.x : 0, h0);
+        f2 q0[PSI_D / 2];
+        edge_q2<WHICH>(h0, q0);
+        body(r0, q0);
+    }
+}
+
 __device__ __forceinline__ float sigmoidf_acc(float s) { return 1.0f / (1.0f + expf(-s)); }
 
 // LayerNorm over the 10 latent channels, eps 1e-5, biased variance (nn.LayerNorm, model.py:270,293).
@@ -401,7 +430,7 @@ __device__ __forceinline__ int node_class(const GraphDev& G, int node, int limit
 // Aggregated messages of one node: mT = ΣΦ→ (interior), mF = ΣΦ← (interior) or ΣΦ_neumann (Neumann rows).  WARP-UNIFORM.
 // Lanes that do not aggregate over a list (Dirichlet rows, Neumann rows over list T, rows beyond the produced range) run the same
 // instructions on row 0 and discard the result.  Padding records contribute relu(NaN) = 0 to S and nothing to deg.
-template <int KIND>
+template <int KIND, bool NOPRE = false>
 __device__ __forceinline__ void aggregate(const GraphDev& G, const float* __restrict__ h, const float* __restrict__ Q, int node, int cls,
                                           WarpStage& st, const CoopMap& M, float (&mT)[PSI_D], float (&mF)[PSI_D]) {
     constexpr int ATTR = KindTraits<KIND>::ATTR;
@@ -428,13 +457,17 @@ __device__ __forceinline__ void aggregate(const GraphDev& G, const float* __rest
         load_row(h, node, hi);                   // re-read per list instead of held across the walks (register pressure)
         edge_pre2<0>(hi, P);
     }
-    walk_list(G.T, Q, slice, lane, st, M,
-              [&](int j) { return cls == 0 ? j : 0; },
-              [&](const int4& rec, const f2 (&q)[PSI_D / 2]) {
-                  f2 z[PSI_D / 2];
-                  edge_z2<0, ATTR>(P, q, rec, z);
-                  relu_acc(rec, z);
-              });
+    auto body_T = [&](const int4& rec, const f2 (&q)[PSI_D / 2]) {
+        f2 z[PSI_D / 2];
+        edge_z2<0, ATTR>(P, q, rec, z);
+        relu_acc(rec, z);
+    };
+    if (NOPRE) {
+        const int64_t base = G.T.slice_off[slice];
+        walk_direct_h<0>(G.T.recs + base, (int)((G.T.slice_off[slice + 1] - base) >> 5), h, lane, cls == 0, body_T);
+    } else {
+        walk_list(G.T, Q, slice, lane, st, M, [&](int j) { return cls == 0 ? j : 0; }, body_T);
+    }
     unpack10(S, Sf);
     if (cls == 0) edge_post<0>(Sf, deg, mT);
     asm volatile("" ::: "memory");               // keep the compiler from carrying the first read of the row across the walk
@@ -461,13 +494,17 @@ __device__ __forceinline__ void aggregate(const GraphDev& G, const float* __rest
                       relu_acc(rec, z);
                   });
     } else {
-        walk_list(G.F, Q, slice, lane, st, M,
-                  [&](int j) { return cls == 0 ? N + j : 0; },
-                  [&](const int4& rec, const f2 (&q)[PSI_D / 2]) {
-                      f2 z[PSI_D / 2];
-                      edge_z2<1, ATTR>(P, q, rec, z);
-                      relu_acc(rec, z);
-                  });
+        auto body_F = [&](const int4& rec, const f2 (&q)[PSI_D / 2]) {
+            f2 z[PSI_D / 2];
+            edge_z2<1, ATTR>(P, q, rec, z);
+            relu_acc(rec, z);
+        };
+        if (NOPRE) {
+            const int64_t base = G.F.slice_off[slice];
+            walk_direct_h<1>(G.F.recs + base, (int)((G.F.slice_off[slice + 1] - base) >> 5), h, lane, cls == 0, body_F);
+        } else {
+            walk_list(G.F, Q, slice, lane, st, M, [&](int j) { return cls == 0 ? N + j : 0; }, body_F);
+        }
     }
     unpack10(S, Sf);
     if (cls == 0) edge_post<1>(Sf, deg, mF);
@@ -585,7 +622,7 @@ __device__ __forceinline__ void solver_epilogue(const SolverEpi& E, int node, bo
     }
 }
 
-template <int KIND, bool EPI>
+template <int KIND, bool EPI, bool NOPRE = false>
 __global__ void __launch_bounds__(PSI_NODE_BLOCK, PSI_OP_MIN_CTAS)
 k_layer_forward(GraphDev G, const float* __restrict__ h, const float* __restrict__ h0, const float* __restrict__ Q, float* __restrict__ out,
                 SolverEpi E) {
@@ -606,7 +643,8 @@ k_layer_forward(GraphDev G, const float* __restrict__ h, const float* __restrict
         float mT[PSI_D], mF[PSI_D];
 #pragma unroll
         for (int o = 0; o < PSI_D; ++o) { mT[o] = 0.f; mF[o] = 0.f; }
-        aggregate<KIND>(G, h, Q, node, cls, stage[threadIdx.x >> 5], M, mT, mF);
+        static_assert(!(NOPRE && KindTraits<KIND>::has_neumann), "the fused per-edge product exists for the kinds without a Neumann edge MLP");
+        aggregate<KIND, NOPRE>(G, h, Q, node, cls, stage[threadIdx.x >> 5], M, mT, mF);
         if (valid) {
             load_row(h, node, hi);
             node_update<KIND>(G, h0, node, cls, hi, mT, mF, fx);

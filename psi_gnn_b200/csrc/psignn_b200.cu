@@ -371,7 +371,20 @@ static int graph_q(const psi_graph* cg, cudaStream_t st, float** q) {
     return 0;
 }
 
+// grids of at most two CTAs per SM (C0 / C1 / C2-size batches): the operator is latency-bound, one launch less is worth more than the
+// per-edge recomputation of W1j·h_j costs (layer.cuh walk_direct_h; bit-identical results)
+static inline bool small_grid(unsigned grid) {
+    static const bool off = getenv("PSI_NO_FUSED_PRE") != nullptr;              // A/B switch
+    return !off && grid <= 2u * PSI_NUM_SMS_B200;
+}
+
+static inline bool fused_pre(const psi_graph* g, int kind) {
+    const bool mixed = (kind == PSI_KIND_MIXED || kind == PSI_KIND_DSGPS_MIXED);
+    return !mixed && g->part == nullptr && small_grid(node_grid(g->dev.n_compute));
+}
+
 // one application of the layer = pre-pass (per-source half of the first edge layer) + fused gather/update kernel: 2 launches
+// (1 launch on small grids for the kinds without a Neumann edge MLP)
 template <bool EPI>
 static int launch_layer(const psi_graph* g, int kind, const float* h, const float* h0, float* out, SolverEpi E, cudaStream_t st) {
     if (g->dev.n_compute == 0) return 0;
@@ -380,6 +393,15 @@ static int launch_layer(const psi_graph* g, int kind, const float* h, const floa
     const unsigned grid = node_grid(g->dev.n_compute);
     const unsigned pre_grid = node_grid(g->N);           // every row that can be a message source (owned + ghost rows)
     const bool mixed = (kind == PSI_KIND_MIXED || kind == PSI_KIND_DSGPS_MIXED);
+    if (fused_pre(g, kind)) {
+        switch (kind) {
+            case PSI_KIND_DIRICHLET: k_layer_forward<KIND_DIRICHLET, EPI, true><<<grid, PSI_NODE_BLOCK, 0, st>>>(g->dev, h, h0, Q, out, E); break;
+            case PSI_KIND_DSS:       k_layer_forward<KIND_DSS, EPI, true><<<grid, PSI_NODE_BLOCK, 0, st>>>(g->dev, h, h0, Q, out, E); break;
+            default:                 k_layer_forward<KIND_DSGPS, EPI, true><<<grid, PSI_NODE_BLOCK, 0, st>>>(g->dev, h, h0, Q, out, E); break;
+        }
+        PSI_CK_LAUNCH();
+        return 0;
+    }
     if (mixed) k_layer_pre<3><<<pre_grid, PSI_NODE_BLOCK, 0, st>>>((int)g->N, h, Q, E.done);
     else k_layer_pre<2><<<pre_grid, PSI_NODE_BLOCK, 0, st>>>((int)g->N, h, Q, E.done);
     switch (kind) {
@@ -1128,7 +1150,7 @@ static int op_eval(psi_solver* s, psi_graph* g, int kind, int op, const float* a
     if (g->part != nullptr && op == PSI_OP_LAYER && halo_refresh(g, s->x, 0, &s->ctrl->done, st)) return -1;
     prof_begin(s, step, 0, s->op_bytes, st);
     if (op == PSI_OP_LAYER) {
-        s->launches += 2;
+        s->launches += fused_pre(g, kind) ? 1 : 2;
         rc = launch_layer<true>(g, kind, s->x, aux, out, E, st);
     } else {
         s->launches += 2;

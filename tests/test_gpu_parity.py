@@ -1124,6 +1124,45 @@ def test_random_ragged_graphs_layer_and_vjp(mixed, seed, n):
     assert abs(r.item() - float(ref_r)) <= 1e-5 * float(ref_r)
 
 
+def test_fused_per_edge_product_is_bit_identical_to_the_prepass(tmp_path):
+    """sub-wave grids run the layer without the pre-pass launch (W1j·h_j recomputed per edge with the same rounding chain,
+    layer.cuh walk_direct_h); PSI_NO_FUSED_PRE=1 restores the two-launch path.  Both must give the same bits: layer application
+    (dirichlet, DSS, DSGPS) and a whole forward solve (trace and result)."""
+    import os
+    import subprocess
+    import sys
+    from conftest import ROOT
+    script = tmp_path / "run.py"
+    script.write_text(
+        "import sys, os, torch\n"
+        "sys.path.insert(0, %r); sys.path.insert(0, os.path.join(%r, 'tests'))\n"
+        "import test_gpu_parity as T\n"
+        "from conftest import Golden\n"
+        "from psi_gnn_b200 import _native as N, weights as W\n"
+        "from psi_gnn_b200.graph import graph_of\n"
+        "out = {}\n"
+        "g = Golden('dirichlet_ckpt'); m = g.model('cuda:0'); b = g.batch('cuda:0')\n"
+        "with torch.no_grad():\n"
+        "    h0 = m._encode_native(b.x); out['psi'] = m.deqdss.f(h0, h0, b).cpu()\n"
+        "    r = m.deqdss.inference(h0, b); out['solve'] = r['result'].cpu(); out['trace'] = torch.tensor(r['rel_trace'])\n"
+        "for name, kind in (('dss_ckpt', N.KIND_DSS), ('dsgps_ckpt', N.KIND_DSGPS)):\n"
+        "    g2, m2, b2 = T._baseline(name)\n"
+        "    W.upload(*m2._layer_block(3, 'cuda:0'))\n"
+        "    gen = torch.Generator().manual_seed(1); h = torch.randn(b2.num_nodes, 10, generator=gen).cuda(); hh0 = torch.randn(b2.num_nodes, 10, generator=gen).cuda()\n"
+        "    out[name] = graph_of(b2, kind).layer_forward(kind, h, None if kind == N.KIND_DSS else hh0).cpu()\n"
+        "torch.save(out, sys.argv[1])\n" % (ROOT, ROOT))
+    outs = []
+    for tag, env in (("fused", {}), ("prepass", {"PSI_NO_FUSED_PRE": "1"})):
+        path = tmp_path / (tag + ".pt")
+        e = dict(os.environ)
+        e.pop("PSI_NO_FUSED_PRE", None)
+        e.update(env)
+        subprocess.run([sys.executable, str(script), str(path)], check=True, env=e, timeout=300)
+        outs.append(torch.load(path))
+    for k in outs[0]:
+        assert torch.equal(outs[0][k], outs[1][k]), k
+
+
 def test_node_permutation_equivariance():
     """relabelling the nodes permutes the output rows (the re-layout is independent of the input ordering)"""
     g = Golden("dirichlet_ckpt")
